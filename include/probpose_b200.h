@@ -1,0 +1,199 @@
+/*
+ * probpose_b200.h -- C ABI of the B200-native ProbPose heatmap hot path.
+ *
+ * The reference (zir-vision/ProbPose_pytorch) is pure Python and has no FFI;
+ * the "interface each entry point replaces" is therefore the Python call the
+ * reference makes at the cited file:line.  The Python shims in
+ * probpose_pytorch_b200/ keep those call signatures and bind these symbols
+ * with ctypes (see INTEGRATION.md for the binding a reference maintainer adds).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer
+ *     unless its name ends in _host;
+ *   - the library never allocates, frees or owns caller memory, never
+ *     synchronises the stream and keeps no mutable global state besides a
+ *     thread-local last-error string and per-function attribute caching;
+ *   - every function returns pp_status (0 = ok, negative = error) and never
+ *     throws; pp_last_error_string() describes the last failure of the
+ *     calling thread;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - heatmaps are dense row-major (B, K, H, W); "N" below means B*K heatmaps.
+ */
+#ifndef PROBPOSE_B200_H_
+#define PROBPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+#define PP_MAX_OKS_RADIUS 9   /* ceil(3 * 3.0): s is clipped to [0.55, 3.0] (heatmap.py:178-179) */
+#define PP_OKS_TAPS (2 * PP_MAX_OKS_RADIUS + 1)
+#define PP_MAX_BLUR_KSIZE 31
+
+#if defined(__GNUC__)
+#define PP_API __attribute__((visibility("default")))
+#else
+#define PP_API
+#endif
+
+typedef void* pp_stream_t;
+
+typedef enum pp_status {
+  PP_OK = 0,
+  PP_ERR_INVALID_ARG = -1,
+  PP_ERR_UNSUPPORTED_SHAPE = -2,
+  PP_ERR_CUDA = -3,
+  PP_ERR_SCRATCH = -4
+} pp_status;
+
+typedef enum pp_dtype { PP_F32 = 0, PP_BF16 = 1, PP_F64 = 2 } pp_dtype;
+
+/* ---- library ---------------------------------------------------------- */
+PP_API int pp_version(void);
+PP_API const char* pp_last_error_string(void);
+/* number of SMs and opt-in shared memory per block of the current device */
+PP_API int pp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin_bytes);
+
+/* ---- encode: generate_probmaps (codec.py:11-70) + ProbMap.encode /
+ *      ArgMaxProbMap.encode flags (codec.py:138-212, 443-513) ------------- */
+typedef struct pp_encode_params {
+  int32_t B, K, H, W;
+  int32_t heatmap_dtype;   /* PP_F32 | PP_BF16: dtype of the maps written */
+  int32_t keypoint_dtype;  /* PP_F32 | PP_F64: dtype of `keypoints`; the division by the codec
+                              scale factor is done in that dtype, as NumPy does (codec.py:180) */
+  int32_t keypoint_dim;    /* trailing dimension D of keypoints (>= 2) */
+  float scale_x, scale_y;  /* codec scale_factor = (input-1)/(heatmap-1), float32 (codec.py:131-133);
+                              1.0f when keypoints are already in heatmap space */
+  float input_w, input_h;  /* for in_image (codec.py:189-200) */
+} pp_encode_params;
+
+PP_API int pp_encode(const pp_encode_params* p,
+              const void* keypoints,     /* (B, K, D) input-image space */
+              const float* visible,      /* (B, K) keypoints_visible; NULL = all ones */
+              const double* two_s,       /* (K) 2*s per keypoint: the divisor of codec.py:65 */
+              void* heatmaps,            /* out (B, K, H, W) */
+              float* keypoint_weights,   /* out (B, K) or NULL (codec.py:46,68) */
+              uint8_t* in_image,         /* out (B, K) or NULL */
+              uint8_t* annotated,        /* out (B, K) or NULL (codec.py:187) */
+              pp_stream_t stream);
+
+/* ---- per-codec constant table for the expected-OKS decoder:
+ *      _prepare_oks_kernels (heatmap.py:170-194), built once on the host ---- */
+typedef struct pp_oks_table {
+  const int32_t* radius;    /* (K) ceil(3 s) in [1, PP_MAX_OKS_RADIUS] */
+  const float* taps_f32;    /* (K, PP_OKS_TAPS) normalised 1-D taps, tap j at column j (j < 2r+1) */
+  const double* kernel2d;   /* (K, PP_OKS_TAPS*PP_OKS_TAPS) the reference's normalised d x d kernel,
+                               packed row-major with row stride d = 2r+1 */
+} pp_oks_table;
+
+typedef struct pp_decode_params {
+  int32_t B, K, H, W;
+  int32_t heatmap_dtype;   /* PP_F32 | PP_BF16 */
+  int32_t apply_tail;      /* 1: decode clamp(x / temperature, 0, 1) (head.py:526-532) instead of x */
+  float temperature;
+  double input_w, input_h; /* keypoints = locs / [W-1, H-1] * input_size (codec.py:237, 541) */
+} pp_decode_params;
+
+/* get_heatmap_expected_value (heatmap.py:291-395) + ProbMap.decode scaling (codec.py:214-239).
+ * conv_out != NULL additionally returns the OKS-convolved maps (return_heatmap=True). */
+PP_API int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* table,
+                       const void* heatmaps,
+                       float* locs,        /* out (N, 2) sub-pixel argmax, heatmap px */
+                       float* vals,        /* out (N) unconvolved map at the integer argmax */
+                       int32_t* argmax,    /* out (N) flat index y*W+x of the convolved maximum, or NULL */
+                       double* keypoints,  /* out (N, 2) input-space coordinates, or NULL */
+                       float* conv_out,    /* out (N, H, W) or NULL */
+                       pp_stream_t stream);
+
+/* Number of floats of `conv_out` work space pp_decode_expected needs for this shape even when the
+ * caller does not want the convolved maps (maps too large for the shared-memory kernel); 0 otherwise. */
+PP_API int64_t pp_decode_expected_workspace_floats(const pp_decode_params* p);
+
+/* get_heatmap_maximum (heatmap.py:13-52) */
+PP_API int pp_heatmap_maximum(const void* heatmaps, int32_t heatmap_dtype, int64_t N, int32_t H, int32_t W,
+                       float* locs,       /* out (N, 2); (-1,-1) where max <= 0 */
+                       float* vals,       /* out (N) */
+                       int32_t* argmax,   /* out (N) or NULL */
+                       pp_stream_t stream);
+
+/* ArgMaxProbMap.decode (codec.py:515-543): argmax + gaussian_blur (codec.py:284-313) +
+ * refine_keypoints_dark_udp (codec.py:315-375) + scaling. */
+PP_API int pp_decode_argmax_dark(const pp_decode_params* p,
+                          const float* blur_taps, int32_t blur_ksize, /* (ksize) float32 taps, odd ksize */
+                          const void* heatmaps,
+                          float* peaks,       /* out (N, 2) integer peaks (or -1) or NULL */
+                          float* scores,      /* out (N) raw maxima */
+                          float* refined,     /* out (N, 2) refined heatmap-space coordinates */
+                          double* keypoints,  /* out (N, 2) input-space coordinates, or NULL */
+                          pp_stream_t stream);
+
+/* head tail (head.py:526-532, normalize=None): y = clamp(x / temperature, 0, 1) */
+PP_API int pp_heatmap_tail(const void* x, void* y, int32_t dtype, int64_t numel, float temperature, pp_stream_t stream);
+
+/* ---- OKSHeatmapLoss.forward (loss.py:55-143) and its backward ---------- */
+typedef enum pp_loss_mode {
+  PP_LOSS_PIXEL_MEAN = 0, /* mean over B*K*H*W of the per-pixel loss: what ProbPoseLoss uses (loss.py:428-431) */
+  PP_LOSS_PER_PIXEL = 1,  /* (B, K, H, W) map (loss.py:122-127) */
+  PP_LOSS_PER_KEYPOINT = 2 /* (B, K) (loss.py:128-134); the default mode is its mean (loss.py:135-141) */
+} pp_loss_mode;
+
+typedef struct pp_loss_params {
+  int32_t B, K, H, W;
+  int32_t dtype;               /* PP_F32 | PP_BF16: output, target, pixel weights, mask, loss map, grad */
+  int32_t mode;                /* pp_loss_mode */
+  int32_t oks_type;            /* 0 minus, 1 plus, 2 both (loss.py:92-99) */
+  int32_t skip_empty_channel;  /* loss.py:180-189 */
+  double smoothing_weight, gaussian_weight, loss_weight; /* the reference's Python floats */
+  int64_t mask_stride_b, mask_stride_k; /* element strides of `mask` over B and K (0 = broadcast) */
+} pp_loss_params;
+
+/* bytes of caller-provided scratch needed by the loss entry points */
+PP_API int64_t pp_oks_loss_scratch_bytes(const pp_loss_params* p);
+
+/* Forward.  Outputs by mode:
+ *   PIXEL_MEAN   : loss_scalar[0] (float32).  If grad != NULL the backward is fused into the same
+ *                  pass: grad = d loss / d output * grad_scale (grad_scale is a host float, 1.0f for
+ *                  a plain backward()).
+ *   PER_PIXEL    : loss_map (B,K,H,W) in `dtype`.
+ *   PER_KEYPOINT : loss_kpt (B,K) float32, loss_scalar[0] = mean(loss_kpt), peak_index (B,K) int32 =
+ *                  flat index of the maximum masked Sobel energy (needed by the backward).
+ * target_out_of_range (device int32, or NULL) is set to 1 when some target value is outside [0, 1]
+ * -- the condition the reference asserts on (loss.py:85-86) -- and to 0 otherwise, in the same pass.
+ */
+PP_API int pp_oks_loss_forward(const pp_loss_params* p,
+                        const void* output, const void* target,
+                        const float* keypoint_weights, /* (B,K) or NULL */
+                        const void* pixel_weights,     /* (B,K,H,W) in `dtype` or NULL */
+                        const void* mask,              /* strided (B,K|1,H,W) in `dtype` or NULL */
+                        void* loss_map, float* loss_kpt, float* loss_scalar, int32_t* peak_index,
+                        void* grad, float grad_scale,
+                        int32_t* target_out_of_range,
+                        void* scratch, int64_t scratch_bytes, pp_stream_t stream);
+
+typedef enum pp_upstream_kind {
+  PP_UPSTREAM_SCALAR = 0, /* one float32 on the device, broadcast over the forward's output
+                             (d L / d loss for PIXEL_MEAN; an expanded gradient for the other modes) */
+  PP_UPSTREAM_FULL = 1    /* PER_PIXEL: (B,K,H,W) in `dtype`; PER_KEYPOINT: (B,K) float32 */
+} pp_upstream_kind;
+
+/* Backward for an arbitrary upstream gradient; peak_index (from the forward) is required for
+ * PER_KEYPOINT. */
+PP_API int pp_oks_loss_backward(const pp_loss_params* p,
+                         const void* output, const void* target,
+                         const float* keypoint_weights, const void* pixel_weights, const void* mask,
+                         const void* upstream, int32_t upstream_kind, const int32_t* peak_index,
+                         void* grad,
+                         void* scratch, int64_t scratch_bytes, pp_stream_t stream);
+
+/* grad *= scale[0] unless scale[0] == 1 (device scalar): lets the fused PIXEL_MEAN gradient be
+ * reused by autograd without a host sync; a no-op launch in the usual case. */
+PP_API int pp_scale_inplace(void* data, int32_t dtype, int64_t numel, const float* scale_dev, pp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROBPOSE_B200_H_ */

@@ -1,0 +1,76 @@
+"""Build the C-ABI CUDA library in-tree: ``python -m probpose_pytorch_b200.build``.
+
+nvcc cross-compiles for sm_100a without a GPU.  The resulting
+``csrc/libprobpose_b200.so`` has no dependency on torch or Python (cudart is
+linked statically) and is git-ignored but travels to the GPU box with the tree.
+"""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB = CSRC / "libprobpose_b200.so"
+SOURCES = ["pp_api.cu", "pp_encode.cu", "pp_decode.cu", "pp_loss.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(cand).exists():
+        raise RuntimeError("nvcc not found: cannot build libprobpose_b200.so")
+    return cand
+
+
+def _stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + [CSRC.parents[1] / "include" / "probpose_b200.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a and link ``libprobpose_b200.so``."""
+    if not force and not _stale():
+        return LIB
+    nvcc = _nvcc()
+    objdir = CSRC / "build"
+    objdir.mkdir(exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = objdir / (Path(src).stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for src, obj, pr in procs:
+        out, _ = pr.communicate()
+        if verbose or pr.returncode:
+            sys.stderr.write(out)
+        if pr.returncode:
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(str(obj))
+    tmp = LIB.with_suffix(".so.tmp")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+            "-Xcompiler", "-fPIC", "-o", str(tmp), *objs]
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("link of libprobpose_b200.so failed")
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,93 @@
+// Library-level entry points of the C ABI: version, error string, device info.
+#include <cstdarg>
+#include <cstdio>
+
+#include "pp_common.cuh"
+
+namespace {
+thread_local char g_error[512] = "";
+}
+
+void pp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+struct DevInfo {
+  int sm_count = 0, major = 0, minor = 0;
+  int64_t smem_optin = 0;
+  bool ok = false;
+};
+// one slot per device ordinal; written once (benign race: same values)
+DevInfo g_dev[64];
+
+const DevInfo* dev_info() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  DevInfo& d = g_dev[dev];
+  if (!d.ok) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return nullptr;
+    d.sm_count = v;
+    cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    d.smem_optin = v;
+    d.ok = true;
+  }
+  return &d;
+}
+}  // namespace
+
+int pp_sm_count() {
+  const DevInfo* d = dev_info();
+  return d ? d->sm_count : 148;
+}
+int64_t pp_smem_optin() {
+  const DevInfo* d = dev_info();
+  return d ? d->smem_optin : 227 * 1024;
+}
+
+int pp_configure_kernel(const void* kernel, int threads, size_t smem, int* ctas_per_sm) {
+  struct Entry { const void* fn; int dev, threads; size_t smem; int per_sm; };
+  static thread_local Entry cache[32];
+  static thread_local int used = 0;
+  int dev = 0;
+  PP_CUDA_OK(cudaGetDevice(&dev));
+  for (int i = 0; i < used; ++i) {
+    const Entry& e = cache[i];
+    if (e.fn == kernel && e.dev == dev && e.threads == threads && e.smem == smem) {
+      *ctas_per_sm = e.per_sm;
+      return PP_OK;
+    }
+  }
+  if (smem > 48 * 1024)
+    PP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  PP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  PP_REQUIRE(per_sm >= 1, PP_ERR_UNSUPPORTED_SHAPE, "kernel does not fit on an SM (threads=%d, smem=%zu)", threads, smem);
+  if (used < 32) cache[used++] = Entry{kernel, dev, threads, smem, per_sm};
+  *ctas_per_sm = per_sm;
+  return PP_OK;
+}
+
+extern "C" {
+
+int pp_version(void) { return PP_ABI_VERSION; }
+
+const char* pp_last_error_string(void) { return g_error; }
+
+int pp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin_bytes) {
+  const DevInfo* d = dev_info();
+  PP_REQUIRE(d != nullptr, PP_ERR_CUDA, "pp_device_info: no usable CUDA device");
+  if (sm_count) *sm_count = d->sm_count;
+  if (cc_major) *cc_major = d->major;
+  if (cc_minor) *cc_minor = d->minor;
+  if (smem_optin_bytes) *smem_optin_bytes = d->smem_optin;
+  return PP_OK;
+}
+
+}  // extern "C"

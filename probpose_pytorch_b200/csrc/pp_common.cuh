@@ -1,0 +1,137 @@
+// Shared device/host helpers for the ProbPose B200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/probpose_b200.h"
+
+// ---------------------------------------------------------------------------
+// host side: error reporting
+// ---------------------------------------------------------------------------
+void pp_set_error(const char* fmt, ...);
+
+#define PP_CUDA_OK(expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      pp_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PP_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define PP_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      pp_set_error(__VA_ARGS__);     \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+int pp_sm_count();            // SMs of the current device (cached per device)
+int64_t pp_smem_optin();      // opt-in dynamic shared memory per block
+
+// Opt the kernel in to `smem` bytes of dynamic shared memory and report how many CTAs of `threads`
+// threads fit per SM.  Cached per (kernel, device, threads, smem) in thread-local storage.
+int pp_configure_kernel(const void* kernel, int threads, size_t smem, int* ctas_per_sm);
+
+static inline bool pp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------
+namespace pp {
+
+constexpr int kWarp = 32;
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int kVec = 4;  // elements per 128-bit access
+  __device__ static __forceinline__ float to_f32(float v) { return v; }
+  __device__ static __forceinline__ float from_f32(float v) { return v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int kVec = 8;
+  __device__ static __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __forceinline__ __nv_bfloat16 from_f32(float v) { return __float2bfloat16_rn(v); }
+};
+
+// 128-bit streaming load (read once: do not allocate in L1) and store.
+__device__ __forceinline__ uint4 ldg_stream_128(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_128(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// Unpack one 128-bit word into kVec floats / pack kVec floats into one 128-bit word.
+__device__ __forceinline__ void unpack(const uint4& w, float (&f)[4], float) {
+  f[0] = __uint_as_float(w.x); f[1] = __uint_as_float(w.y);
+  f[2] = __uint_as_float(w.z); f[3] = __uint_as_float(w.w);
+}
+__device__ __forceinline__ void unpack(const uint4& w, float (&f)[8], __nv_bfloat16) {
+  const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // bf16 -> f32 is a 16-bit shift
+    f[2 * i] = __uint_as_float(u[i] << 16);
+    f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack(const float (&f)[4], float) {
+  return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+__device__ __forceinline__ uint4 pack(const float (&f)[8], __nv_bfloat16) {
+  uint32_t u[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    u[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(u[0], u[1], u[2], u[3]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// (value, index) max with lowest index on ties -- NumPy argmax semantics.
+__device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int oi) {
+  if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    argmax_combine(v, i, ov, oi);
+  }
+}
+
+// scipy.ndimage 'reflect' (half-sample symmetric: d c b a | a b c d | d c b a), any offset.
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  if (i >= 0 && i < n) return i;
+  const int period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - 1 - i;
+}
+
+}  // namespace pp

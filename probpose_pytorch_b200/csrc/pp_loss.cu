@@ -1,0 +1,350 @@
+// OKS heatmap loss (reference: OKSHeatmapLoss.forward/_get_mask, loss.py:55-191) forward and backward.
+//
+//   per pixel:  e   = gx^2 + gy^2            gx, gy = 3x3 Sobel cross-correlations of `output`, zero 'same' pad
+//               oks = out (1 - tgt) | (1 - out) tgt | their mean        (loss.py:92-99)
+//               mse = (out - tgt)^2                                     (loss.py:103)
+//               l   = (w_s e m + w_o oks m + w_g mse m) * loss_weight   (loss.py:112-127, 143)
+//   d l / d out = U m (w_o d oks + 2 w_g (out - tgt)) lw  -  Sx * (2 c gx)  -  Sy * (2 c gy),   c = lw w_s U m
+//   (the adjoint of a zero-padded cross-correlation with Sx is a cross-correlation with flip(Sx) = -Sx).
+//
+// General kernel (this file): one CTA owns one heatmap; `output` is staged once into a zero-bordered
+// shared plane, P = 2 c gx and Q = 2 c gy go to two more planes, and the gradient is the 3x3 adjoint
+// stencil over them.  Supports every mode / weight / mask combination of the reference.
+#include <algorithm>
+
+#include "pp_common.cuh"
+
+namespace {
+
+using namespace pp;
+
+constexpr int kLossThreads = 256;
+
+// upstream gradient: a scalar (host value and/or one device float) broadcast over the forward's output, or a full tensor
+enum Upstream : int { kUpScalar = 0, kUpPerPixel = 2, kUpPerKeypoint = 3 };
+
+struct LossArgs {
+  pp_loss_params p;
+  const void* output;
+  const void* target;
+  const float* kp_weights;
+  const void* pix_weights;
+  const void* mask;
+  void* loss_map;
+  float* loss_kpt;
+  int32_t* peak_out;
+  double* partials;       // (N) per-heatmap sum of the per-pixel loss
+  void* grad;
+  int upstream_kind;
+  float host_scale;
+  const void* upstream;
+  const int32_t* peak_in;
+  int32_t* range_flag;
+};
+
+__device__ __forceinline__ float oks_term(int type, float o, float t) {
+  const float minus = __fmul_rn(o, __fsub_rn(1.0f, t));
+  if (type == 0) return minus;
+  const float plus = __fmul_rn(__fsub_rn(1.0f, o), t);
+  if (type == 1) return plus;
+  return __fdiv_rn(__fadd_rn(minus, plus), 2.0f);
+}
+__device__ __forceinline__ float oks_term_grad(int type, float t) {
+  return type == 0 ? (1.0f - t) : type == 1 ? -t : 0.5f * (1.0f - 2.0f * t);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLossThreads)
+oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red_f[8];
+  __shared__ double red_d[3][8];
+  __shared__ int red_i[8];
+
+  const pp_loss_params& p = a.p;
+  const int H = p.H, W = p.W, HW = H * W, S = W + 2;
+  const int plane = (H + 2) * S;
+  float* A = smem;
+  float* P = A + plane;
+  float* Q = P + plane;
+  const int64_t N = static_cast<int64_t>(p.B) * p.K;
+  const T* out = static_cast<const T*>(a.output);
+  const T* tgt = static_cast<const T*>(a.target);
+  const T* pixw = static_cast<const T*>(a.pix_weights);
+  const T* mask = static_cast<const T*>(a.mask);
+  // loss.py:118-120: Python-float arithmetic, rounded to float32 when it meets the tensor
+  const float w_s = static_cast<float>(p.smoothing_weight), w_g = static_cast<float>(p.gaussian_weight);
+  const float w_o = static_cast<float>(1.0 - p.smoothing_weight - p.gaussian_weight);
+  const float lw = static_cast<float>(p.loss_weight);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // zero borders once; interiors are rewritten per heatmap
+  for (int i = threadIdx.x; i < (want_grad ? 3 : 1) * plane; i += kLossThreads) smem[i] = 0.0f;
+  __syncthreads();
+
+  int bad_target = 0;
+  for (int64_t hm = blockIdx.x; hm < N; hm += gridDim.x) {
+    const int b = static_cast<int>(hm / p.K), k = static_cast<int>(hm % p.K);
+    const T* o_ptr = out + hm * HW;
+    const T* t_ptr = tgt + hm * HW;
+    const T* m_ptr = mask ? mask + b * p.mask_stride_b + k * p.mask_stride_k : nullptr;
+    const T* pw_ptr = pixw ? pixw + hm * HW : nullptr;
+
+    float m_k = a.kp_weights ? a.kp_weights[hm] : 1.0f;
+    if (p.skip_empty_channel) {  // (target != 0).any() per channel, loss.py:180-183
+      int nz = 0;
+      for (int i = threadIdx.x; i < HW; i += kLossThreads) nz |= (Elem<T>::to_f32(t_ptr[i]) != 0.0f);
+      nz = __syncthreads_or(nz);
+      if (!nz) m_k = 0.0f;
+    }
+
+    for (int i = threadIdx.x; i < HW; i += kLossThreads) {
+      const int y = i / W, x = i - y * W;
+      A[(y + 1) * S + x + 1] = Elem<T>::to_f32(o_ptr[i]);
+    }
+    __syncthreads();
+
+    // upstream coefficient shared by the whole heatmap
+    float u_k = 1.0f;
+    int peak = -1;
+    if (want_grad) {
+      if (a.upstream_kind == kUpScalar) {
+        u_k = a.host_scale;
+        if (a.upstream) u_k *= static_cast<const float*>(a.upstream)[0];
+        if (p.mode == PP_LOSS_PIXEL_MEAN) u_k /= static_cast<float>(N * HW);
+      } else if (a.upstream_kind == kUpPerKeypoint) {
+        u_k = static_cast<const float*>(a.upstream)[hm];
+      }
+      if (p.mode == PP_LOSS_PER_KEYPOINT) peak = a.peak_in[hm];
+    }
+
+    double sum_l = 0.0, sum_oks = 0.0, sum_mse = 0.0;
+    float max_e = -INFINITY;
+    int max_i = 0x7fffffff;
+
+    for (int i = threadIdx.x; i < HW; i += kLossThreads) {
+      const int y = i / W, x = i - y * W;
+      const float* c = A + (y + 1) * S + x + 1;
+      const float o = c[0];
+      const float t = Elem<T>::to_f32(t_ptr[i]);
+      // Sobel cross-correlations (loss.py:106-109)
+      const float gx = (c[-S - 1] - c[-S + 1]) + 2.0f * (c[-1] - c[1]) + (c[S - 1] - c[S + 1]);
+      const float gy = (c[-S - 1] + 2.0f * c[-S] + c[-S + 1]) - (c[S - 1] + 2.0f * c[S] + c[S + 1]);
+      float m = m_k;
+      if (pw_ptr) m *= Elem<T>::to_f32(pw_ptr[i]);
+      if (m_ptr) m *= Elem<T>::to_f32(m_ptr[i]);
+
+      if (want_fwd) {
+        bad_target |= !(t >= 0.0f && t <= 1.0f);
+        const float e = __fmul_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), m);
+        const float ok = __fmul_rn(oks_term(p.oks_type, o, t), m);
+        const float d = __fsub_rn(o, t);
+        const float ms = __fmul_rn(__fmul_rn(d, d), m);
+        if (p.mode == PP_LOSS_PER_KEYPOINT) {
+          sum_oks += ok;
+          sum_mse += ms;
+          if (e > max_e) { max_e = e; max_i = i; }
+        } else {
+          const float l = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(w_s, e), __fmul_rn(w_o, ok)), __fmul_rn(w_g, ms)), lw);
+          if (p.mode == PP_LOSS_PER_PIXEL) static_cast<T*>(a.loss_map)[hm * HW + i] = Elem<T>::from_f32(l);
+          else sum_l += l;
+        }
+      }
+      if (want_grad) {
+        float u = u_k;
+        if (a.upstream_kind == kUpPerPixel) u = Elem<T>::to_f32(static_cast<const T*>(a.upstream)[hm * HW + i]);
+        float cs = lw * w_s * u * m;
+        if (p.mode == PP_LOSS_PER_KEYPOINT && i != peak) cs = 0.0f;  // max() routes to one pixel
+        P[(y + 1) * S + x + 1] = 2.0f * cs * gx;
+        Q[(y + 1) * S + x + 1] = 2.0f * cs * gy;
+      }
+    }
+
+    if (want_fwd && p.mode != PP_LOSS_PER_PIXEL) {
+      // block reductions (fixed order -> deterministic)
+      sum_l = warp_sum(sum_l); sum_oks = warp_sum(sum_oks); sum_mse = warp_sum(sum_mse);
+      warp_argmax(max_e, max_i);
+      if (lane == 0) { red_d[0][warp] = sum_l; red_d[1][warp] = sum_oks; red_d[2][warp] = sum_mse; red_f[warp] = max_e; red_i[warp] = max_i; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double sl = 0, so = 0, sm = 0;
+        float me = red_f[0]; int mi = red_i[0];
+        for (int w = 0; w < kLossThreads / 32; ++w) { sl += red_d[0][w]; so += red_d[1][w]; sm += red_d[2][w]; }
+        for (int w = 1; w < kLossThreads / 32; ++w) argmax_combine(me, mi, red_f[w], red_i[w]);
+        if (p.mode == PP_LOSS_PER_KEYPOINT) {
+          // w_o * sum(oks) + w_s * max(e) + w_g * mean(mse), then * loss_weight (loss.py:128-134, 143)
+          const float v = (w_o * static_cast<float>(so) + w_s * me + w_g * static_cast<float>(sm / HW)) * lw;
+          a.loss_kpt[hm] = v;
+          if (a.peak_out) a.peak_out[hm] = mi;
+          a.partials[hm] = static_cast<double>(v);
+        } else {
+          a.partials[hm] = sl;
+        }
+      }
+    }
+
+    if (want_grad) {
+      __syncthreads();
+      T* g_ptr = static_cast<T*>(a.grad) + hm * HW;
+      for (int i = threadIdx.x; i < HW; i += kLossThreads) {
+        const int y = i / W, x = i - y * W;
+        const int at = (y + 1) * S + x + 1;
+        const float* pc = P + at;
+        const float* qc = Q + at;
+        const float sx = (pc[-S - 1] - pc[-S + 1]) + 2.0f * (pc[-1] - pc[1]) + (pc[S - 1] - pc[S + 1]);
+        const float sy = (qc[-S - 1] + 2.0f * qc[-S] + qc[-S + 1]) - (qc[S - 1] + 2.0f * qc[S] + qc[S + 1]);
+        const float o = A[at];
+        const float t = Elem<T>::to_f32(t_ptr[i]);
+        float m = m_k;
+        if (pw_ptr) m *= Elem<T>::to_f32(pw_ptr[i]);
+        if (m_ptr) m *= Elem<T>::to_f32(m_ptr[i]);
+        float u = u_k;
+        if (a.upstream_kind == kUpPerPixel) u = Elem<T>::to_f32(static_cast<const T*>(a.upstream)[hm * HW + i]);
+        float wg = w_g;
+        if (p.mode == PP_LOSS_PER_KEYPOINT) wg = w_g / static_cast<float>(HW);  // mean over pixels
+        const float direct = lw * u * m * (w_o * oks_term_grad(p.oks_type, t) + wg * 2.0f * (o - t));
+        g_ptr[i] = Elem<T>::from_f32(direct - sx - sy);
+      }
+    }
+    __syncthreads();
+  }
+  if (a.range_flag && bad_target) atomicOr(a.range_flag, 1);
+}
+
+// sum of N doubles * scale -> one float; single CTA, fixed order
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int64_t n, double scale,
+                                                       float* __restrict__ out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) s += partials[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[0] = static_cast<float>(t * scale);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ data, int64_t numel, const float* __restrict__ scale) {
+  const float s = scale[0];
+  if (s == 1.0f) return;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < numel; i += stride)
+    data[i] = Elem<T>::from_f32(Elem<T>::to_f32(data[i]) * s);
+}
+
+int check_loss_params(const char* fn, const pp_loss_params* p) {
+  PP_REQUIRE(p != nullptr, PP_ERR_INVALID_ARG, "%s: null params", fn);
+  PP_REQUIRE(p->B >= 0 && p->K > 0 && p->H > 0 && p->W > 0, PP_ERR_INVALID_ARG, "%s: bad shape B=%d K=%d H=%d W=%d", fn,
+             p->B, p->K, p->H, p->W);
+  PP_REQUIRE(p->dtype == PP_F32 || p->dtype == PP_BF16, PP_ERR_INVALID_ARG, "%s: unsupported dtype %d", fn, p->dtype);
+  PP_REQUIRE(p->mode >= 0 && p->mode <= 2, PP_ERR_INVALID_ARG, "%s: bad mode %d", fn, p->mode);
+  PP_REQUIRE(p->oks_type >= 0 && p->oks_type <= 2, PP_ERR_INVALID_ARG, "%s: bad oks_type %d", fn, p->oks_type);
+  return PP_OK;
+}
+
+template <typename T>
+int launch_loss(const LossArgs& a, bool fwd, bool grad, cudaStream_t st) {
+  const pp_loss_params& p = a.p;
+  const int64_t N = static_cast<int64_t>(p.B) * p.K;
+  const size_t plane = sizeof(float) * static_cast<size_t>(p.H + 2) * (p.W + 2);
+  const size_t smem = plane * (grad ? 3 : 1);
+  PP_REQUIRE(smem <= static_cast<size_t>(pp_smem_optin()), PP_ERR_UNSUPPORTED_SHAPE,
+             "pp_oks_loss: %dx%d maps need %zu bytes of shared memory (> %lld)", p.H, p.W, smem,
+             static_cast<long long>(pp_smem_optin()));
+  int per_sm = 1;
+  if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(oks_loss_kernel<T>), kLossThreads, smem, &per_sm)) return rc;
+  const int grid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  oks_loss_kernel<T><<<grid, kLossThreads, smem, st>>>(a, fwd, grad);
+  PP_CUDA_OK(cudaGetLastError());
+  return PP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t pp_oks_loss_scratch_bytes(const pp_loss_params* p) {
+  if (!p) return 0;
+  return static_cast<int64_t>(sizeof(double)) * std::max<int64_t>(1, static_cast<int64_t>(p->B) * p->K);
+}
+
+int pp_oks_loss_forward(const pp_loss_params* p, const void* output, const void* target, const float* keypoint_weights,
+                        const void* pixel_weights, const void* mask, void* loss_map, float* loss_kpt,
+                        float* loss_scalar, int32_t* peak_index, void* grad, float grad_scale,
+                        int32_t* target_out_of_range, void* scratch, int64_t scratch_bytes, pp_stream_t stream) {
+  if (int rc = check_loss_params("pp_oks_loss_forward", p)) return rc;
+  if (static_cast<int64_t>(p->B) * p->K == 0) return PP_OK;
+  PP_REQUIRE(output && target, PP_ERR_INVALID_ARG, "pp_oks_loss_forward: null heatmaps");
+  PP_REQUIRE(scratch && scratch_bytes >= pp_oks_loss_scratch_bytes(p), PP_ERR_SCRATCH,
+             "pp_oks_loss_forward: scratch too small (%lld < %lld)", static_cast<long long>(scratch_bytes),
+             static_cast<long long>(pp_oks_loss_scratch_bytes(p)));
+  if (p->mode == PP_LOSS_PER_PIXEL) PP_REQUIRE(loss_map, PP_ERR_INVALID_ARG, "pp_oks_loss_forward: loss_map required");
+  if (p->mode == PP_LOSS_PER_KEYPOINT) PP_REQUIRE(loss_kpt, PP_ERR_INVALID_ARG, "pp_oks_loss_forward: loss_kpt required");
+  if (p->mode != PP_LOSS_PER_PIXEL) PP_REQUIRE(loss_scalar, PP_ERR_INVALID_ARG, "pp_oks_loss_forward: loss_scalar required");
+  PP_REQUIRE(grad == nullptr || p->mode == PP_LOSS_PIXEL_MEAN, PP_ERR_INVALID_ARG,
+             "pp_oks_loss_forward: the fused gradient exists for PP_LOSS_PIXEL_MEAN only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t N = static_cast<int64_t>(p->B) * p->K;
+  if (N == 0) return PP_OK;
+
+  LossArgs a{};
+  a.p = *p;
+  a.output = output; a.target = target; a.kp_weights = keypoint_weights; a.pix_weights = pixel_weights; a.mask = mask;
+  a.loss_map = loss_map; a.loss_kpt = loss_kpt; a.peak_out = peak_index;
+  a.partials = static_cast<double*>(scratch);
+  a.grad = grad; a.upstream_kind = kUpScalar; a.host_scale = grad_scale; a.upstream = nullptr;
+  a.range_flag = target_out_of_range;
+  if (target_out_of_range) PP_CUDA_OK(cudaMemsetAsync(target_out_of_range, 0, sizeof(int32_t), st));
+  int rc = (p->dtype == PP_F32) ? launch_loss<float>(a, true, grad != nullptr, st)
+                                : launch_loss<__nv_bfloat16>(a, true, grad != nullptr, st);
+  if (rc) return rc;
+  if (p->mode != PP_LOSS_PER_PIXEL) {
+    const double scale = (p->mode == PP_LOSS_PIXEL_MEAN) ? 1.0 / (static_cast<double>(N) * p->H * p->W) : 1.0 / static_cast<double>(N);
+    finalize_kernel<<<1, 256, 0, st>>>(a.partials, N, scale, loss_scalar);
+    PP_CUDA_OK(cudaGetLastError());
+  }
+  return PP_OK;
+}
+
+int pp_oks_loss_backward(const pp_loss_params* p, const void* output, const void* target, const float* keypoint_weights,
+                         const void* pixel_weights, const void* mask, const void* upstream, int32_t upstream_kind,
+                         const int32_t* peak_index, void* grad, void* scratch, int64_t scratch_bytes,
+                         pp_stream_t stream) {
+  (void)scratch; (void)scratch_bytes;
+  if (int rc = check_loss_params("pp_oks_loss_backward", p)) return rc;
+  if (static_cast<int64_t>(p->B) * p->K == 0) return PP_OK;
+  PP_REQUIRE(output && target && upstream && grad, PP_ERR_INVALID_ARG, "pp_oks_loss_backward: null argument");
+  PP_REQUIRE(p->mode != PP_LOSS_PER_KEYPOINT || peak_index, PP_ERR_INVALID_ARG,
+             "pp_oks_loss_backward: peak_index required for PP_LOSS_PER_KEYPOINT");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (static_cast<int64_t>(p->B) * p->K == 0) return PP_OK;
+  LossArgs a{};
+  a.p = *p;
+  a.output = output; a.target = target; a.kp_weights = keypoint_weights; a.pix_weights = pixel_weights; a.mask = mask;
+  a.grad = grad; a.upstream = upstream; a.peak_in = peak_index;
+  a.host_scale = 1.0f;
+  PP_REQUIRE(upstream_kind == PP_UPSTREAM_SCALAR || upstream_kind == PP_UPSTREAM_FULL, PP_ERR_INVALID_ARG,
+             "pp_oks_loss_backward: bad upstream_kind %d", upstream_kind);
+  PP_REQUIRE(!(upstream_kind == PP_UPSTREAM_FULL && p->mode == PP_LOSS_PIXEL_MEAN), PP_ERR_INVALID_ARG,
+             "pp_oks_loss_backward: PP_LOSS_PIXEL_MEAN has a scalar upstream");
+  a.upstream_kind = upstream_kind == PP_UPSTREAM_SCALAR ? kUpScalar : p->mode == PP_LOSS_PER_PIXEL ? kUpPerPixel : kUpPerKeypoint;
+  return (p->dtype == PP_F32) ? launch_loss<float>(a, false, true, st) : launch_loss<__nv_bfloat16>(a, false, true, st);
+}
+
+int pp_scale_inplace(void* data, int32_t dtype, int64_t numel, const float* scale_dev, pp_stream_t stream) {
+  PP_REQUIRE(data && scale_dev && numel >= 0, PP_ERR_INVALID_ARG, "pp_scale_inplace: bad argument");
+  if (numel == 0) return PP_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = static_cast<int>(std::min<int64_t>((numel + 255) / 256, static_cast<int64_t>(pp_sm_count()) * 8));
+  if (dtype == PP_F32) scale_kernel<float><<<grid, 256, 0, st>>>(static_cast<float*>(data), numel, scale_dev);
+  else if (dtype == PP_BF16) scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<__nv_bfloat16*>(data), numel, scale_dev);
+  else { pp_set_error("pp_scale_inplace: unsupported dtype %d", dtype); return PP_ERR_INVALID_ARG; }
+  PP_CUDA_OK(cudaGetLastError());
+  return PP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""CPU: the C-ABI library builds/loads and exports every symbol include/probpose_b200.h declares;
+the product path refuses to run without a GPU instead of falling back to the CPU."""
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from probpose_pytorch_b200.build import build
+    path = build()
+    return ctypes.CDLL(str(path))
+
+
+def _declared():
+    text = (ROOT / "include" / "probpose_b200.h").read_text()
+    return sorted(set(re.findall(r"^PP_API\s+[\w\s\*]+?\b(pp_\w+)\(", text, flags=re.M)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/probpose_b200.h but not exported"
+
+
+def test_binding_covers_header():
+    from probpose_pytorch_b200 import _lib
+    assert sorted(_lib.EXPORTS) == _declared()
+
+
+def test_version_and_error_string(lib):
+    lib.pp_version.restype = ctypes.c_int
+    lib.pp_last_error_string.restype = ctypes.c_char_p
+    assert lib.pp_version() == 1
+    assert isinstance(lib.pp_last_error_string(), bytes)
+
+
+def test_invalid_arguments_return_status_not_crash(lib):
+    # argument validation happens before any CUDA call, so this is safe without a GPU
+    lib.pp_last_error_string.restype = ctypes.c_char_p
+    assert lib.pp_encode(None, None, None, None, None, None, None, None, None) == -1
+    assert b"pp_encode" in lib.pp_last_error_string()
+    assert lib.pp_decode_expected(None, None, None, None, None, None, None, None, None) == -1
+    assert lib.pp_heatmap_tail(None, None, 0, ctypes.c_int64(4), ctypes.c_float(0.5), None) == -1
+
+
+def test_struct_layouts_match_header():
+    from probpose_pytorch_b200 import _lib
+    assert ctypes.sizeof(_lib.EncodeParams) == 44
+    assert ctypes.sizeof(_lib.DecodeParams) == 48
+    assert ctypes.sizeof(_lib.LossParams) == 72
+    assert ctypes.sizeof(_lib.OksTable) == 24
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    import probpose_pytorch_b200 as pp
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pp.get_heatmap_maximum(np.zeros((2, 4, 4), dtype=np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pp.ProbMap((192, 256), (48, 64), np.full(17, 0.05)).encode(np.zeros((1, 17, 2)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pp.OKSHeatmapLoss()(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4, 4))
+
+
+def test_product_does_not_import_oracle():
+    pkg = ROOT / "probpose_pytorch_b200"
+    for f in pkg.rglob("*.py"):
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read_text(), flags=re.M), f
+
+
+def test_host_tables_match_oracle():
+    """Host constant tables (product) against the oracle's restatement of the reference."""
+    import oracle as oc
+    from probpose_pytorch_b200 import _tables, synth
+    for wl in (synth.WORKLOADS[1], synth.WORKLOADS[4], synth.WORKLOADS[5]):
+        W, H = wl.heatmap_size
+        K = wl.num_keypoints
+        assert np.array_equal(_tables.oks_variance(wl.sigmas, H, W), oc.oks_variance_table(wl.sigmas, H, W))
+        assert np.array_equal(_tables.encode_divisors(wl.sigmas, -1, K, H, W), 2 * oc.oks_variance_table(wl.sigmas, H, W))
+        assert np.array_equal(_tables.encode_divisors(wl.sigmas, 2.0, K, H, W), np.full(K, 4.0))
+        ref = oc.oks_kernels_2d(K, H, W, wl.sigmas)
+        s = _tables.oks_variance(wl.sigmas, H, W)
+        for k in (0, K // 2, K - 1):
+            r = int(np.ceil(3 * s[k]))
+            ax = np.arange(-r, r + 1)
+            dist = np.sqrt(ax[None, :] ** 2 + ax[:, None] ** 2)
+            ker = np.exp(-(dist ** 2) / (2 * s[k]))
+            assert np.array_equal(ker / ker.sum(), ref[k])
+    assert np.array_equal(_tables.gaussian_taps(11), oc.gaussian_taps_f32(11))

@@ -1,0 +1,560 @@
+"""GPU parity: the CUDA path (through the Python shims -> ctypes -> C ABI) against the oracle on the
+same seeded inputs and against the committed reference outputs (tests/golden).
+
+Tolerances are the ones BASELINE.json's north_star states: argmax indices bit-exact; encoded targets,
+decoded coordinates, scores and loss values within 1e-5 relative in float32 and 1e-2 in bfloat16.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as oc
+from probpose_pytorch_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-5
+RTOL16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def pp():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import probpose_pytorch_b200 as mod
+    from probpose_pytorch_b200 import _lib
+    _lib.lib()  # fail loudly if the extension is missing
+    torch.cuda.set_device(0)
+    return mod
+
+
+def _oracle_encode(kind, wl, kps, vis, sigma=None):
+    outs = [oc.encode(kind, wl.input_size, wl.heatmap_size, wl.sigmas, kps[b:b + 1], vis[b:b + 1], sigma=sigma)
+            for b in range(kps.shape[0])]
+    return {k: (np.stack([o[k] for o in outs]) if k == "heatmaps" else np.concatenate([o[k] for o in outs]))
+            for k in ("heatmaps", "keypoint_weights", "in_image", "annotated")}
+
+
+def _assert_maps_close(got, want, rtol):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    # relative on normal numbers; float32 subnormals (< 1.2e-38) carry fewer bits, so give them an absolute floor
+    err = np.abs(got - want)
+    assert (err <= rtol * np.abs(want) + 1e-37).all(), f"max rel err {np.max(err / np.maximum(np.abs(want), 1e-30))}"
+
+
+# --------------------------------------------------------------------------- encode
+@pytest.mark.parametrize("kind", ["probmap", "argmax"])
+def test_encode_matches_golden_reference(pp, golden_dir, kind):
+    g = np.load(golden_dir / "encode_small.npz")
+    wl = synth.WORKLOADS[3]
+    cls = pp.ProbMap if kind == "probmap" else pp.ArgMaxProbMap
+    codec = cls(wl.input_size, wl.heatmap_size, wl.sigmas)
+    for b in range(g["keypoints"].shape[0]):
+        enc = codec.encode(g["keypoints"][b:b + 1], g["visible"][b:b + 1])
+        assert enc["heatmaps"].dtype == np.float32 and enc["heatmaps"].shape == g[f"{kind}_heatmaps"][b].shape
+        _assert_maps_close(enc["heatmaps"], g[f"{kind}_heatmaps"][b], RTOL32)
+        mism = np.count_nonzero(enc["heatmaps"] != g[f"{kind}_heatmaps"][b])
+        assert mism <= 2, f"{mism} float32 elements differ from the reference bit pattern"
+        assert np.array_equal(enc["keypoint_weights"], g[f"{kind}_weights"][b:b + 1])
+        assert np.array_equal(enc["in_image"], g[f"{kind}_in_image"][b:b + 1])
+        assert np.array_equal(enc["annotated"], g[f"{kind}_annotated"][b:b + 1])
+        if kind == "probmap":
+            assert np.array_equal(enc["heatmap_keypoints"], g["keypoints"][b:b + 1] / codec.scale_factor)
+
+
+@pytest.mark.parametrize("cid,batch", [(1, 8), (3, 8), (4, 4), (5, 2)])
+@pytest.mark.parametrize("kpdtype", [np.float32, np.float64])
+def test_encode_batch_matches_oracle(pp, cid, batch, kpdtype):
+    wl = synth.WORKLOADS[cid]
+    kps, vis, _ = synth.make_keypoints(wl, batch=batch, dtype=kpdtype)
+    for kind, cls in (("probmap", pp.ProbMap), ("argmax", pp.ArgMaxProbMap)):
+        codec = cls(wl.input_size, wl.heatmap_size, wl.sigmas)
+        out = codec.encode_batch(kps, vis)
+        want = _oracle_encode(kind, wl, kps, vis)
+        _assert_maps_close(out["heatmaps"].cpu().numpy(), want["heatmaps"], RTOL32)
+        assert np.array_equal(out["keypoint_weights"].cpu().numpy(), want["keypoint_weights"].astype(np.float32))
+        assert np.array_equal(out["in_image"].cpu().numpy(), want["in_image"])
+        assert np.array_equal(out["annotated"].cpu().numpy(), want["annotated"])
+
+
+def test_encode_edge_cases(pp):
+    wl = synth.WORKLOADS[1]
+    K = wl.num_keypoints
+    codec = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    kps = np.zeros((1, K, 2), dtype=np.float64)
+    kps[0, 0] = (-500.0, -500.0)      # far outside: map underflows, weight 0
+    kps[0, 1] = (191.0, 255.0)        # last pixel
+    kps[0, 2] = (192.0, 10.0)         # just outside in x
+    kps[0, 3] = (95.5, 127.5)         # half-grid
+    vis = np.ones((1, K), dtype=np.float32)
+    vis[0, 4] = 0.0                   # unlabelled: zero channel, weight copied
+    vis[0, 5] = 0.4
+    got = codec.encode(kps, vis)
+    want = oc.encode("argmax", wl.input_size, wl.heatmap_size, wl.sigmas, kps, vis)
+    _assert_maps_close(got["heatmaps"], want["heatmaps"], RTOL32)
+    for key in ("keypoint_weights", "in_image", "annotated"):
+        assert np.array_equal(got[key], want[key]), key
+    assert got["keypoint_weights"][0, 0] == 0 and not got["heatmaps"][0].any()
+    assert not got["heatmaps"][4].any() and got["keypoint_weights"][0, 5] == np.float32(0.4)
+    # bool visibility keeps a bool weight array (dataset.py:124)
+    got_b = codec.encode(kps, vis > 0.5)
+    assert got_b["keypoint_weights"].dtype == bool
+    # default visible = ones; generate_probmaps with heatmap-space keypoints and the scalar sigma override
+    hm, w = pp.generate_probmaps((48, 64), (kps / codec.scale_factor), vis, wl.sigmas, sigma=0.55)
+    hm_ref, w_ref = oc.generate_probmaps((48, 64), (kps / codec.scale_factor), vis, wl.sigmas, sigma=0.55)
+    _assert_maps_close(hm, hm_ref, RTOL32)
+    assert np.array_equal(w, w_ref)
+    with pytest.raises(AssertionError):
+        codec.encode(np.zeros((2, K, 2)))
+
+
+def test_encode_odd_width_and_bf16(pp):
+    wl = synth.Workload(9, "odd", 3, 5, (101, 75), (27, 19), True)
+    kps, vis, _ = synth.make_keypoints(wl, seed=5)
+    codec = pp.ProbMap(wl.input_size, wl.heatmap_size, np.full(5, 0.05), sigma=-1)
+    out = codec.encode_batch(kps, vis)
+    want = np.stack([oc.encode("probmap", wl.input_size, wl.heatmap_size, np.full(5, 0.05), kps[b:b + 1], vis[b:b + 1],
+                               sigma=-1)["heatmaps"] for b in range(3)])
+    _assert_maps_close(out["heatmaps"].cpu().numpy(), want, RTOL32)
+    wl = synth.WORKLOADS[3]
+    kps, vis, _ = synth.make_keypoints(wl, batch=4)
+    codec = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    out16 = codec.encode_batch(kps, vis, dtype=torch.bfloat16)["heatmaps"]
+    want = torch.from_numpy(_oracle_encode("argmax", wl, kps, vis)["heatmaps"]).bfloat16()
+    assert out16.dtype == torch.bfloat16
+    assert torch.equal(out16.cpu(), want) or (out16.cpu().float() - want.float()).abs().max() <= RTOL16
+
+
+# --------------------------------------------------------------------------- argmax
+def test_heatmap_maximum_exact(pp):
+    rng = np.random.default_rng(11)
+    hm = rng.random((3, 17, 64, 48), dtype=np.float32)
+    hm[0, 0] = 0.0                       # empty channel -> (-1, -1)
+    hm[0, 1] = -1.0
+    hm[1, 2, 10, 7] = hm[1, 2, 50, 3] = 2.0   # tie -> lowest flat index
+    for arr in (hm, hm[0]):
+        locs, vals = pp.get_heatmap_maximum(arr)
+        locs_ref, vals_ref = oc.heatmap_maximum(arr)
+        assert locs.dtype == np.float32 and np.array_equal(locs, locs_ref) and np.array_equal(vals, vals_ref)
+    odd = rng.random((2, 3, 19, 27), dtype=np.float32)
+    assert np.array_equal(pp.get_heatmap_maximum(odd)[0], oc.heatmap_maximum(odd)[0])
+    t = torch.from_numpy(hm).cuda()
+    locs_t, vals_t = pp.get_heatmap_maximum(t)
+    assert locs_t.is_cuda and np.array_equal(locs_t.cpu().numpy(), oc.heatmap_maximum(hm)[0])
+    with pytest.raises(AssertionError):
+        pp.get_heatmap_maximum(np.zeros((4, 4), dtype=np.float32))
+
+
+# --------------------------------------------------------------------------- expected-OKS decoder
+@pytest.mark.parametrize("name", ["blob", "uniform", "clean"])
+def test_expected_decoder_matches_golden_reference(pp, golden_dir, name):
+    g = np.load(golden_dir / "decode.npz")
+    wl = synth.WORKLOADS[3]
+    arr = g[name]
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    # batched device call: argmax bit-exact, coordinates/scores within 1e-5
+    dev = pm.decode_device(torch.from_numpy(arr).cuda())
+    locs = dev["locs"].cpu().numpy()
+    np.testing.assert_allclose(locs, g[f"{name}_locs"], rtol=RTOL32, atol=1e-5)
+    assert np.array_equal(dev["vals"].cpu().numpy(), g[f"{name}_vals"])
+    np.testing.assert_allclose(dev["keypoints"].cpu().numpy(), g[f"{name}_keypoints"], rtol=RTOL32, atol=1e-5)
+    assert np.array_equal(dev["argmax"][0].cpu().numpy(), g[f"{name}_argmax0"])
+    # reference-shaped single-sample calls
+    for b in range(arr.shape[0]):
+        l, v = pp.get_heatmap_expected_value(arr[b], wl.sigmas)
+        assert l.shape == (17, 2) and l.dtype == np.float32 and v.shape == (17,)
+        np.testing.assert_allclose(l, g[f"{name}_locs"][b], rtol=RTOL32, atol=1e-5)
+        kp, sc = pm.decode(arr[b])
+        assert kp.shape == (1, 17, 2) and kp.dtype == np.float64 and sc.shape == (1, 17)
+        np.testing.assert_allclose(kp[0], g[f"{name}_keypoints"][b], rtol=RTOL32, atol=1e-5)
+        assert np.array_equal(sc[0], g[f"{name}_scores"][b])
+    # return_heatmap: the convolved map itself, float32, bit for bit (double accumulation in scipy's order)
+    l, v, conv = pp.get_heatmap_expected_value(arr[0], wl.sigmas, return_heatmap=True)
+    assert np.array_equal(conv, g[f"{name}_conv0"])
+    np.testing.assert_allclose(l, g[f"{name}_locs"][0], rtol=RTOL32, atol=1e-5)
+
+
+@pytest.mark.parametrize("cid,batch", [(2, 6), (4, 3), (5, 1)])
+def test_expected_decoder_argmax_exact_vs_oracle(pp, cid, batch):
+    wl = synth.WORKLOADS[cid]
+    kps, vis, _ = synth.make_keypoints(wl, batch=batch, seed=200 + cid)
+    tgt = _oracle_encode("argmax", wl, synth.jitter_keypoints(wl, kps, 201), vis)["heatmaps"]
+    pred = synth.blob_predictions_numpy(tgt, synth.blob_params(tgt.shape[:2], 202), 203)
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = pm.decode_device(torch.from_numpy(pred).cuda())
+    W = wl.heatmap_size[0]
+    for b in range(batch):
+        locs, vals, conv = oc.heatmap_expected_value(pred[b], wl.sigmas, return_heatmap=True, conv="scipy")
+        am = conv.reshape(conv.shape[0], -1).argmax(1)
+        assert np.array_equal(dev["argmax"][b].cpu().numpy(), am), f"sample {b}"
+        np.testing.assert_allclose(dev["locs"][b].cpu().numpy(), locs, rtol=RTOL32, atol=1e-5)
+        assert np.array_equal(dev["vals"][b].cpu().numpy(), vals)
+
+
+def test_expected_decoder_ties_plateaus_and_constants(pp):
+    """On-grid / half-grid targets (exact ties), saturated plateaus, all-zero and constant maps."""
+    wl = synth.WORKLOADS[1]
+    K, (W, H) = wl.num_keypoints, wl.heatmap_size
+    rng = np.random.default_rng(31)
+    grid = (rng.integers(0, [W - 1, H - 1], size=(4, K, 2)) + rng.choice([0.0, 0.5], size=(4, K, 2)))
+    kps = (grid * ((np.array(wl.input_size) - 1) / (np.array(wl.heatmap_size) - 1))).astype(np.float64)
+    vis = np.ones((4, K), dtype=np.float32)
+    maps = _oracle_encode("argmax", wl, kps, vis)["heatmaps"]
+    maps[1] = np.clip(maps[1] * 3.0, 0, 1)        # plateaus of exactly 1.0
+    maps[2, 0] = 0.0                               # all-zero channel -> (0, 0), no -1 sentinel (B-5)
+    maps[2, 1] = 0.25                              # constant channel
+    maps[3] = np.round(maps[3] * 4) / 4            # heavy quantisation -> many exact ties
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = pm.decode_device(torch.from_numpy(maps).cuda())
+    for b in range(4):
+        locs, vals, conv = oc.heatmap_expected_value(maps[b], wl.sigmas, return_heatmap=True, conv="scipy")
+        assert np.array_equal(dev["argmax"][b].cpu().numpy(), conv.reshape(K, -1).argmax(1)), f"sample {b}"
+        np.testing.assert_allclose(dev["locs"][b].cpu().numpy(), locs, rtol=RTOL32, atol=1e-5)
+        assert np.array_equal(dev["vals"][b].cpu().numpy(), vals)
+    assert dev["locs"][2, 0].tolist() == [0.0, 0.0]
+
+
+def test_expected_decoder_reference_test_shape_and_generic_path(pp):
+    """Seeded version of the reference's tests/test_heatmap.py (20 x 256 x 256 uniform maps, random
+    sigmas): maps too large for shared memory take the exact full-map path."""
+    rng = np.random.default_rng(5)
+    hms = rng.random((3, 256, 256), dtype=np.float32)
+    sig = rng.random(3).astype(np.float32)
+    l, v, conv = pp.get_heatmap_expected_value(hms, sig, return_heatmap=True, backend="torch")
+    l_ref, v_ref, conv_ref = oc.heatmap_expected_value(hms, sig, return_heatmap=True, conv="scipy")
+    np.testing.assert_allclose(conv, conv_ref, rtol=1e-5, atol=1e-8)   # the reference test's own tolerance
+    assert np.array_equal(conv, conv_ref)
+    np.testing.assert_allclose(l, l_ref, rtol=RTOL32, atol=1e-5)
+    assert np.array_equal(v, v_ref)
+    l2, v2 = pp.get_heatmap_expected_value(hms, sig)                   # no conv requested: work space is internal
+    assert np.array_equal(l2, l) and np.array_equal(v2, v)
+    # odd sizes
+    odd = rng.random((5, 19, 27), dtype=np.float32)
+    l, v = pp.get_heatmap_expected_value(odd, np.full(5, 0.07))
+    l_ref, v_ref = oc.heatmap_expected_value(odd, np.full(5, 0.07), conv="scipy")
+    np.testing.assert_allclose(l, l_ref, rtol=RTOL32, atol=1e-5)
+    assert np.array_equal(v, v_ref)
+
+
+def test_decoder_fused_head_tail(pp):
+    wl = synth.WORKLOADS[2]
+    rng = np.random.default_rng(41)
+    logits = rng.normal(0.1, 0.3, size=(4, 17, 64, 48)).astype(np.float32)
+    x = torch.from_numpy(logits).cuda()
+    tail = pp.heatmap_tail(x, 0.5)
+    assert np.array_equal(tail.cpu().numpy(), oc.head_tail(logits, 0.5))
+    assert torch.equal(tail, torch.clamp(x / 0.5, 0, 1))
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    a = pm.decode_device(x, temperature=0.5)
+    b = pm.decode_device(tail)
+    for key in ("locs", "vals", "argmax", "keypoints"):
+        assert torch.equal(a[key], b[key]), key
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    a, b = am.decode_device(x, temperature=0.5), am.decode_device(tail)
+    for key in ("peaks", "scores", "locs", "keypoints"):
+        assert torch.equal(a[key], b[key]), key
+
+
+# --------------------------------------------------------------------------- DARK decoder
+def _dark_tolerance(hm, peaks, wl, base_rtol):
+    """Per-keypoint tolerance (input px).  cv2 / numpy float32 blurs agree to ~2e-7 relative and the
+    float32 log to ~1 ulp; DARK multiplies that by the inverse Hessian of the log-map at the peak."""
+    K, H, W = hm.shape
+    work = oc.gaussian_blur_modulate(hm.copy(), 11)
+    np.clip(work, 1e-3, 50.0, work)
+    lg = np.log(work.astype(np.float64))
+    pad = np.pad(lg, ((0, 0), (1, 1), (1, 1)), mode="edge")
+    tol = np.zeros((K, 2))
+    scale = np.array(wl.input_size, dtype=np.float64) / (np.array(wl.heatmap_size) - 1)
+    for k in range(K):
+        x, y = int(peaks[k, 0]) + 1, int(peaks[k, 1]) + 1
+        if x <= 0:
+            continue
+        c = pad[k, y, x]
+        dxx = pad[k, y, x + 1] - 2 * c + pad[k, y, x - 1]
+        dyy = pad[k, y + 1, x] - 2 * c + pad[k, y - 1, x]
+        dxy = 0.5 * (pad[k, y + 1, x + 1] - pad[k, y, x + 1] - pad[k, y + 1, x] + 2 * c - pad[k, y, x - 1] - pad[k, y - 1, x]
+                     + pad[k, y - 1, x - 1])
+        hess = np.array([[dxx, dxy], [dxy, dyy]]) + np.finfo(np.float32).eps * np.eye(2)
+        inv = np.linalg.pinv(hess)
+        g = np.array([0.5 * (pad[k, y, x + 1] - pad[k, y, x - 1]), 0.5 * (pad[k, y + 1, x] - pad[k, y - 1, x])])
+        shift = np.abs(inv @ g).max()
+        delta = 2e-6  # absolute noise of the float32 log-values (|log| <= 6.9, a few ulp)
+        amp = np.abs(inv).sum(axis=1).max()
+        tol[k] = amp * delta * (1.0 + 4.0 * shift)
+    return tol * scale
+
+
+@pytest.mark.parametrize("name", ["clean", "blob"])
+def test_dark_decoder_matches_golden_reference(pp, golden_dir, name):
+    g = np.load(golden_dir / "decode.npz")
+    wl = synth.WORKLOADS[3]
+    arr = g[name]
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = am.decode_device(torch.from_numpy(arr).cuda())
+    assert np.array_equal(dev["peaks"].cpu().numpy(), g[f"{name}_peaks"])           # argmax bit-exact
+    assert np.array_equal(dev["scores"].cpu().numpy(), g[f"{name}_dark_scores"])
+    got = dev["keypoints"].cpu().numpy()
+    want = g[f"{name}_dark_keypoints"]
+    n_strict = n_total = 0
+    for b in range(arr.shape[0]):
+        live = g[f"{name}_peaks"][b, :, 0] >= 0
+        tol = _dark_tolerance(arr[b], g[f"{name}_peaks"][b], wl, RTOL32)
+        err = np.abs(got[b] - want[b])
+        bound = RTOL32 * np.maximum(np.abs(want[b]), 1.0) + tol
+        assert (err[live] <= bound[live]).all(), (b, np.max(err[live] / bound[live]))
+        strict = err[live] <= RTOL32 * np.maximum(np.abs(want[b][live]), 1.0)
+        n_strict += strict.sum(); n_total += strict.size
+        # empty channels keep the sentinel (documented deviation from the reference's out-of-range reads)
+        assert (dev["locs"][b].cpu().numpy()[~live] == -1).all()
+        kp, sc = am.decode(arr[b])      # reference-shaped call
+        assert kp.shape == (1, 17, 2) and kp.dtype == np.float64
+        assert np.array_equal(kp[0], got[b]) and np.array_equal(sc[0], g[f"{name}_dark_scores"][b])
+    if name == "clean":      # noise-free OKS-shaped maps: plain 1e-5 everywhere
+        assert n_strict == n_total, f"{n_total - n_strict} of {n_total} coordinates outside 1e-5"
+    else:
+        assert n_strict >= 0.9 * n_total
+
+
+@pytest.mark.parametrize("cid,batch", [(4, 2), (5, 1)])
+def test_dark_decoder_vs_oracle_other_shapes(pp, cid, batch):
+    wl = synth.WORKLOADS[cid]
+    kps, vis, _ = synth.make_keypoints(wl, batch=batch, seed=300 + cid)
+    inside = (kps[..., 0] >= 8) & (kps[..., 0] < wl.input_size[0] - 8) & (kps[..., 1] >= 8) & (kps[..., 1] < wl.input_size[1] - 8)
+    maps = _oracle_encode("argmax", wl, kps, np.ones_like(vis))["heatmaps"]
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = am.decode_device(torch.from_numpy(maps).cuda())
+    for b in range(batch):
+        kp, sc = oc.decode_argmax_dark(maps[b], wl.input_size, wl.heatmap_size, backend="cv2")
+        peaks, _ = oc.heatmap_maximum(maps[b])
+        assert np.array_equal(dev["peaks"][b].cpu().numpy(), peaks)
+        assert np.array_equal(dev["scores"][b].cpu().numpy(), sc[0])
+        ok = inside[b] & (peaks[:, 0] >= 0)
+        got = dev["keypoints"][b].cpu().numpy()
+        tol = _dark_tolerance(maps[b], peaks, wl, RTOL32)
+        bound = RTOL32 * np.maximum(np.abs(kp[0]), 1.0) + tol
+        assert (np.abs(got - kp[0])[ok] <= bound[ok]).all()
+
+
+# --------------------------------------------------------------------------- loss
+_VARIANTS = {
+    "train": dict(smoothing_weight=0.05, oks_type="minus"),
+    "both": dict(smoothing_weight=0.2, gaussian_weight=0.1, oks_type="both", loss_weight=2.0),
+    "plus_skip": dict(oks_type="plus", skip_empty_channel=True),
+}
+
+
+def _close(got, want, rtol, scale=None):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    scale = np.abs(want).max() if scale is None else scale
+    err = np.abs(got - want)
+    assert (err <= rtol * np.abs(want) + rtol * 0.05 * scale + 1e-30).all(), \
+        f"max err {err.max():.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("vname", list(_VARIANTS))
+def test_loss_matches_golden_reference(pp, golden_dir, vname):
+    g = np.load(golden_dir / "loss.npz")
+    out = torch.from_numpy(g["output"]).cuda()
+    tgt = torch.from_numpy(g["target"]).cuda()
+    tw = torch.from_numpy(g["target_weights"]).cuda()
+    mask = torch.from_numpy(g["mask"]).cuda()
+    mod = pp.OKSHeatmapLoss(use_target_weight=True, **_VARIANTS[vname])
+    for wname, w, m in (("w", tw, None), ("wm", tw, mask), ("none", None, None)):
+        for mname, mode in (("pixel", dict(per_pixel=True)), ("kpt", dict(per_keypoint=True)), ("mean", dict())):
+            o = out.clone().requires_grad_(True)
+            l = mod(o, tgt, w, m, **mode)
+            (l.mean() if mname == "pixel" else l.sum()).backward()
+            key = f"{vname}/{wname}/{mname}"
+            want_v, want_g = g[key + "/value"], g[key + "/grad"]
+            assert tuple(l.shape) == want_v.shape, key
+            _close(l.detach().cpu().numpy(), want_v, RTOL32)
+            _close(o.grad.cpu().numpy(), want_g, RTOL32)
+        # fused mean == per_pixel.mean(), values and gradients
+        o = out.clone().requires_grad_(True)
+        l = mod.forward_mean(o, tgt, w, m)
+        (l * 3.0).backward()
+        key = f"{vname}/{wname}/pixel"
+        assert abs(float(l) - g[key + "/value"].mean(dtype=np.float64)) <= RTOL32 * abs(g[key + "/value"].mean(dtype=np.float64)) + 1e-12
+        _close(o.grad.cpu().numpy(), 3.0 * g[key + "/grad"], RTOL32)
+
+
+def test_loss_full_upstream_and_pixel_weights(pp):
+    torch.manual_seed(3)
+    B, K, H, W = 3, 4, 40, 36
+    out, tgt = torch.rand(B, K, H, W), torch.rand(B, K, H, W)
+    twp = torch.rand(B, K, H, W)
+    up_px, up_k = torch.rand(B, K, H, W), torch.rand(B, K)
+    kw = dict(smoothing_weight=0.1, gaussian_weight=0.2, oks_type="both")
+    mod = pp.OKSHeatmapLoss(**kw)
+    for mode, up in ((dict(per_pixel=True), up_px), (dict(per_keypoint=True), up_k)):
+        o_ref = out.clone().requires_grad_(True)
+        l_ref = oc.oks_heatmap_loss(o_ref, tgt, twp, None, **mode, **kw)
+        (l_ref * up).sum().backward()
+        o = out.cuda().requires_grad_(True)
+        l = mod(o, tgt.cuda(), twp.cuda(), None, **mode)
+        (l * up.cuda()).sum().backward()
+        _close(l.detach().cpu().numpy(), l_ref.detach().numpy(), RTOL32)
+        _close(o.grad.cpu().numpy(), o_ref.grad.numpy(), RTOL32)
+
+
+def test_loss_known_answer_and_asserts(pp):
+    """tests/test_loss.py of the reference: 192x192 target, zero prediction -> loss 0.0; target range assert."""
+    codec = pp.ArgMaxProbMap((768, 768), (192, 192), np.array([0.1] * 20))
+    enc = codec.encode(np.array([[[96.0, 96.0]]]), np.array([[1.0]]), np.array([[1.0]]))
+    hm = enc["heatmaps"][None]
+    assert hm.shape == (1, 1, 192, 192)
+    assert abs(float(hm.max()) - 0.9970669150352478) <= 1e-5 * 0.9970669150352478
+    mod = pp.OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus")
+    loss = mod(torch.zeros(hm.shape).cuda(), torch.from_numpy(hm).cuda(), torch.tensor([[1.0]]).cuda())
+    assert float(loss) == 0.0
+    with pytest.raises(AssertionError, match="normalized"):
+        mod(torch.zeros(1, 1, 8, 8).cuda(), torch.full((1, 1, 8, 8), 1.5).cuda())
+    with pytest.raises(AssertionError):
+        mod(torch.zeros(1, 2, 8, 8).cuda(), torch.zeros(1, 2, 8, 8).cuda(), torch.ones(1, 3).cuda())
+
+
+def test_loss_closed_form_gradient_c4_shape(pp):
+    """Full-size shape (96x72): gradient of the fused kernel vs the float64 closed form; linearity in
+    the upstream gradient; determinism."""
+    wl = synth.WORKLOADS[4]
+    B = 4
+    kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=17)
+    tgt = _oracle_encode("argmax", wl, kps, vis)["heatmaps"]
+    pred = synth.blob_predictions_numpy(_oracle_encode("argmax", wl, synth.jitter_keypoints(wl, kps, 18), vis)["heatmaps"],
+                                        synth.blob_params(tgt.shape[:2], 19), 20)
+    w = (np.random.default_rng(21).random((B, 17)) < 0.8).astype(np.float32)
+    kw = dict(smoothing_weight=0.05, oks_type="minus")
+    mod = pp.OKSHeatmapLoss(use_target_weight=True, **kw)
+    o = torch.from_numpy(pred).cuda().requires_grad_(True)
+    l = mod.forward_mean(o, torch.from_numpy(tgt).cuda(), torch.from_numpy(w).cuda())
+    l.backward()
+    want = oc.oks_heatmap_loss_grad_closed_form(pred, tgt, w[:, :, None, None], **kw)
+    _close(o.grad.cpu().numpy(), want, RTOL32)
+    l_ref = oc.oks_heatmap_loss(torch.from_numpy(pred), torch.from_numpy(tgt), torch.from_numpy(w), per_pixel=True, **kw).mean()
+    assert abs(float(l) - float(l_ref)) <= RTOL32 * abs(float(l_ref))
+    o2 = torch.from_numpy(pred).cuda().requires_grad_(True)
+    l2 = mod.forward_mean(o2, torch.from_numpy(tgt).cuda(), torch.from_numpy(w).cuda())
+    (l2 * 0.25).backward()
+    assert float(l2) == float(l)                                         # deterministic reduction
+    _close(o2.grad.cpu().numpy() * 4.0, o.grad.cpu().numpy(), 1e-6)      # linear in the upstream gradient
+
+
+def test_loss_bf16(pp):
+    """The reference cannot run the loss in bfloat16 (Sobel kernels are float32); the
+    bf16 oracle is the float32 reference on bf16-rounded inputs, tolerance 1e-2."""
+    torch.manual_seed(9)
+    B, K, H, W = 2, 5, 64, 48
+    out = torch.rand(B, K, H, W).bfloat16()
+    tgt = torch.rand(B, K, H, W).bfloat16()
+    tw = (torch.rand(B, K) < 0.8).float()
+    kw = dict(smoothing_weight=0.05, oks_type="minus")
+    o_ref = out.float().requires_grad_(True)
+    l_ref = oc.oks_heatmap_loss(o_ref, tgt.float(), tw, per_pixel=True, **kw).mean()
+    l_ref.backward()
+    mod = pp.OKSHeatmapLoss(use_target_weight=True, **kw)
+    o = out.cuda().requires_grad_(True)
+    l = mod.forward_mean(o, tgt.cuda(), tw.cuda())
+    l.backward()
+    assert o.grad.dtype == torch.bfloat16
+    assert abs(float(l) - float(l_ref)) <= RTOL16 * abs(float(l_ref))
+    _close(o.grad.float().cpu().numpy(), o_ref.grad.numpy(), RTOL16)
+
+
+def test_decoders_bf16(pp):
+    wl = synth.WORKLOADS[3]
+    kps, vis, _ = synth.make_keypoints(wl, batch=3, seed=55)
+    maps = _oracle_encode("argmax", wl, kps, vis)["heatmaps"]
+    pred = synth.blob_predictions_numpy(maps, synth.blob_params(maps.shape[:2], 56), 57)
+    p16 = torch.from_numpy(pred).bfloat16()
+    rounded = p16.float().numpy()
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = pm.decode_device(p16.cuda())
+    for b in range(3):
+        locs, vals, conv = oc.heatmap_expected_value(rounded[b], wl.sigmas, return_heatmap=True, conv="scipy")
+        assert np.array_equal(dev["argmax"][b].cpu().numpy(), conv.reshape(17, -1).argmax(1))   # ties are common in bf16
+        np.testing.assert_allclose(dev["locs"][b].cpu().numpy(), locs, rtol=RTOL16, atol=1e-2)
+        assert np.array_equal(dev["vals"][b].cpu().numpy(), vals)
+    peaks, scores = oc.heatmap_maximum(rounded)
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    d = am.decode_device(p16.cuda())
+    assert np.array_equal(d["peaks"].cpu().numpy(), peaks) and np.array_equal(d["scores"].cpu().numpy(), scores)
+
+
+# --------------------------------------------------------------------------- round trips at full size
+@pytest.mark.parametrize("cid", [2, 4, 5])
+def test_round_trip_full_size(pp, cid):
+    """encode -> decode at BASELINE.json's full batch sizes: for in-image, labelled keypoints the
+    expected-OKS argmax is the pixel nearest to the encoded keypoint (size-independent property)."""
+    wl = synth.WORKLOADS[cid]
+    kps, vis, _ = synth.make_keypoints(wl)
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    enc = am.encode_batch(kps, vis)
+    hm = enc["heatmaps"]
+    assert tuple(hm.shape) == (wl.batch, wl.num_keypoints, wl.heatmap_size[1], wl.heatmap_size[0])
+    dec = pm.decode_device(hm)
+    dark = am.decode_device(hm)
+    hm_kp = kps / am.scale_factor
+    W, H = wl.heatmap_size
+    live = (vis >= 0.5) & (hm_kp[..., 0] >= 1) & (hm_kp[..., 0] <= W - 2) & (hm_kp[..., 1] >= 1) & (hm_kp[..., 1] <= H - 2)
+    frac = hm_kp - np.floor(hm_kp)
+    unambiguous = live & (np.abs(frac - 0.5) > 0.02).all(-1)
+    nearest = np.floor(hm_kp + 0.5)
+    peaks = dark["peaks"].cpu().numpy()
+    assert np.array_equal(peaks[unambiguous], nearest[unambiguous].astype(np.float32))
+    am_idx = dec["argmax"].cpu().numpy()
+    got_xy = np.stack([am_idx % W, am_idx // W], -1)
+    assert (np.abs(got_xy[unambiguous] - nearest[unambiguous]) <= 1).all()
+    deep = unambiguous & (hm_kp[..., 0] >= 8) & (hm_kp[..., 0] <= W - 9) & (hm_kp[..., 1] >= 8) & (hm_kp[..., 1] <= H - 9)
+    assert (np.abs(dark["locs"].cpu().numpy()[deep] - hm_kp[deep]) < 0.1).all()  # DARK recovers the sub-pixel position
+    dead = vis < 0.5
+    assert (peaks[dead] == -1).all() and (dark["scores"].cpu().numpy()[dead] == 0).all()
+    # loss of the target against itself: closed form check of the fused kernel on the full batch
+    mod = pp.OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus", check_target=False)
+    o = hm.clone().requires_grad_(True)
+    l = mod.forward_mean(o, hm, enc["keypoint_weights"])
+    l.backward()
+    assert torch.isfinite(l) and torch.isfinite(o.grad).all()
+    per = mod(hm[:2], hm[:2], enc["keypoint_weights"][:2], per_pixel=True)
+    assert abs(float(per.mean()) - float(mod.forward_mean(hm[:2], hm[:2], enc["keypoint_weights"][:2]))) <= 1e-6 * abs(float(per.mean())) + 1e-12
+
+
+def test_empty_batch_and_errors(pp):
+    wl = synth.WORKLOADS[1]
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    out = pm.decode_device(torch.zeros((0, 17, 64, 48), device="cuda"))
+    assert out["locs"].shape == (0, 17, 2)
+    enc = pm.encode_batch(np.zeros((0, 17, 2), dtype=np.float32))
+    assert enc["heatmaps"].shape == (0, 17, 64, 48)
+    with pytest.raises(TypeError):
+        pm.decode_device(torch.zeros((1, 17, 64, 48), device="cuda", dtype=torch.float16))
+    with pytest.raises(IndexError):
+        pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas[:5]).decode_device(torch.zeros((1, 17, 64, 48), device="cuda"))
+
+
+def test_codec_decode_tuple(pp):
+    """Codec.decode of the model 5-tuple (codec.py:249-263) on a batch."""
+    wl = synth.WORKLOADS[2]
+    B, K = 5, 17
+    kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=71)
+    maps = _oracle_encode("argmax", wl, kps, vis)["heatmaps"]
+    rng = np.random.default_rng(72)
+    heads = [torch.from_numpy(rng.random((B, K, 1, 1), dtype=np.float32)).cuda() for _ in range(4)]
+    codec = pp.Codec(pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas))
+    (kp, sc), prob, visb, oks, err = codec.decode((torch.from_numpy(maps).cuda(), *heads))
+    assert kp.shape == (B, K, 2) and sc.shape == (B, K)
+    for a, h in ((prob, heads[0]), (visb, heads[1]), (oks, heads[2])):
+        assert a.shape == (B, 1, K) and np.array_equal(a, h.cpu().numpy().reshape(B, 1, K))
+    np.testing.assert_allclose(err, heads[3].cpu().numpy().reshape(B, 1, K) / np.sqrt(64 ** 2 + 48 ** 2), rtol=1e-7)
+    for b in range(B):
+        k_ref, s_ref = oc.decode_expected(maps[b], wl.input_size, wl.heatmap_size, wl.sigmas, conv="scipy")
+        np.testing.assert_allclose(kp[b], k_ref[0], rtol=RTOL32, atol=1e-5)
+        assert np.array_equal(sc[b], s_ref[0])
+    rec = codec.decode_device((torch.from_numpy(maps).cuda(), *heads))
+    assert rec.shape == (B, K, 7) and np.array_equal(rec[..., :2].cpu().numpy(), kp)
+    hk, hs = codec.decode_heatmap(torch.from_numpy(maps[0]).cuda())
+    assert hk.shape == (1, K, 2) and np.array_equal(hk[0], kp[0])
