@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""Benchmark of the ProbPose heatmap hot path: heatmaps/s of encode + decode + OKS loss fwd/bwd.
+
+    python bench.py --gpus N --steps K --warmup W            # product arm (CUDA, this repo)
+    python bench.py --impl reference --steps K --warmup W    # reference arm: the CPU port on host cores
+    torchrun ... bench.py --gpus N ...                       # N > 1: one rank per GPU, NCCL
+
+One *step* = one pass of the hot path over one batch of synthetic input (per GPU):
+    target encode  (keypoints -> (B,K,H,W) maps)             write 1 x HW x e
+    decode         (predicted maps -> keypoint records)      read  1 x HW x e
+    loss fwd+bwd   (read prediction + target, write grad)    read 2, write 1
+=> 5 x H x W x e algorithmic bytes per heatmap.  Rank 0 prints ONE JSON line.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "heatmaps/sec encode+decode+loss (BxKxHxW)"
+UNIT = "heatmaps/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configuration (2..5) whose shapes are used")
+    ap.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32")
+    ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set must exceed L2)")
+    ap.add_argument("--sample", type=int, default=0, help="reference arm: images per step (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying CUDA graphs")
+    return ap.parse_args()
+
+
+# =============================================================================================
+# reference arm: the oracle port (CPU restatement of the reference, checked bit-exact against it)
+# on the host cores.  This is the only place besides the tests that executes oracle/.
+# =============================================================================================
+def _cpu_chunk(job):
+    """encode -> expected-OKS decode -> loss fwd+bwd for a chunk of images, as the reference does it:
+    per-sample NumPy encode (codec.py:138), per-sample scipy convolution decode (codec.py:214) and the
+    torch-CPU loss with autograd (loss.py:428-431)."""
+    import numpy as np
+    import torch
+
+    import oracle as oc
+    from probpose_pytorch_b200 import synth
+
+    cfg, lo, hi, seed = job
+    torch.set_num_threads(1)
+    wl = synth.WORKLOADS[cfg]
+    kps, vis, _ = synth.make_keypoints(wl, batch=hi, seed=seed)
+    kps, vis = kps[lo:hi], vis[lo:hi]
+    n = hi - lo
+    t0 = time.perf_counter()
+    tgt = np.stack([oc.encode("argmax", wl.input_size, wl.heatmap_size, wl.sigmas, kps[b:b + 1], vis[b:b + 1])["heatmaps"]
+                    for b in range(n)])
+    t1 = time.perf_counter()
+    pred = np.clip(tgt * 0.8 + 0.01, 0, 1).astype(np.float32)   # stand-in prediction (not timed as encode)
+    t2 = time.perf_counter()
+    for b in range(n):
+        oc.decode_expected(pred[b], wl.input_size, wl.heatmap_size, wl.sigmas, conv="scipy")
+    t3 = time.perf_counter()
+    o = torch.from_numpy(pred).requires_grad_(True)
+    w = torch.from_numpy(vis)
+    loss = oc.oks_heatmap_loss(o, torch.from_numpy(tgt), w, per_pixel=True, smoothing_weight=0.05, oks_type="minus").mean()
+    loss.backward()
+    t4 = time.perf_counter()
+    return n, (t1 - t0), (t3 - t2), (t4 - t3)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+
+    from probpose_pytorch_b200 import synth
+
+    wl = synth.WORKLOADS[args.config]
+    cores = os.cpu_count() or 1
+    sample = args.sample or min(wl.batch, max(cores, 64))
+    ctx = mp.get_context("fork")
+
+    def one_step(pool, images, seed):
+        per = max(1, (images + cores - 1) // cores)
+        jobs = [(args.config, lo, min(images, lo + per), seed) for lo in range(0, images, per)]
+        t0 = time.perf_counter()
+        parts = pool.map(_cpu_chunk, jobs)
+        return time.perf_counter() - t0, parts
+
+    with ctx.Pool(cores) as pool:
+        t_probe, _ = one_step(pool, sample, 0)          # also warms the workers (imports)
+        t_probe, _ = one_step(pool, sample, 0)
+        budget = 150.0
+        total_steps = args.steps + args.warmup
+        if t_probe * total_steps > budget:               # keep the whole run within a few minutes
+            sample = max(cores // 2 or 1, int(sample * budget / (t_probe * total_steps)))
+        for i in range(args.warmup):
+            one_step(pool, sample, i)
+        t0 = time.perf_counter()
+        enc = dec = los = 0.0
+        for i in range(args.steps):
+            _, parts = one_step(pool, sample, 100 + i)
+            enc += sum(p[1] for p in parts); dec += sum(p[2] for p in parts); los += sum(p[3] for p in parts)
+        dt = time.perf_counter() - t0
+    hms = sample * wl.num_keypoints * args.steps
+    value = hms / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (f64 encode/convolution)", "data": "synthetic",
+        "config": {"workload": wl.name, "heatmap": list(wl.heatmap_size), "keypoints": wl.num_keypoints,
+                   "images_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} images x {wl.num_keypoints} keypoints per step, {args.steps} steps; "
+                                   "oracle port (NumPy encode, scipy.ndimage decode, torch-CPU loss+autograd), "
+                                   f"{cores} worker processes",
+                         "cpu_seconds_split": {"encode": enc, "decode": dec, "loss": los}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# =============================================================================================
+# product arm
+# =============================================================================================
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the GPU is being timed."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.mark = index, [], False, None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.samples.append((time.perf_counter(), mhz, reasons, util, self.mark))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        timed = [s for s in self.samples if s[4] == "timed"]
+        pool = timed or [s for s in self.samples if s[4] is not None] or self.samples
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost",
+                 0x100: "display_clock_setting"}
+        seen = set()
+        for s in pool:
+            for bit, name in names.items():
+                if s[2] & bit:
+                    seen.add(name)
+        return {"sm_mhz": statistics.median(s[1] for s in pool), "sm_max_mhz": self.max_mhz, "reasons": sorted(seen),
+                "samples": len(pool), "window": "timed region" if timed else "whole measurement phase"}
+
+
+def run_product(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import probpose_pytorch_b200 as pp
+    from probpose_pytorch_b200 import _lib, synth
+    from probpose_pytorch_b200 import distributed as ppd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (product arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    wl = synth.WORKLOADS[args.config]
+    B, K = wl.batch, wl.num_keypoints            # per-GPU batch: weak scaling (C3 = 128 images per GPU)
+    if args.config == 3:
+        B = wl.batch // 8
+    W, H = wl.heatmap_size
+    tdtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    esize = 4 if args.dtype == "fp32" else 2
+    hm_bytes = H * W * esize
+    n_hm = B * K
+
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    codec = pp.Codec(pm)
+    loss_fn = pp.OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus", check_target=False)
+
+    # ---- synthetic inputs: `sets` distinct buffer sets so that consecutive steps never find their
+    # inputs in L2 (per set: prediction + target + gradient = 3 x B*K*H*W*e bytes)
+    sets = []
+    rng = np.random.default_rng(1000 + args.config + 17 * rank)
+    for s in range(args.sets):
+        kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=1000 + args.config + 97 * rank + s)
+        kps_d = torch.from_numpy(kps).to(dev)
+        vis_d = torch.from_numpy(vis).to(dev)
+        jit = torch.from_numpy(synth.jitter_keypoints(wl, kps, seed=5000 + s)).to(dev)
+        blob = am.encode_batch(jit, vis_d)["heatmaps"]
+        amp = torch.from_numpy(synth.blob_params((B, K), seed=6000 + s)).to(dev)
+        noise = torch.rand(blob.shape, device=dev) * 0.02
+        pred = (blob * amp[:, :, None, None] + noise).clamp_(0, 1).to(tdtype).contiguous()
+        heads = [torch.rand((B, K, 1, 1), device=dev) for _ in range(4)]
+        sets.append(dict(kps=kps_d, vis=vis_d, pred=pred, heads=heads, kps_host=torch.from_numpy(kps).pin_memory(),
+                         vis_host=torch.from_numpy(vis).pin_memory(), pred_host=pred.cpu().pin_memory()))
+        del blob, noise
+    set_bytes = 3 * n_hm * hm_bytes
+    torch.cuda.synchronize()
+
+    def step_device(s):
+        """The hot path on device-resident inputs."""
+        enc = am.encode_batch(s["kps"], s["vis"], dtype=tdtype)
+        rec = codec.decode_device((s["pred"], *s["heads"]))
+        out = s["pred"].detach().requires_grad_(True)
+        loss = loss_fn.forward_mean(out, enc["heatmaps"], enc["keypoint_weights"])
+        loss.backward()
+        return rec, loss.detach(), out.grad
+
+    # ---- CUDA graphs of the step, one per buffer set
+    graphs, results = [], []
+    use_graph = not args.no_graph
+    for s in sets:
+        for _ in range(2):
+            step_device(s)
+    torch.cuda.synchronize()
+    if use_graph:
+        for s in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                results.append(step_device(s))
+            graphs.append(g)
+        torch.cuda.synchronize()
+
+    def run_step(i):
+        j = i % len(sets)
+        if use_graph:
+            graphs[j].replay()
+            rec, loss, _ = results[j]
+        else:
+            rec, loss, _ = step_device(sets[j])
+        if world > 1:   # the only exchange on the path: keypoint records + loss partial (one collective)
+            return ppd.exchange_step_results(rec, loss)
+        return rec, loss
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.mark = "warm"
+    for i in range(max(args.warmup, 3)):
+        run_step(i)
+    torch.cuda.synchronize()
+
+    # ---- timed region: EXACTLY args.steps steps, barrier + synchronize on both sides
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.mark = "timed"
+    ev0.record()
+    for i in range(args.steps):
+        run_step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.mark = "post"
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    value = world * n_hm * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timings (CUDA events on the launching stream, same rotating sets)
+    def time_kernel(fn, iters):
+        for i in range(3):
+            fn(sets[i % len(sets)])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            fn(sets[i % len(sets)])
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / iters
+
+    targets = [am.encode_batch(s["kps"], s["vis"], dtype=tdtype) for s in sets]
+    for s, t in zip(sets, targets):
+        s["tgt"], s["w"] = t["heatmaps"], t["keypoint_weights"]
+    grads = [torch.empty_like(s["pred"]) for s in sets]
+
+    def k_encode(s):
+        am.encode_batch(s["kps"], s["vis"], dtype=tdtype)
+
+    def k_decode(s):
+        pm.decode_device(s["pred"])
+
+    def k_dark(s):
+        am.decode_device(s["pred"])
+
+    prep_cache = {}
+
+    def k_loss(s):
+        from probpose_pytorch_b200.loss import _Prepared
+        key = id(s)
+        if key not in prep_cache:
+            prep_cache[key] = _Prepared(loss_fn, s["pred"], s["tgt"], s["w"], None, _lib.PP_LOSS_PIXEL_MEAN)
+        prep_cache[key].forward(want_grad=True)
+
+    sampler.mark = "kernels"
+    iters = max(20, min(200, args.steps))
+    kt = {"encode": time_kernel(k_encode, iters), "decode_expected": time_kernel(k_decode, iters),
+          "decode_dark": time_kernel(k_dark, iters), "loss_fwd_bwd": time_kernel(k_loss, iters)}
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    alg = {"encode": 1, "decode_expected": 1, "decode_dark": 1, "loss_fwd_bwd": 3}
+    kernels = {k: {"ms": 1e3 * t, "GBps": alg[k] * n_hm * hm_bytes / t / 1e9,
+                   "frac": alg[k] * n_hm * hm_bytes / t / 1e9 / peak,
+                   "heatmaps_per_s": n_hm / t} for k, t in kt.items()}
+    dom = "loss_fwd_bwd"
+    traffic = None
+    tfile = ROOT / "profiles" / "traffic.json"
+    if tfile.exists():
+        traffic = json.loads(tfile.read_text()).get(f"{dom}/C{args.config}/{args.dtype}")
+    roofline = {"bound": "hbm", "kernel": "oks_loss_kernel (fused OKS loss forward+backward)",
+                "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": 3 * n_hm * hm_bytes,
+                "step": {"GBps": 5 * n_hm * hm_bytes * args.steps / (ms * 1e-3) / 1e9,
+                         "frac": 5 * n_hm * hm_bytes * args.steps / (ms * 1e-3) / 1e9 / peak,
+                         "note": "whole step, 5 x H x W x e bytes per heatmap"}}
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D of the step's inputs,
+    # D2H of the decoded records and the loss value inside the timed region
+    def step_e2e(s):
+        kps = s["kps_host"].to(dev, non_blocking=True)
+        vis = s["vis_host"].to(dev, non_blocking=True)
+        pred = s["pred_host"].to(dev, non_blocking=True)
+        enc = am.encode_batch(kps, vis, dtype=tdtype)
+        rec = codec.decode_device((pred, *s["heads"]))
+        out = pred.requires_grad_(True)
+        loss = loss_fn.forward_mean(out, enc["heatmaps"], enc["keypoint_weights"])
+        loss.backward()
+        rec_h = rec.cpu()
+        return rec_h, float(loss)
+
+    sampler.mark = "e2e"
+    e2e_steps = max(5, min(50, args.steps))
+    for i in range(3):
+        step_e2e(sets[i % len(sets)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_e2e(sets[i % len(sets)])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
+    s0 = sets[0]
+    h2d = s0["pred_host"].numel() * s0["pred_host"].element_size() + s0["kps_host"].numel() * 4 + s0["vis_host"].numel() * 4
+    d2h = n_hm * 7 * 8 + 4
+    e2e = {"value": world * n_hm * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": e2e_steps, "note": "public API (encode_batch, Codec.decode_device, OKSHeatmapLoss.forward_mean+backward) "
+                                       "on pinned host buffers"}
+
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    clocks = sampler.summary()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                   "--config", str(args.config)]
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            ref = json.loads(res.stdout.strip().splitlines()[-1])
+            cpu_baseline = ref["cpu_baseline"]
+        except Exception as e:  # pragma: no cover
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+
+    if rank == 0:
+        launches_per_step = 5   # encode, decode, loss, loss finalize, grad-scale check
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (f64 for the encode exponentials and the exact argmax check)" if args.dtype == "fp32" else "bf16 storage, f32 arithmetic",
+            "data": "synthetic",
+            "config": {"workload": wl.name + " -- heatmap path only (encode + expected-OKS decode + OKS loss fwd/bwd); "
+                                             "the ViT backbone is not on the path",
+                       "batch_per_gpu": B, "keypoints": K, "heatmap": [W, H], "heatmaps_per_step_per_gpu": n_hm,
+                       "l2": f"rotating {args.sets} buffer sets x {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
+                       "launch": "CUDA graph replay" if use_graph else "eager",
+                       "parallelism": f"dp{world} (batch sharded by image)"},
+            "roofline": roofline, "kernels": kernels, "e2e": e2e, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_product(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing of the heatmap path: one process per GPU, batch sharded by image.
+
+Every (b, k) heatmap is independent in encode and decode, and the loss is a sum over
+heatmaps, so there is no data-path collective.  The only exchanges are
+  * the loss all-reduce (a few floats), and
+  * the gather of the decoded keypoint records (B/G x K x 7 values per rank),
+both latency-bound over NVLink/NVSwitch.  ``exchange_step_results`` folds them into ONE
+``all_gather`` per step (the loss partial rides in the same buffer), which halves the
+collective launch latency of small steps.  torch.distributed is used as plumbing (NCCL on
+GPUs, gloo in the CPU tests).
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def world() -> tuple[int, int]:
+    """(world_size, rank); (1, 0) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def shard_bounds(batch: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous split of ``batch`` images over ``world_size`` ranks (earlier ranks take the remainder)."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    base, rem = divmod(batch, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(t, world_size: int | None = None, rank: int | None = None):
+    """This rank's contiguous slice (by image) of a global batch tensor / array."""
+    ws, rk = world()
+    ws = ws if world_size is None else world_size
+    rk = rk if rank is None else rank
+    lo, hi = shard_bounds(len(t), ws, rk)
+    return t[lo:hi]
+
+
+def all_reduce_loss(loss_sum: Tensor, count: int | Tensor) -> Tensor:
+    """Global mean loss from per-rank partial sums: all-reduce(SUM) of (sum, count)."""
+    buf = torch.stack([loss_sum.detach().reshape(()).double(),
+                       torch.as_tensor(count, dtype=torch.float64, device=loss_sum.device).reshape(())])
+    if world()[0] > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return (buf[0] / buf[1]).to(loss_sum.dtype)
+
+
+def all_gather_keypoints(records: Tensor) -> Tensor:
+    """Gather per-rank keypoint records (B_local, K, C) into (sum B_local, K, C), rank order.
+    Ranks may hold different B_local (ragged split): shorter shards are padded for the collective."""
+    ws, _ = world()
+    if ws == 1:
+        return records
+    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
+    sizes = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s) for s in sizes]
+    m = max(sizes)
+    if records.shape[0] < m:
+        pad = records.new_zeros((m - records.shape[0],) + tuple(records.shape[1:]))
+        records = torch.cat([records, pad])
+    out = records.new_empty((ws * m,) + tuple(records.shape[1:]))
+    dist.all_gather_into_tensor(out.view(-1), records.contiguous().view(-1))
+    if all(s == m for s in sizes):
+        return out
+    return torch.cat([out[r * m: r * m + s] for r, s in enumerate(sizes)])
+
+
+def exchange_step_results(records: Tensor, loss_mean_local: Tensor) -> tuple[Tensor, Tensor]:
+    """One collective per step: every rank contributes its (B_local, K, C) records and its local
+    mean loss (equal B_local on all ranks); returns the gathered records and the global mean loss."""
+    ws, _ = world()
+    if ws == 1:
+        return records, loss_mean_local
+    flat = torch.cat([records.reshape(-1), loss_mean_local.detach().reshape(1).to(records.dtype)])
+    out = flat.new_empty(ws * flat.numel())
+    dist.all_gather_into_tensor(out, flat)
+    out = out.view(ws, flat.numel())
+    rec = out[:, :-1].reshape((ws * records.shape[0],) + tuple(records.shape[1:]))
+    return rec, out[:, -1].mean().to(loss_mean_local.dtype)
