@@ -54,8 +54,9 @@ def encode_device(keypoints: Tensor, visible: Tensor | None, divisors: Tensor, h
     }
     inside = ann = None
     if flags:
-        inside = torch.empty((B, K), dtype=torch.uint8, device=dev)
-        ann = torch.empty((B, K), dtype=torch.uint8, device=dev)
+        # torch.bool is one byte holding 0/1, which is exactly what the kernel writes
+        inside = torch.empty((B, K), dtype=torch.bool, device=dev)
+        ann = torch.empty((B, K), dtype=torch.bool, device=dev)
     p = _lib.EncodeParams(B, K, H, W, _lib.dtype_code(dtype), _lib.dtype_code(kp.dtype), D,
                           float(scale_factor[0]), float(scale_factor[1]), float(input_size[0]), float(input_size[1]))
     assert divisors.dtype == torch.float64 and divisors.numel() >= K and divisors.device == dev
@@ -65,8 +66,8 @@ def encode_device(keypoints: Tensor, visible: Tensor | None, divisors: Tensor, h
                                   _lib.stream_ptr(dev))
     _lib.check(rc, "pp_encode")
     if flags:
-        out["in_image"] = inside.bool()
-        out["annotated"] = ann.bool()
+        out["in_image"] = inside
+        out["annotated"] = ann
     return out
 
 

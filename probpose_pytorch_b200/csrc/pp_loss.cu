@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "pp_common.cuh"
+#include "pp_loss_fast.cuh"
 
 namespace {
 
@@ -263,6 +264,69 @@ int launch_loss(const LossArgs& a, bool fwd, bool grad, cudaStream_t st) {
   return PP_OK;
 }
 
+// ---- fast path dispatch (pp_loss_fast.cuh) ---------------------------------------------------
+bool fast_path_ok(const pp_loss_params& p, const void* output, const void* target, const void* pixel_weights,
+                  const void* mask, const void* grad) {
+  const int e = p.dtype == PP_F32 ? 4 : 2;
+  return p.mode == PP_LOSS_PIXEL_MEAN && !pixel_weights && !mask && !p.skip_empty_channel && p.W % 4 == 0 &&
+         p.W / 4 <= 128 && (static_cast<int64_t>(p.H) * p.W * e) % 16 == 0 && pp_aligned16(output) &&
+         pp_aligned16(target) && pp_aligned16(grad) &&
+         static_cast<int64_t>(p.H) * p.W * e + 160 <= pp_smem_optin();
+}
+
+template <typename T, bool kFwd, bool kGrad>
+int launch_fast_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
+  int per_sm = 1;
+  auto kern = pp_loss_fast::oks_loss_fast_kernel<T, kFwd, kGrad>;
+  if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), threads, smem, &per_sm)) return rc;
+  const int grid = static_cast<int>(std::min<int64_t>(a.N, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  kern<<<grid, threads, smem, st>>>(a);
+  PP_CUDA_OK(cudaGetLastError());
+  *grid_out = grid;
+  return PP_OK;
+}
+
+// Runs the fused mean-mode kernel; *grid_out = number of per-CTA partial sums written (forward).
+int launch_fast(const pp_loss_params& p, const void* output, const void* target, const float* kp_weights, void* grad,
+                double* partials, int32_t* range_flag, const float* upstream, float host_scale, bool fwd,
+                cudaStream_t st, int* grid_out) {
+  pp_loss_fast::FastArgs a{};
+  const int e = p.dtype == PP_F32 ? 4 : 2;
+  a.output = output; a.target = target; a.kp_weights = kp_weights; a.grad = grad; a.partials = partials;
+  a.range_flag = range_flag; a.upstream = upstream; a.host_scale = host_scale;
+  a.N = static_cast<long long>(p.B) * p.K;
+  a.H = p.H; a.W = p.W;
+  a.strips = p.W / 4;
+  int segs = std::max(1, std::min(p.H / 4 > 0 ? p.H / 4 : 1, (112 + a.strips / 2) / a.strips));
+  a.T = (p.H + segs - 1) / segs;
+  a.segs = (p.H + a.T - 1) / a.T;
+  while (a.strips * a.segs > 256) { a.T *= 2; a.segs = (p.H + a.T - 1) / a.T; }
+  a.w_s = static_cast<float>(p.smoothing_weight);
+  a.w_g = static_cast<float>(p.gaussian_weight);
+  a.w_o = static_cast<float>(1.0 - p.smoothing_weight - p.gaussian_weight);
+  a.lw = static_cast<float>(p.loss_weight);
+  // oks = a_o o + a_t t - o t ;  d oks / d o = d_a + d_b t   (loss.py:92-99)
+  if (p.oks_type == 0) { a.a_o = 1.f; a.a_t = 0.f; a.d_a = 1.f; a.d_b = -1.f; }
+  else if (p.oks_type == 1) { a.a_o = 0.f; a.a_t = 1.f; a.d_a = 0.f; a.d_b = -1.f; }
+  else { a.a_o = 0.5f; a.a_t = 0.5f; a.d_a = 0.5f; a.d_b = -1.f; }
+  a.inv_count = static_cast<float>(1.0 / (static_cast<double>(a.N) * p.H * p.W));
+  a.plane_bytes = static_cast<unsigned>(static_cast<int64_t>(p.H) * p.W * e);
+  a.stage_bytes = (a.plane_bytes + 32 + 127) / 128 * 128;
+  a.stages = (2ull * a.stage_bytes <= static_cast<size_t>(pp_smem_optin()) / 2) ? 2 : 1;
+  if (static_cast<size_t>(a.stages) * a.stage_bytes > static_cast<size_t>(pp_smem_optin())) a.stages = 1;
+  const size_t smem = static_cast<size_t>(a.stages) * a.stage_bytes;
+  const int threads = a.strips * a.segs;
+  const bool g = grad != nullptr;
+  if (p.dtype == PP_F32) {
+    if (fwd && g) return launch_fast_t<float, true, true>(a, threads, smem, st, grid_out);
+    if (fwd) return launch_fast_t<float, true, false>(a, threads, smem, st, grid_out);
+    return launch_fast_t<float, false, true>(a, threads, smem, st, grid_out);
+  }
+  if (fwd && g) return launch_fast_t<__nv_bfloat16, true, true>(a, threads, smem, st, grid_out);
+  if (fwd) return launch_fast_t<__nv_bfloat16, true, false>(a, threads, smem, st, grid_out);
+  return launch_fast_t<__nv_bfloat16, false, true>(a, threads, smem, st, grid_out);
+}
+
 }  // namespace
 
 extern "C" {
@@ -290,6 +354,18 @@ int pp_oks_loss_forward(const pp_loss_params* p, const void* output, const void*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t N = static_cast<int64_t>(p->B) * p->K;
   if (N == 0) return PP_OK;
+
+  if (fast_path_ok(*p, output, target, pixel_weights, mask, grad)) {
+    if (target_out_of_range) PP_CUDA_OK(cudaMemsetAsync(target_out_of_range, 0, sizeof(int32_t), st));
+    int parts = 0;
+    if (int rc = launch_fast(*p, output, target, keypoint_weights, grad, static_cast<double*>(scratch),
+                             target_out_of_range, nullptr, grad_scale, true, st, &parts))
+      return rc;
+    finalize_kernel<<<1, 256, 0, st>>>(static_cast<double*>(scratch), parts, 1.0 / (static_cast<double>(N) * p->H * p->W),
+                                       loss_scalar);
+    PP_CUDA_OK(cudaGetLastError());
+    return PP_OK;
+  }
 
   LossArgs a{};
   a.p = *p;
@@ -322,6 +398,11 @@ int pp_oks_loss_backward(const pp_loss_params* p, const void* output, const void
              "pp_oks_loss_backward: peak_index required for PP_LOSS_PER_KEYPOINT");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (static_cast<int64_t>(p->B) * p->K == 0) return PP_OK;
+  if (upstream_kind == PP_UPSTREAM_SCALAR && fast_path_ok(*p, output, target, pixel_weights, mask, grad)) {
+    int parts = 0;
+    return launch_fast(*p, output, target, keypoint_weights, grad, nullptr, nullptr, static_cast<const float*>(upstream),
+                       1.0f, false, st, &parts);
+  }
   LossArgs a{};
   a.p = *p;
   a.output = output; a.target = target; a.kp_weights = keypoint_weights; a.pix_weights = pixel_weights; a.mask = mask;

@@ -1,0 +1,295 @@
+// Fast path of the OKS heatmap loss: mean-per-pixel mode with per-heatmap weights (what
+// ProbPoseLoss does with OKSHeatmapLoss, loss.py:428-431), forward + backward in one pass.
+//
+// HBM-bound by design: read `output` and `target` once, write `grad` once = 3 H W e bytes per heatmap.
+// To stay under the ~66 instructions / pixel that the HBM roofline allows at fp32, the 3x3 Sobel
+// stencil and its adjoint are evaluated with a register-rolling row pipeline:
+//
+//   * a persistent CTA pulls whole `output` heatmaps (contiguous H*W*e bytes) into shared memory with
+//     1-D bulk async copies (TMA, cp.async.bulk + mbarrier), double buffered, so the next heatmap lands
+//     while the current one is processed;
+//   * a thread owns a strip 4 pixels wide and T rows tall.  Per row it reads 8 values of `output`
+//     (the strip plus a 2-pixel halo) from shared memory, forms the separable row factors of the
+//     Sobel pair (d = a[x-1]-a[x+1], s = a[x-1]+2a[x]+a[x+1]) for 6 columns, combines three rows into
+//     gx, gy, scales them into P = 2 c gx, Q = 2 c gy, forms the row factors of the adjoint stencil
+//     and, three rows later, emits one 128-bit gradient store.  The 1-pixel ring of gx/gy a strip needs
+//     from its neighbours is recomputed instead of exchanged, so there is no shared-memory write and no
+//     barrier inside a heatmap;
+//   * `target` is read straight from global memory with 128-bit streaming loads, two rows ahead of use.
+#pragma once
+
+#include "pp_common.cuh"
+
+namespace pp_loss_fast {
+
+using namespace pp;
+
+struct FastArgs {
+  const void* output;
+  const void* target;
+  const float* kp_weights;   // (N) or null
+  void* grad;                // (N, H, W) or null
+  double* partials;          // one per CTA (forward)
+  int32_t* range_flag;       // or null
+  const float* upstream;     // device scalar or null
+  float host_scale;
+  long long N;
+  int H, W, strips, segs, T, stages;
+  float w_s, w_o, w_g, lw;
+  float a_o, a_t;            // oks(o, t) = a_o o + a_t t - o t
+  float d_a, d_b;            // d oks / d o = d_a + d_b t
+  float inv_count;           // 1 / (N H W)
+  unsigned plane_bytes, stage_bytes;
+};
+
+struct RowState {
+  float hd[3][6], hs[3][6];  // row factors of the Sobel pair, rows r-2, r-1, r
+  float dP[3][4], sQ[3][4];  // row factors of the adjoint stencil, rows r-3, r-2, r-1
+  float oc[3][4];            // `output` at the strip, rows r-2, r-1, r
+  float tt[3][4];            // `target` at the strip, rows r-2, r-1, r
+};
+
+template <typename T>
+__device__ __forceinline__ void load_strip8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load_strip8<float>(const float* p, float (&v)[8]) {
+  const float2 l = *reinterpret_cast<const float2*>(p - 2);
+  const float4 c = *reinterpret_cast<const float4*>(p);
+  const float2 r = *reinterpret_cast<const float2*>(p + 4);
+  v[0] = l.x; v[1] = l.y; v[2] = c.x; v[3] = c.y; v[4] = c.z; v[5] = c.w; v[6] = r.x; v[7] = r.y;
+}
+template <>
+__device__ __forceinline__ void load_strip8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint32_t l = *reinterpret_cast<const uint32_t*>(p - 2);
+  const uint2 c = *reinterpret_cast<const uint2*>(p);
+  const uint32_t r = *reinterpret_cast<const uint32_t*>(p + 4);
+  v[0] = __uint_as_float(l << 16); v[1] = __uint_as_float(l & 0xffff0000u);
+  v[2] = __uint_as_float(c.x << 16); v[3] = __uint_as_float(c.x & 0xffff0000u);
+  v[4] = __uint_as_float(c.y << 16); v[5] = __uint_as_float(c.y & 0xffff0000u);
+  v[6] = __uint_as_float(r << 16); v[7] = __uint_as_float(r & 0xffff0000u);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_target4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load_target4<float>(const float* p, float (&v)[4]) {
+  const uint4 w = ldg_stream_128(p);
+  v[0] = __uint_as_float(w.x); v[1] = __uint_as_float(w.y); v[2] = __uint_as_float(w.z); v[3] = __uint_as_float(w.w);
+}
+template <>
+__device__ __forceinline__ void load_target4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  uint2 w;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p));
+  v[0] = __uint_as_float(w.x << 16); v[1] = __uint_as_float(w.x & 0xffff0000u);
+  v[2] = __uint_as_float(w.y << 16); v[3] = __uint_as_float(w.y & 0xffff0000u);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_grad4(T* p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void store_grad4<float>(float* p, const float (&v)[4]) {
+  stg_stream_128(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+}
+template <>
+__device__ __forceinline__ void store_grad4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  const uint32_t x = *reinterpret_cast<uint32_t*>(&a), y = *reinterpret_cast<uint32_t*>(&b);
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+
+struct Coef {
+  float c2;            // 2 lw w_s u m   (P = c2 gx, Q = c2 gy)
+  float k_a, k_b, k_g; // direct gradient = k_a + k_b t + k_g (o - t)
+  float a_o, a_t;
+  bool has_mse;
+};
+
+struct Sums {
+  float se, so, sm, tmin, tmax;
+};
+
+// One row step of the pipeline; PH = step index mod 3 selects the rotating register slots.
+template <typename T, bool kFwd, bool kGrad, int PH>
+__device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& cf, int q, int y0, int y1, int H, int W,
+                                         int x0, bool left_ok, bool right_ok, const T* __restrict__ plane,
+                                         const T* __restrict__ tgt, T* __restrict__ grad) {
+  constexpr int cur = PH, p1 = (PH + 2) % 3, p2 = (PH + 1) % 3;  // rows r, r-1, r-2 (and r-3 == cur for dP/sQ)
+  const int r = y0 - 2 + q;
+
+  // 1. row r of `output` -> row factors of the Sobel pair at columns x0-1 .. x0+4
+  float av[8];
+  if (r >= 0 && r < H) {
+    load_strip8<T>(plane + r * W + x0, av);
+    if (!left_ok) { av[0] = 0.0f; av[1] = 0.0f; }
+    if (!right_ok) { av[6] = 0.0f; av[7] = 0.0f; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) av[j] = 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    st.hd[cur][j] = av[j] - av[j + 2];
+    st.hs[cur][j] = (av[j] + av[j + 2]) + 2.0f * av[j + 1];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st.oc[cur][i] = av[2 + i];
+  if (r >= y0 && r < y1) load_target4<T>(tgt + r * W + x0, st.tt[cur]);  // consumed two steps later
+
+  // 2. gx, gy at row r-1, columns x0-1 .. x0+4
+  const int rm = r - 1;
+  float gx[6], gy[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    gx[j] = (st.hd[p2][j] + st.hd[cur][j]) + 2.0f * st.hd[p1][j];
+    gy[j] = st.hs[p2][j] - st.hs[cur][j];
+  }
+  if (kFwd && rm >= y0 && rm < y1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sums.se += gx[1 + i] * gx[1 + i] + gy[1 + i] * gy[1 + i];
+  }
+  if (kGrad) {
+    const float cr = (rm >= 0 && rm < H) ? cf.c2 : 0.0f;
+    float P[6], Q[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { P[j] = cr * gx[j]; Q[j] = cr * gy[j]; }
+    if (!left_ok) { P[0] = 0.0f; Q[0] = 0.0f; }     // column -1 is outside the map
+    if (!right_ok) { P[5] = 0.0f; Q[5] = 0.0f; }    // column W is outside the map
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      st.dP[p1][i] = P[i] - P[i + 2];
+      st.sQ[p1][i] = (Q[i] + Q[i + 2]) + 2.0f * Q[i + 1];
+    }
+  }
+
+  // 3. emit row r-2
+  const int ro = r - 2;
+  if (ro >= y0 && ro < y1) {
+    float g[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float o = st.oc[p2][i], t = st.tt[p2][i];
+      if (kFwd) {
+        sums.so += cf.a_o * o + cf.a_t * t - o * t;
+        if (cf.has_mse) { const float d = o - t; sums.sm += d * d; }
+        sums.tmin = fminf(sums.tmin, t);
+        sums.tmax = fmaxf(sums.tmax, t);
+      }
+      if (kGrad) {
+        float direct = cf.k_a + cf.k_b * t;
+        if (cf.has_mse) direct += cf.k_g * (o - t);
+        const float sx = (st.dP[cur][i] + st.dP[p1][i]) + 2.0f * st.dP[p2][i];  // rows r-3, r-1, r-2
+        const float sy = st.sQ[cur][i] - st.sQ[p1][i];                           // rows r-3, r-1
+        g[i] = (direct - sx) - sy;
+      }
+    }
+    if (kGrad) store_grad4<T>(grad + ro * W + x0, g);
+  }
+}
+
+template <typename T, bool kFwd, bool kGrad>
+__global__ void __launch_bounds__(256)
+oks_loss_fast_kernel(FastArgs a) {
+  extern __shared__ __align__(128) unsigned char stage_mem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ double red[8];
+  __shared__ int red_flag;
+
+  const int tid = threadIdx.x;
+  const int H = a.H, W = a.W;
+  const long long HW = static_cast<long long>(H) * W;
+  const int sx = tid % a.strips, sy = tid / a.strips;
+  const int x0 = sx * 4, y0 = sy * a.T, y1 = min(y0 + a.T, H);
+  const bool left_ok = sx > 0, right_ok = sx < a.strips - 1;
+  const T* out = static_cast<const T*>(a.output);
+  const T* tgt_all = static_cast<const T*>(a.target);
+  T* grad_all = static_cast<T*>(a.grad);
+  // 16 bytes of slack in front of / behind each plane keep the halo reads of the first / last strip in bounds
+  auto plane_of = [&](int s) { return reinterpret_cast<const T*>(stage_mem + static_cast<size_t>(s) * a.stage_bytes + 16); };
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    red_flag = 0;
+  }
+  __syncthreads();
+
+  float u = a.host_scale * a.inv_count;
+  if (kGrad && a.upstream) u *= a.upstream[0];
+
+  long long hm = blockIdx.x;
+  if (tid == 0 && hm < a.N) {
+    mbar_expect_tx(&bars[0], a.plane_bytes);
+    tma_load_1d(const_cast<T*>(plane_of(0)), out + hm * HW, a.plane_bytes, &bars[0]);
+  }
+
+  double acc = 0.0;
+  Sums sums{0.f, 0.f, 0.f, INFINITY, -INFINITY};
+  const int nsteps = (y1 - y0) + 4;
+
+  for (int it = 0; hm < a.N; hm += gridDim.x, ++it) {
+    const int s = (a.stages == 2) ? (it & 1) : 0;
+    const long long nxt = hm + gridDim.x;
+    if (a.stages == 2 && tid == 0 && nxt < a.N) {  // prefetch the next heatmap into the other stage
+      mbar_expect_tx(&bars[s ^ 1], a.plane_bytes);
+      tma_load_1d(const_cast<T*>(plane_of(s ^ 1)), out + nxt * HW, a.plane_bytes, &bars[s ^ 1]);
+    }
+    const float m = a.kp_weights ? a.kp_weights[hm] : 1.0f;
+    Coef cf;
+    cf.c2 = 2.0f * a.lw * a.w_s * u * m;
+    cf.k_a = a.lw * u * m * a.w_o * a.d_a;
+    cf.k_b = a.lw * u * m * a.w_o * a.d_b;
+    cf.k_g = 2.0f * a.lw * u * m * a.w_g;
+    cf.a_o = a.a_o; cf.a_t = a.a_t;
+    cf.has_mse = a.w_g != 0.0f;
+
+    const T* tgt = tgt_all + hm * HW;
+    T* grad = kGrad ? grad_all + hm * HW : nullptr;
+    RowState st;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { st.hd[i][j] = 0.f; st.hs[i][j] = 0.f; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { st.dP[i][j] = 0.f; st.sQ[i][j] = 0.f; st.oc[i][j] = 0.f; st.tt[i][j] = 0.f; }
+    }
+    sums.se = sums.so = sums.sm = 0.f;
+
+    mbar_wait(&bars[s], (a.stages == 2) ? ((it >> 1) & 1) : (it & 1));
+    const T* plane = plane_of(s);
+    if (sy < a.segs) {
+      for (int q = 0; q < nsteps; q += 3) {
+        row_step<T, kFwd, kGrad, 0>(st, sums, cf, q, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+        if (q + 1 < nsteps)
+          row_step<T, kFwd, kGrad, 1>(st, sums, cf, q + 1, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+        if (q + 2 < nsteps)
+          row_step<T, kFwd, kGrad, 2>(st, sums, cf, q + 2, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+      }
+    }
+    if (kFwd) {
+      // per-pixel loss = (w_s e + w_o oks + w_g mse) m lw (loss.py:122-127, 143), summed per strip
+      const float part = (a.w_s * sums.se + a.w_o * sums.so + a.w_g * sums.sm) * (m * a.lw);
+      acc += static_cast<double>(part);
+    }
+    __syncthreads();  // every thread is done with stage s before it is refilled
+    if (a.stages == 1 && tid == 0 && nxt < a.N) {
+      mbar_expect_tx(&bars[0], a.plane_bytes);
+      tma_load_1d(const_cast<T*>(plane_of(0)), out + nxt * HW, a.plane_bytes, &bars[0]);
+    }
+  }
+
+  if (kFwd) {
+    acc = warp_sum(acc);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    if (a.range_flag && (sums.tmin < 0.0f || sums.tmax > 1.0f)) red_flag = 1;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+      a.partials[blockIdx.x] = t;
+      if (a.range_flag && red_flag) atomicOr(a.range_flag, 1);
+    }
+  }
+}
+
+}  // namespace pp_loss_fast
