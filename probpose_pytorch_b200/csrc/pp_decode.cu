@@ -296,7 +296,7 @@ template <typename T>
 __global__ void __launch_bounds__(512)
 decode_expected_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict__ heatmaps, float* __restrict__ locs,
                        float* __restrict__ vals, int32_t* __restrict__ argmax, double* __restrict__ keypoints,
-                       bool vector_ok) {
+                       bool vector_ok, bool only_marked) {
   extern __shared__ __align__(16) float smem[];
   __shared__ BlockScratch bs;
   __shared__ float taps[PP_OKS_TAPS];
@@ -310,6 +310,8 @@ decode_expected_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 
   for (int64_t hm = blockIdx.x; hm < N; hm += gridDim.x) {
+    // second launch after the pruned kernel: only the heatmaps it marked (NaN in locs) are left
+    if (only_marked && !isnan(locs[hm * 2])) continue;
     const int k = static_cast<int>(hm % p.K);
     const int r = tab.radius[k];
     const double* w2d = tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
@@ -416,6 +418,8 @@ decode_expected_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict
     __syncthreads();  // shared planes / scratch are reused by the next heatmap
   }
 }
+
+#include "pp_decode_fast.cuh"
 
 // ---------------------------------------------------------------------------
 // generic exact path: full convolved map (return_heatmap=True, or maps too large for shared memory)
@@ -699,10 +703,27 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   }
   const bool vec = (p.W % Elem<T>::kVec == 0) && pp_aligned16(heatmaps);
   const int threads = pick_threads(p.H, p.W);
+
+  // pruned kernel first (TMA-staged, convolution only around {h >= L}); it marks what it defers
+  const size_t plane_bytes = sizeof(T) * static_cast<size_t>(p.H) * p.W;
+  const size_t tile_off = (plane_bytes + 127) / 128 * 128;
+  const size_t fsmem = tile_off + sizeof(float) * (kFTileRows * kFTileStride + kFTmpRows * kFTmpStride);
+  const bool fast = plane_bytes % 16 == 0 && pp_aligned16(heatmaps) && (!p.apply_tail || p.temperature > 0.0f) &&
+                    fsmem <= static_cast<size_t>(pp_smem_optin()) && p.W >= 2 && p.H >= 2;
+  if (fast) {
+    int fper = 1;
+    if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_fast_kernel<T>), kFThreads, fsmem, &fper))
+      return rc;
+    const int fgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper));
+    decode_expected_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints,
+                                                                  static_cast<unsigned>(plane_bytes),
+                                                                  static_cast<unsigned>(tile_off));
+    PP_CUDA_OK(cudaGetLastError());
+  }
   int per_sm = 1;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_kernel<T>), threads, smem, &per_sm)) return rc;
   const int grid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * per_sm));
-  decode_expected_kernel<T><<<grid, threads, smem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, vec);
+  decode_expected_kernel<T><<<grid, threads, smem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, vec, fast);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }
