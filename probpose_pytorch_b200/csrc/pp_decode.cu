@@ -704,26 +704,37 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   const bool vec = (p.W % Elem<T>::kVec == 0) && pp_aligned16(heatmaps);
   const int threads = pick_threads(p.H, p.W);
 
-  // pruned kernel first (TMA-staged, convolution only around {h >= L}); it marks what it defers
-  const size_t plane_bytes = sizeof(T) * static_cast<size_t>(p.H) * p.W;
-  const size_t tile_off = (plane_bytes + 127) / 128 * 128;
-  const size_t fsmem = tile_off + sizeof(float) * (kFTileRows * kFTileStride + kFTmpRows * kFTmpStride);
-  const bool fast = plane_bytes % 16 == 0 && pp_aligned16(heatmaps) && (!p.apply_tail || p.temperature > 0.0f) &&
-                    fsmem <= static_cast<size_t>(pp_smem_optin()) && p.W >= 2 && p.H >= 2;
+  // main kernel: TMA-staged plane, convolution pruned to the neighbourhood of {h >= L} when possible
+  FastGeom geo{};
+  geo.plane_bytes = static_cast<unsigned>(sizeof(T) * static_cast<size_t>(p.H) * p.W);
+  geo.W8 = round_up(p.W, kTile);
+  geo.full_stride = conflict_free_stride(kFMarg + geo.W8 + kFMarg);
+  geo.work_off = (geo.plane_bytes + 127) / 128 * 128;
+  // + 32 floats of slack: the last window of the last row reads a little past its row (zero taps only)
+  geo.work_floats = static_cast<unsigned>(
+      round_up(static_cast<int>(std::max<size_t>(kFTileFloats, static_cast<size_t>(p.H) * geo.full_stride)) + 32, 4));
+  geo.taskmax_off = geo.work_off + static_cast<unsigned>(sizeof(float)) * geo.work_floats;
+  geo.w2d_off = geo.taskmax_off + static_cast<unsigned>(sizeof(float) * round_up((geo.W8 / kTile) * p.H, 4));
+  const size_t fsmem = geo.w2d_off + sizeof(double) * PP_OKS_TAPS * PP_OKS_TAPS;
+  const bool fast = geo.plane_bytes % 16 == 0 && pp_aligned16(heatmaps) && p.W % Elem<T>::kVec == 0 &&
+                    (!p.apply_tail || p.temperature > 0.0f) && fsmem <= static_cast<size_t>(pp_smem_optin()) &&
+                    p.W > PP_MAX_OKS_RADIUS + 1 && p.H > PP_MAX_OKS_RADIUS + 1 && static_cast<int64_t>(p.H) * p.W < (1 << 20);
   if (fast) {
+    geo.div_WV = div_magic(static_cast<unsigned>(p.W / Elem<T>::kVec));
+    geo.div_W = div_magic(static_cast<unsigned>(p.W));
+    geo.div_H = div_magic(static_cast<unsigned>(p.H));
     int fper = 1;
     if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_fast_kernel<T>), kFThreads, fsmem, &fper))
       return rc;
     const int fgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper));
-    decode_expected_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints,
-                                                                  static_cast<unsigned>(plane_bytes),
-                                                                  static_cast<unsigned>(tile_off));
+    decode_expected_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, geo);
     PP_CUDA_OK(cudaGetLastError());
+    return PP_OK;
   }
   int per_sm = 1;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_kernel<T>), threads, smem, &per_sm)) return rc;
   const int grid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * per_sm));
-  decode_expected_kernel<T><<<grid, threads, smem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, vec, fast);
+  decode_expected_kernel<T><<<grid, threads, smem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, vec, false);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }

@@ -1,179 +1,307 @@
-// Fast path of the expected-OKS decoder (included into pp_decode.cu, inside its anonymous namespace).
+// Main kernel of the expected-OKS decoder (included into pp_decode.cu, inside its anonymous namespace).
 //
-// The full separable convolution costs ~2 x 13 FFMA per pixel on COCO sigmas -- more than the ~2100
-// warp instructions per 64x48 heatmap that the HBM roofline allows -- so this kernel prunes it, exactly:
-//
-//   the OKS kernel is non-negative and sums to 1, hence for every pixel p
+// Exact pruning.  The full separable convolution costs ~2 x 13 FFMA per pixel on COCO sigmas -- more
+// than the ~2100 warp instructions per 64x48 heatmap that the HBM roofline allows.  But the OKS kernel
+// is non-negative and sums to 1, hence for every pixel p
 //        R(p) = float32(sum_q w(q) h(p+q))  <=  max over the kernel window of h,
-//   and  max_p R(p) >= R(p0) =: L  for any pixel p0 (we take the raw maximum).  Therefore the argmax of
-//   R -- and every pixel tied with it -- lies within `radius` of the set S = {h >= L}.  For blob-shaped
-//   heatmaps S is a handful of pixels around the peak.
+// and    max_p R(p) >= R(p0) =: L            for any pixel p0 (we take the raw maximum).
+// Therefore the argmax of R -- and every pixel tied with it -- lies within `radius` of S = {h >= L}.
+// For blob-shaped heatmaps S is a handful of pixels around the peak.
 //
-// Per heatmap: (A) one TMA bulk copy of the contiguous plane into shared memory (prefetched during the
-// previous heatmap), one scan for max/min/argmax; (B) L = exact R(p0) (double accumulation of the
-// reference's d x d table); (C) bounding box of S; (D) gather the box dilated by the radius (+ reflect
-// halo) into a small padded tile; (E/F) separable float32 prefilter on the tile only; (G) exact
-// re-evaluation of the near-maximal pixels and of the four neighbours of the winner; (H) sub-pixel fit.
-// Heatmaps whose box is larger than the tile (flat / multi-modal / noisy maps) are marked by writing
-// NaN into locs[2*hm] and are finished by the full-plane kernel in a second launch.
+// Per heatmap, one persistent CTA of 128 threads:
+//   (A) the contiguous plane arrives in shared memory by one TMA bulk copy (issued during the previous
+//       heatmap); one vector scan gives max / first argmax / min.  Constant maps finish here.
+//   (B) L = exact R(p0): double accumulation of the reference's d x d table, float32 result.
+//   (C) second vector scan: bounding box of S.
+//   tile path (box dilated by the radius fits 24 x 24):
+//   (D) gather the dilated box + reflect halo into a padded tile, head tail applied; the plane is then
+//       free and the next heatmap's TMA is issued;  (E/F) separable float32 prefilter on the tile only;
+//   full path (flat / noisy / multi-modal maps):
+//   (D') column pass straight from the plane (reflect in y by row index) into a padded float32 plane
+//       whose reflect columns are written by the producing thread; (E') row pass with 128-bit windows;
+//       only the per-task maxima are kept, tasks that can hold a candidate are recomputed;
+//   (G) exact re-evaluation (double, reference table) of the pixels within the prefilter's rigorous
+//       error band of its maximum, NumPy tie-break, and of the winner's four neighbours;
+//   (H) float32 sub-pixel fit in the reference's operation order, outputs.
+//
+// The filter passes are written once for all radii (taps zero-padded to a multiple of 8, 8 outputs per
+// task, 16-register sliding window): per-radius template instances blew the instruction cache
+// (profiles/r01c: stall_no_inst dominated every line).
 #pragma once
 
 constexpr int kFThreads = 128;
-constexpr int kFRegion = 24;                    // largest output region side handled here
-constexpr int kFMarg = 12;                      // tile column margin: >= radius + 1, multiple of 4
-constexpr int kFTileW = kFMarg + kFRegion + kFMarg;             // 48
-constexpr int kFTileStride = 52;                // multiple of 4 with odd quarter (conflict-free 128-bit rows)
+constexpr int kFWarps = kFThreads / 32;
+constexpr int kFRegion = 24;                    // largest output region side of the tile path
+constexpr int kFMarg = 12;                      // column margin: >= radius + 1, multiple of 4
+constexpr int kFTileStride = 60;                // >= 12 + 24 + 12 + 8, multiple of 4 with odd quarter
 constexpr int kFTileRows = kFRegion + 2 * (PP_MAX_OKS_RADIUS + 1);   // 44
 constexpr int kFTmpRows = kFRegion + 2 * PP_MAX_OKS_RADIUS;          // 42
 constexpr int kFTmpStride = 28;                 // 24 -> multiple of 4 with odd quarter
-constexpr int kFT = 4;                          // outputs per task
+constexpr int kFTileFloats = kFTileRows * kFTileStride + (kFTmpRows + 8) * kFTmpStride;
+constexpr int kFTaps = 24;                      // taps padded to 3 chunks of 8
+
+struct FastGeom {
+  unsigned plane_bytes;   // H*W*sizeof(T)
+  unsigned work_off;      // byte offset of the float work area (tile + tmp | padded full plane)
+  unsigned work_floats;
+  unsigned taskmax_off;   // byte offset of the per-task maxima (full path)
+  unsigned w2d_off;       // byte offset of the staged d x d table (doubles)
+  int full_stride;        // row stride of the padded full plane (floats)
+  int W8;                 // W rounded up to 8
+  unsigned div_WV, div_W, div_H;   // reciprocals for the index decompositions
+};
 
 struct FastShared {
-  float red_f[2][4];
-  int red_i[4];
-  float taps[PP_OKS_TAPS];
+  float red_f[2][kFWarps];
+  int red_i[kFWarps];
+  __align__(16) float grow[kFTaps];   // row-pass taps, shifted so that the window starts 16-byte aligned
+  __align__(16) float gcol[kFTaps];   // column-pass taps
   float nb[4];
-  float L;
+  float L, e0;
   int bbox[4];        // min x, max x, min y, max y of S
   int cand[kMaxCand];
   int cand_count;
 };
 
+// n / d for small n, d via a precomputed reciprocal (exact for n * d < 2^31)
+__host__ __device__ inline unsigned div_magic(unsigned d) { return 0xFFFFFFFFu / d + 1u; }
+__device__ __forceinline__ int fast_div(int n, unsigned magic) {
+  return static_cast<int>(__umulhi(static_cast<unsigned>(n), magic));
+}
+
 template <typename T>
-__device__ __forceinline__ float plane_value(const T* plane, int idx, bool tail, float temperature) {
-  return apply_tail<T>(Elem<T>::to_f32(plane[idx]), tail, temperature);
+__device__ __forceinline__ float plane_value(const T* plane, int idx) {
+  return Elem<T>::to_f32(plane[idx]);
 }
 
-// row pass on the gathered tile: tmp[ty][x] = sum_j tap[j] * tile[ty + 1][kFMarg + x - R + j]
-template <int R>
-__device__ __forceinline__ void fast_row_pass(const float* __restrict__ tile, float* __restrict__ tmp,
-                                              const float* __restrict__ taps, int rows, int xblocks) {
-  constexpr int PADR = (R + 3) & ~3;
-  constexpr int WIN = kFT + 2 * PADR;
-  float g[R + 1];
+// clamp(x / temperature, 0, 1) rounded like torch does for the tensor dtype; out of line: the IEEE
+// division expands to a long sequence and this is called from one place only.
+template <typename T>
+__device__ __noinline__ float tail_value(float v, float temperature) {
+  return apply_tail<T>(v, true, temperature);
+}
+
+// single reflection, valid for -n <= i < 2n (the kernel requires radius < min(H, W))
+__device__ __forceinline__ int reflect1(int i, int n) {
+  i = i < 0 ? -1 - i : i;
+  return i >= n ? 2 * n - 1 - i : i;
+}
+
+__device__ __forceinline__ void ld8(const float* p, float* v) {   // 32-byte aligned shared address
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// acc[o] = sum_{j < 8 nch} g[j] * src[o + j], o = 0..7; src 16-byte aligned and contiguous
+__device__ __forceinline__ void conv8_contiguous(const float* __restrict__ src, const float* __restrict__ g, int nch,
+                                                 float (&acc)[8]) {
+  float w[16];
+  ld8(src, w);
 #pragma unroll
-  for (int j = 0; j <= R; ++j) g[j] = taps[j];
-  const int tasks = rows * xblocks;
-  for (int t = threadIdx.x; t < tasks; t += kFThreads) {
-    const int xb = t / rows, ty = t - xb * rows;
-    const float4* src = reinterpret_cast<const float4*>(tile + (ty + 1) * kFTileStride + kFMarg + xb * kFT - PADR);
-    float in[WIN];
+  for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    ld8(src + 8 * c + 8, w + 8);
+    float t[8];
+    ld8(g + 8 * c, t);
 #pragma unroll
-    for (int c = 0; c < WIN / 4; ++c) {
-      const float4 v = src[c];
-      in[4 * c] = v.x; in[4 * c + 1] = v.y; in[4 * c + 2] = v.z; in[4 * c + 3] = v.w;
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = fmaf(t[jj], w[o + jj], acc[o]);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) w[o] = w[o + 8];
+  }
+}
+
+// same with the inputs fetched one by one through `load(j)` (strided / reflected / converted sources)
+template <typename Load>
+__device__ __forceinline__ void conv8_gather(Load load, const float* __restrict__ g, int nch, float (&acc)[8]) {
+  float w[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = load(j);
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[8 + j] = load(8 * c + 8 + j);
+    float t[8];
+    ld8(g + 8 * c, t);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = fmaf(t[jj], w[o + jj], acc[o]);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) w[o] = w[o + 8];
+  }
+}
+
+// exact value of one convolved pixel: double accumulation of the staged d x d table, float32 result
+// (what scipy stores, heatmap.py:362-364).  Warp-collective; lanes stride the flattened taps, two
+// accumulators shorten the dependency chain.  One out-of-line copy serves every call site.
+template <typename T>
+struct ExactCtx {
+  const T* plane;        // whole heatmap (reflect by index) ...
+  const float* tile;     // ... or the gathered tile with its halo materialised
+  const double* w2d;
+  int H, W, r, d, oy0, ox0;
+  bool tile_path;
+};
+
+template <typename T>
+__device__ __noinline__ float exact_eval(const ExactCtx<T>& c, int y, int x) {
+  const int lane = threadIdx.x & 31, d = c.d, n = d * d;
+  const int q32 = 32 / d, r32 = 32 - q32 * d;   // 32 = q32 * d + r32
+  int ti = lane / d, tj = lane - ti * d;
+  double a0 = 0.0, a1 = 0.0;
+  if (c.tile_path) {
+    const float* base = c.tile + (y - c.oy0 + 1) * kFTileStride + (x - c.ox0 + kFMarg - c.r);
+#pragma unroll 1
+    for (int i = lane; i < n; i += 64) {
+      a0 = fma(c.w2d[i], static_cast<double>(base[ti * kFTileStride + tj]), a0);
+      tj += r32; ti += q32;
+      if (tj >= d) { tj -= d; ++ti; }
+      if (i + 32 < n) a1 = fma(c.w2d[i + 32], static_cast<double>(base[ti * kFTileStride + tj]), a1);
+      tj += r32; ti += q32;
+      if (tj >= d) { tj -= d; ++ti; }
     }
-    float acc[kFT];
-#pragma unroll
-    for (int o = 0; o < kFT; ++o) {
+  } else {
+#pragma unroll 1
+    for (int i = lane; i < n; i += 64) {
+      a0 = fma(c.w2d[i], static_cast<double>(plane_value<T>(c.plane, reflect1(y + ti - c.r, c.H) * c.W + reflect1(x + tj - c.r, c.W))), a0);
+      tj += r32; ti += q32;
+      if (tj >= d) { tj -= d; ++ti; }
+      if (i + 32 < n)
+        a1 = fma(c.w2d[i + 32], static_cast<double>(plane_value<T>(c.plane, reflect1(y + ti - c.r, c.H) * c.W + reflect1(x + tj - c.r, c.W))), a1);
+      tj += r32; ti += q32;
+      if (tj >= d) { tj -= d; ++ti; }
+    }
+  }
+  return static_cast<float>(warp_sum(a0 + a1));
+}
+
+// More near-maximal pixels than the candidate list holds (plateaus / heavily quantised maps): every warp
+// walks its share of the region (tile path) or plane (full path), recomputes the prefilter value with the
+// same operation order as the passes and re-evaluates the qualifying pixels exactly.  Rare; out of line.
+struct OverflowCtx {
+  const float* src;      // second-pass input: tmp (tile path, taps along rows) or padded plane (full path)
+  const float* taps;
+  int step, row_stride;  // tap stride / row stride in `src`
+  int x_lo, y_lo, x_n, y_n;
+  float thr;
+};
+
+template <typename T>
+__device__ __noinline__ void overflow_scan(const OverflowCtx& oc, const ExactCtx<T>& ectx, float& wv, int& wi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned magic = div_magic(oc.x_n);
+  for (int base = warp * 32; base < oc.x_n * oc.y_n; base += kFWarps * 32) {
+    const int q = base + lane;
+    bool want = false;
+    int y = 0, x = 0;
+    if (q < oc.x_n * oc.y_n) {
+      const int qy = fast_div(q, magic), qx = q - qy * oc.x_n;
+      y = oc.y_lo + qy; x = oc.x_lo + qx;
+      const float* c = oc.src + (ectx.tile_path ? qy : y) * oc.row_stride + (ectx.tile_path ? qx : x);
       float a = 0.0f;
-#pragma unroll
-      for (int j = 0; j <= 2 * R; ++j) a = fmaf(g[j <= R ? j : 2 * R - j], in[PADR - R + o + j], a);
-      acc[o] = a;
+      for (int j = 0; j < ectx.d; ++j) a = fmaf(oc.taps[j], c[j * oc.step], a);
+      want = a >= oc.thr;
     }
-    *reinterpret_cast<float4*>(tmp + ty * kFTmpStride + xb * kFT) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  }
-}
-
-// column pass: conv(x, y) = sum_j tap[j] * tmp[y + j][x]; up to two tasks (kFT rows each) per thread,
-// results stay in registers.
-template <int R>
-__device__ __forceinline__ void fast_col_pass(const float* __restrict__ tmp, const float* __restrict__ taps, int OW,
-                                              int OH, float (&cv)[2][kFT]) {
-  float g[R + 1];
-#pragma unroll
-  for (int j = 0; j <= R; ++j) g[j] = taps[j];
-  const int yblocks = (OH + kFT - 1) / kFT;
-  const int tasks = OW * yblocks;
-#pragma unroll
-  for (int slot = 0; slot < 2; ++slot) {
-    const int t = threadIdx.x + slot * kFThreads;
-#pragma unroll
-    for (int o = 0; o < kFT; ++o) cv[slot][o] = -INFINITY;
-    if (t < tasks) {
-      const int yb = t / OW, x = t - yb * OW;
-      float in[kFT + 2 * R];
-#pragma unroll
-      for (int j = 0; j < kFT + 2 * R; ++j) in[j] = tmp[min(yb * kFT + j, kFTmpRows - 1) * kFTmpStride + x];
-#pragma unroll
-      for (int o = 0; o < kFT; ++o) {
-        float a = 0.0f;
-#pragma unroll
-        for (int j = 0; j <= 2 * R; ++j) a = fmaf(g[j <= R ? j : 2 * R - j], in[o + j], a);
-        if (yb * kFT + o < OH) cv[slot][o] = a;
-      }
+    unsigned msk = __ballot_sync(0xffffffffu, want);
+    while (msk) {
+      const int b = __ffs(msk) - 1;
+      msk &= msk - 1;
+      const int yy = __shfl_sync(0xffffffffu, y, b), xx = __shfl_sync(0xffffffffu, x, b);
+      argmax_combine(wv, wi, exact_eval<T>(ectx, yy, xx), yy * ectx.W + xx);
     }
   }
-}
-
-// exact value of one convolved pixel from the gathered tile (reflect halo already materialised):
-// double accumulation of the d x d table, float32 result.  Warp-collective.
-__device__ __forceinline__ float exact_conv_tile(const float* __restrict__ tile, int ty, int tc, int r,
-                                                 const double* __restrict__ w2d) {
-  const int d = 2 * r + 1, lane = threadIdx.x & 31;
-  double acc = 0.0;
-  if (lane < d) {
-    const float* p = tile + (ty - r) * kFTileStride + tc - r + lane;
-    const double* w = w2d + lane;
-    for (int ti = 0; ti < d; ++ti) acc = fma(w[ti * d], static_cast<double>(p[ti * kFTileStride]), acc);
-  }
-  return static_cast<float>(warp_sum(acc));
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kFThreads, 6)
 decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict__ heatmaps,
                             float* __restrict__ locs, float* __restrict__ vals, int32_t* __restrict__ argmax,
-                            double* __restrict__ keypoints, unsigned plane_bytes, unsigned tile_off) {
+                            double* __restrict__ keypoints, FastGeom geo) {
   extern __shared__ __align__(128) unsigned char fsm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ FastShared sh;
 
   const T* plane = reinterpret_cast<const T*>(fsm);
-  float* tile = reinterpret_cast<float*>(fsm + tile_off);
-  float* tmp = tile + kFTileRows * kFTileStride;
+  T* plane_rw = reinterpret_cast<T*>(fsm);
+  float* work = reinterpret_cast<float*>(fsm + geo.work_off);
+  float* tile = work;
+  float* tmp = work + kFTileRows * kFTileStride;
+  float* task_max = reinterpret_cast<float*>(fsm + geo.taskmax_off);
+  double* w2d = reinterpret_cast<double*>(fsm + geo.w2d_off);
 
   constexpr int V = Elem<T>::kVec;
-  const int H = p.H, W = p.W, HW = H * W;
+  const int H = p.H, W = p.W, HW = H * W, WV = W / V, FS = geo.full_stride;
   const int64_t N = static_cast<int64_t>(p.B) * p.K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool tail = p.apply_tail != 0;
   const float temp = p.temperature;
+  // (row, vector-in-row) of this thread's first vector and the per-iteration step of the scans
+  const int step_y = fast_div(kFThreads, geo.div_WV), step_x = kFThreads - step_y * WV;
+  const int first_y = fast_div(tid, geo.div_WV), first_x = tid - first_y * WV;
 
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
   }
+  // stale work-area contents only ever meet zero taps or unused outputs, but they must be finite
+  for (int i = tid; i < static_cast<int>(geo.work_floats); i += kFThreads) work[i] = 0.0f;
   __syncthreads();
   int64_t hm = blockIdx.x;
   if (tid == 0 && hm < N) {
-    mbar_expect_tx(&bar, plane_bytes);
-    tma_load_1d(fsm, heatmaps + hm * HW, plane_bytes, &bar);
+    mbar_expect_tx(&bar, geo.plane_bytes);
+    tma_load_1d(fsm, heatmaps + hm * HW, geo.plane_bytes, &bar);
   }
 
   for (int it = 0; hm < N; hm += gridDim.x, ++it) {
     const int k = static_cast<int>(hm % p.K);
     const int r = tab.radius[k];
-    const double* w2d = tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
-    if (tid < PP_OKS_TAPS) sh.taps[tid] = tab.taps_f32[k * PP_OKS_TAPS + tid];
+    const int d = 2 * r + 1;
+    const int padr = (r + 3) & ~3, shift = padr - r;
+    const int nch_row = (shift + d + 7) >> 3, nch_col = (d + 7) >> 3;
+    {
+      const double* src = tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
+      for (int i = tid; i < d * d; i += kFThreads) w2d[i] = src[i];
+      const float* t1 = tab.taps_f32 + k * PP_OKS_TAPS;
+      if (tid < kFTaps) {
+        sh.gcol[tid] = tid < d ? t1[tid] : 0.0f;
+        sh.grow[tid] = (tid >= shift && tid < shift + d) ? t1[tid - shift] : 0.0f;
+      }
+    }
     if (tid == 0) {
       sh.bbox[0] = W; sh.bbox[1] = -1; sh.bbox[2] = H; sh.bbox[3] = -1;
       sh.cand_count = 0;
     }
     mbar_wait(&bar, it & 1);
 
-    // ---- A: one scan of the raw plane: max (first index) and min.  The head tail is monotone
-    // (temperature > 0 is required for this path), so the raw extrema are the extrema after the tail.
+    // ---- A: one scan of the plane: max (first index) and min.  The head tail (head.py:526-532), when
+    // requested, is applied here once, in place, so that every later phase reads plain values.
     float xmax = -INFINITY, xmin = INFINITY;
     int imax = 0x7fffffff;
+#pragma unroll 2
     for (int i = tid; i < HW / V; i += kFThreads) {
       float f[V];
-      const uint4 w = *reinterpret_cast<const uint4*>(plane + i * V);
-      unpack(w, f, T());
+      uint4* vec = reinterpret_cast<uint4*>(plane_rw + i * V);
+      unpack(*vec, f, T());
+      if (tail) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        if (f[j] > xmax) { xmax = f[j]; imax = i * V + j; }
-        xmin = fminf(xmin, f[j]);
+        for (int j = 0; j < V; ++j) f[j] = tail_value<T>(f[j], temp);
+        *vec = pack(f, T());
+      }
+      float m = f[0], lo = f[0];
+#pragma unroll
+      for (int j = 1; j < V; ++j) { m = fmaxf(m, f[j]); lo = fminf(lo, f[j]); }
+      xmin = fminf(xmin, lo);
+      if (m > xmax) {   // rare after the first few vectors
+        xmax = m;
+        int jj = V - 1;
+#pragma unroll
+        for (int j = V - 2; j >= 0; --j) jj = (f[j] == m) ? j : jj;
+        imax = i * V + jj;
       }
     }
     warp_argmax(xmax, imax);
@@ -182,71 +310,69 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
     __syncthreads();
     xmax = sh.red_f[0][0]; xmin = sh.red_f[1][0]; imax = sh.red_i[0];
 #pragma unroll
-    for (int w = 1; w < kFThreads / 32; ++w) {
+    for (int w = 1; w < kFWarps; ++w) {
       argmax_combine(xmax, imax, sh.red_f[0][w], sh.red_i[w]);
       xmin = fminf(xmin, sh.red_f[1][w]);
     }
-    const float vmax = apply_tail<T>(xmax, tail, temp), vmin = apply_tail<T>(xmin, tail, temp);
+    const float vmax = xmax, vmin = xmin;
 
-    bool finished = false;   // uniform across the CTA
+    // every flag below is uniform across the CTA
+    const bool constant = vmax == vmin;   // e.g. all zeros after the clamp: first index wins, border pixel
+    bool tile_path = false;
     int best = 0;
     float best_val = 0.0f, score = vmax;
     float nb[4] = {0.f, 0.f, 0.f, 0.f};
-    bool interior = false, deferred = false;
-
-    if (vmax == vmin) {
-      // constant map (e.g. all zeros after the clamp): all convolved pixels are the same float, the
-      // first index wins and (0,0) is a border pixel
-      finished = true;
-    }
-
+    bool interior = false;
     int ox0 = 0, oy0 = 0, OW = 0, OH = 0;
-    if (!finished) {
-      // ---- B: L = exact convolved value at the raw maximum p0
-      const int py = imax / W, px = imax - py * W;
+
+    ExactCtx<T> ectx;
+    ectx.plane = plane; ectx.tile = tile; ectx.w2d = w2d;
+    ectx.H = H; ectx.W = W; ectx.r = r; ectx.d = d; ectx.oy0 = 0; ectx.ox0 = 0;
+    ectx.tile_path = false;
+
+    if (!constant) {
+      // ---- B: L = exact convolved value at the raw maximum p0 (minus a few ulp: later evaluations may
+      // sum the same terms in a different order)
+      const int py = fast_div(imax, geo.div_W), px = imax - py * W;
       if (warp == 0) {
-        const int d = 2 * r + 1;
-        double acc = 0.0;
-        if (lane < d) {
-          const int xx = reflect_index(px + lane - r, W);
-          for (int ti = 0; ti < d; ++ti) {
-            const int yy = reflect_index(py + ti - r, H);
-            acc = fma(w2d[ti * d + lane], static_cast<double>(plane_value<T>(plane, yy * W + xx, tail, temp)), acc);
-          }
-        }
-        const float e = static_cast<float>(warp_sum(acc));
-        // a few ulp of slack: this evaluation and the tile evaluation sum the same terms in different orders
-        if (lane == 0) sh.L = e - fabsf(e) * 2.4e-7f;
+        const float e = exact_eval<T>(ectx, py, px);
+        if (lane == 0) { sh.e0 = e; sh.L = e - fabsf(e) * 2.4e-7f; }
       }
       __syncthreads();
       const float L = sh.L;
 
       // ---- C: bounding box of S = {h >= L}
       int bx0 = W, bx1 = -1, by0 = H, by1 = -1;
-      for (int i = tid; i < HW / V; i += kFThreads) {
-        float f[V];
-        const uint4 w = *reinterpret_cast<const uint4*>(plane + i * V);
-        unpack(w, f, T());
+      {
+        int y = first_y, xv = first_x;
+#pragma unroll 2
+        for (int i = tid; i < HW / V; i += kFThreads) {
+          float f[V];
+          unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+          bool any = false;
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          if (apply_tail<T>(f[j], tail, temp) >= L) {
-            const int idx = i * V + j, y = idx / W, x = idx - y * W;
-            bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y);
+          for (int j = 0; j < V; ++j) {
+            if (f[j] >= L) {
+              bx0 = min(bx0, xv * V + j);
+              bx1 = max(bx1, xv * V + j);
+              any = true;
+            }
           }
+          if (any) { by0 = min(by0, y); by1 = max(by1, y); }
+          xv += step_x; y += step_y;
+          if (xv >= WV) { xv -= WV; ++y; }
         }
       }
-      if (__any_sync(0xffffffffu, bx1 >= 0)) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-          bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-          by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-          by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-        }
-        if (lane == 0) {
-          atomicMin(&sh.bbox[0], bx0); atomicMax(&sh.bbox[1], bx1);
-          atomicMin(&sh.bbox[2], by0); atomicMax(&sh.bbox[3], by1);
-        }
+      for (int o = 16; o > 0; o >>= 1) {
+        bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+        bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+        by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+        by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+      }
+      if (lane == 0 && bx1 >= 0) {
+        atomicMin(&sh.bbox[0], bx0); atomicMax(&sh.bbox[1], bx1);
+        atomicMin(&sh.bbox[2], by0); atomicMax(&sh.bbox[3], by1);
       }
       __syncthreads();
       // p0 itself is in S (h(p0) = max >= R(p0)), so the box is never empty
@@ -254,136 +380,226 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       oy0 = max(sh.bbox[2] - r, 0);
       OW = min(sh.bbox[1] + r, W - 1) - ox0 + 1;
       OH = min(sh.bbox[3] + r, H - 1) - oy0 + 1;
-      if (OW > kFRegion || OH > kFRegion) {
-        deferred = true;   // too spread out for the tile: leave it to the full-plane kernel
-        finished = true;
-      }
+      tile_path = OW <= kFRegion && OH <= kFRegion;
     }
 
-    if (!finished) {
+    if (!constant && tile_path) {
       // ---- D: gather the region (+ radius + 1 halo, reflect-extended, tail applied) into the tile
       const int rows = OH + 2 * (r + 1);
       const int c_lo = kFMarg - (r + 1), c_hi = kFMarg + OW + r;   // inclusive
-      for (int ty = warp; ty < rows; ty += kFThreads / 32) {
-        const int yy = reflect_index(oy0 - (r + 1) + ty, H);
-        for (int c = c_lo + lane; c <= c_hi; c += 32) {
-          const int xx = reflect_index(ox0 - kFMarg + c, W);
-          tile[ty * kFTileStride + c] = plane_value<T>(plane, yy * W + xx, tail, temp);
+      int xx0 = 0, xx1 = 0;
+      const int c0 = c_lo + lane, c1 = c0 + 32;
+      if (c0 <= c_hi) xx0 = reflect1(ox0 - kFMarg + c0, W);
+      if (c1 <= c_hi) xx1 = reflect1(ox0 - kFMarg + c1, W);
+      for (int ty = warp; ty < rows; ty += kFWarps) {
+        const int yy = reflect1(oy0 - (r + 1) + ty, H);
+        if (c0 <= c_hi) tile[ty * kFTileStride + c0] = plane_value<T>(plane, yy * W + xx0);
+        if (c1 <= c_hi) tile[ty * kFTileStride + c1] = plane_value<T>(plane, yy * W + xx1);
+      }
+    } else if (!constant) {
+      // ---- D': full path, column pass from the plane into the padded float32 plane:
+      // full[y][kFMarg + x] = sum_j tap[j] h[reflect(y - r + j)][x]; columns within r of an edge are
+      // mirrored into the pad by the thread that produces them.
+      const int yblocks = (H + 7) >> 3;
+      for (int t = tid; t < W * yblocks; t += kFThreads) {
+        const int yb = fast_div(t, geo.div_W), x = t - yb * W;
+        const int y0 = yb * 8;
+        float acc[8];
+        const int need = 8 + 2 * r;
+        const bool inside = y0 - r >= 0 && y0 + 7 + r < H;
+        const T* col = plane + x;
+        conv8_gather(
+            [&](int j) -> float {
+              if (j >= need) return 0.0f;
+              const int yy = inside ? (y0 - r + j) : reflect1(y0 - r + j, H);
+              return Elem<T>::to_f32(col[yy * W]);
+            },
+            sh.gcol, nch_col, acc);
+        const bool left = x < r, right = x >= W - r;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          if (y0 + o < H) {
+            float* row = work + (y0 + o) * FS + kFMarg;
+            row[x] = acc[o];
+            if (left) row[-1 - x] = acc[o];
+            if (right) row[2 * W - 1 - x] = acc[o];
+          }
         }
       }
     }
-    __syncthreads();   // the plane is not read after this point
-    {
-      const int64_t nxt = hm + gridDim.x;
-      if (tid == 0 && nxt < N) {   // the next heatmap streams in while this one is finished from the tile
-        mbar_expect_tx(&bar, plane_bytes);
-        tma_load_1d(fsm, heatmaps + nxt * HW, plane_bytes, &bar);
-      }
+    __syncthreads();
+    const bool plane_free = constant || tile_path;   // the full path still needs the plane for step G
+    const int64_t nxt = hm + gridDim.x;
+    if (plane_free && tid == 0 && nxt < N) {   // the next heatmap streams in while this one is finished
+      fence_proxy_async();
+      mbar_expect_tx(&bar, geo.plane_bytes);
+      tma_load_1d(fsm, heatmaps + nxt * HW, geo.plane_bytes, &bar);
     }
 
-    if (!finished) {
-      // ---- E/F: separable float32 prefilter on the tile
-      float cv[2][kFT];
-      const int trows = OH + 2 * r, xblocks = (OW + kFT - 1) / kFT;
-      switch (r) {
-#define PP_FCASE(R)                                         \
-  case R:                                                   \
-    fast_row_pass<R>(tile, tmp, sh.taps, trows, xblocks);   \
-    __syncthreads();                                        \
-    fast_col_pass<R>(tmp, sh.taps, OW, OH, cv);             \
-    break;
-        PP_FCASE(1) PP_FCASE(2) PP_FCASE(3) PP_FCASE(4) PP_FCASE(5) PP_FCASE(6) PP_FCASE(7) PP_FCASE(8) PP_FCASE(9)
-#undef PP_FCASE
-        default: break;
-      }
+    if (!constant) {
+      // ---- E/F: separable float32 prefilter
       float pmax = -INFINITY;
+      float cv[8];
 #pragma unroll
-      for (int s = 0; s < 2; ++s)
+      for (int o = 0; o < 8; ++o) cv[o] = -INFINITY;
+      int cx = 0, cyb = 0;
+      bool have_cv = false;
+      if (tile_path) {
+        // rows of the tile: tmp[ty][x] = sum_j tap[j] tile[ty + 1][kFMarg + x - r + j]
+        const int trows = OH + 2 * r, xblocks = (OW + 7) >> 3;
+        const unsigned mrows = div_magic(trows);
+        for (int t = tid; t < trows * xblocks; t += kFThreads) {
+          const int xb = fast_div(t, mrows), ty = t - xb * trows;
+          float acc[8];
+          conv8_contiguous(tile + (ty + 1) * kFTileStride + kFMarg + xb * 8 - padr, sh.grow, nch_row, acc);
+          float4* dst = reinterpret_cast<float4*>(tmp + ty * kFTmpStride + xb * 8);
+          dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        __syncthreads();
+        // columns: conv(x, y) = sum_j tap[j] tmp[y + j][x]; one task (8 rows) per thread, kept in registers
+        const int yblocks = (OH + 7) >> 3;
+        if (tid < OW * yblocks) {
+          cyb = fast_div(tid, div_magic(OW)); cx = tid - cyb * OW;
+          have_cv = true;
+          const float* colp = tmp + cx;
+          const int y0 = cyb * 8;
+          float acc[8];
+          conv8_gather([&](int j) -> float { return colp[min(y0 + j, kFTmpRows + 7) * kFTmpStride]; }, sh.gcol, nch_col,
+                       acc);
 #pragma unroll
-        for (int o = 0; o < kFT; ++o) pmax = fmaxf(pmax, cv[s][o]);
+          for (int o = 0; o < 8; ++o) {
+            if (y0 + o < OH) { cv[o] = acc[o]; pmax = fmaxf(pmax, acc[o]); }
+          }
+        }
+      } else {
+        // rows of the padded plane, 8 outputs per task; only the per-task maximum is kept
+        const int tasks = (geo.W8 >> 3) * H;
+        for (int t = tid; t < tasks; t += kFThreads) {
+          const int xb = fast_div(t, geo.div_H), y = t - xb * H;
+          float acc[8];
+          conv8_contiguous(work + y * FS + kFMarg + xb * 8 - padr, sh.grow, nch_row, acc);
+          float m = -INFINITY;
+#pragma unroll
+          for (int o = 0; o < 8; ++o)
+            if (xb * 8 + o < W) m = fmaxf(m, acc[o]);
+          task_max[t] = m;
+          pmax = fmaxf(pmax, m);
+        }
+      }
       pmax = warp_max(pmax);
       if (lane == 0) sh.red_f[0][warp] = pmax;
       __syncthreads();
       pmax = fmaxf(fmaxf(sh.red_f[0][0], sh.red_f[0][1]), fmaxf(sh.red_f[0][2], sh.red_f[0][3]));
       const float amax = fmaxf(fabsf(vmax), fabsf(vmin));
-      const float gamma = static_cast<float>(2 * (2 * r + 1) + 8) * 1.1920929e-7f;
+      const float gamma = static_cast<float>(2 * d + 8) * 1.1920929e-7f;   // (2d + 8) * 2^-23
       const float thr = pmax - (2.0f * gamma + 4.0f * 5.9604645e-8f) * amax;
-      const int yblocks = (OH + kFT - 1) / kFT;
+
+      // candidates: pixels whose prefilter value is within the error band of the maximum
+      if (tile_path) {
+        if (have_cv) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int t = tid + s * kFThreads;
-        if (t < OW * yblocks) {
-          const int yb = t / OW, x = t - yb * OW;
-#pragma unroll
-          for (int o = 0; o < kFT; ++o) {
-            if (cv[s][o] >= thr) {   // cv is -inf for rows beyond the region
+          for (int o = 0; o < 8; ++o) {
+            if (cv[o] >= thr) {   // cv is -inf for rows beyond the region
               const int slot = atomicAdd(&sh.cand_count, 1);
-              if (slot < kMaxCand) sh.cand[slot] = (oy0 + yb * kFT + o) * W + ox0 + x;
+              if (slot < kMaxCand) sh.cand[slot] = (oy0 + cyb * 8 + o) * W + ox0 + cx;
+            }
+          }
+        }
+      } else {
+        const int tasks = (geo.W8 >> 3) * H;
+        for (int t = tid; t < tasks; t += kFThreads) {
+          if (!(task_max[t] >= thr)) continue;
+          const int xb = fast_div(t, geo.div_H), y = t - xb * H;
+          float acc[8];
+          conv8_contiguous(work + y * FS + kFMarg + xb * 8 - padr, sh.grow, nch_row, acc);
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            if (xb * 8 + o < W && acc[o] >= thr) {
+              const int slot = atomicAdd(&sh.cand_count, 1);
+              if (slot < kMaxCand) sh.cand[slot] = y * W + xb * 8 + o;
             }
           }
         }
       }
       __syncthreads();
       const int count = sh.cand_count;
-      if (count > kMaxCand) {
-        deferred = true;   // plateau wider than the list: full-plane kernel
+
+      // ---- G: exact values of the candidates
+      ectx.tile_path = tile_path; ectx.oy0 = oy0; ectx.ox0 = ox0;
+      auto exact_at = [&](int y, int x) -> float { return exact_eval<T>(ectx, y, x); };
+      if (count == 1 && sh.cand[0] == imax) {
+        // the usual case: the convolved maximum sits on the raw maximum, whose exact value is known from B
+        best = imax;
+        best_val = sh.e0;
       } else {
-        // ---- G: exact values of the near-maximal pixels
         float wv = -INFINITY;
         int wi = 0x7fffffff;
-        for (int c = warp; c < count; c += kFThreads / 32) {
-          const int idx = sh.cand[c], y = idx / W, x = idx - y * W;
-          const float e = exact_conv_tile(tile, y - oy0 + r + 1, x - ox0 + kFMarg, r, w2d);
-          argmax_combine(wv, wi, e, idx);
+        if (count <= kMaxCand) {
+          for (int c = warp; c < count; c += kFWarps) {
+            const int idx = sh.cand[c], y = fast_div(idx, geo.div_W), x = idx - y * W;
+            argmax_combine(wv, wi, exact_at(y, x), idx);
+          }
+        } else {
+          OverflowCtx oc;
+          oc.src = tile_path ? tmp : work + kFMarg - r;
+          oc.step = tile_path ? kFTmpStride : 1;
+          oc.row_stride = tile_path ? kFTmpStride : FS;
+          oc.x_lo = tile_path ? ox0 : 0; oc.y_lo = tile_path ? oy0 : 0;
+          oc.x_n = tile_path ? OW : W; oc.y_n = tile_path ? OH : H;
+          oc.taps = sh.gcol; oc.thr = thr;
+          overflow_scan<T>(oc, ectx, wv, wi);
         }
         if (lane == 0) { sh.red_f[0][warp] = wv; sh.red_i[warp] = wi; }
         __syncthreads();
         best_val = sh.red_f[0][0]; best = sh.red_i[0];
 #pragma unroll
-        for (int w = 1; w < kFThreads / 32; ++w) argmax_combine(best_val, best, sh.red_f[0][w], sh.red_i[w]);
-        const int by = best / W, bx = best - by * W;
-        interior = bx > 0 && bx < W - 1 && by > 0 && by < H - 1;
-        if (interior) {
-          const int dx = (warp == 0) ? -1 : (warp == 1) ? 1 : 0;
-          const int dy = (warp == 2) ? -1 : (warp == 3) ? 1 : 0;
-          const float e = exact_conv_tile(tile, by + dy - oy0 + r + 1, bx + dx - ox0 + kFMarg, r, w2d);
-          if (lane == 0) sh.nb[warp] = e;
-          __syncthreads();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) nb[q] = sh.nb[q];
-        }
-        score = tile[(by - oy0 + r + 1) * kFTileStride + bx - ox0 + kFMarg];
+        for (int w = 1; w < kFWarps; ++w) argmax_combine(best_val, best, sh.red_f[0][w], sh.red_i[w]);
       }
+      const int by = fast_div(best, geo.div_W), bx = best - by * W;
+      interior = bx > 0 && bx < W - 1 && by > 0 && by < H - 1;
+      if (interior) {
+        const int dx = (warp == 0) ? -1 : (warp == 1) ? 1 : 0;
+        const int dy = (warp == 2) ? -1 : (warp == 3) ? 1 : 0;
+        const float e = exact_at(by + dy, bx + dx);
+        if (lane == 0) sh.nb[warp] = e;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nb[q] = sh.nb[q];
+      }
+      score = tile_path ? tile[(by - oy0 + r + 1) * kFTileStride + bx - ox0 + kFMarg]
+                        : plane_value<T>(plane, best);
     }
 
     // ---- H: outputs
     if (tid == 0) {
-      if (deferred) {
-        locs[hm * 2] = __int_as_float(0x7fc00000);   // NaN marks "finish me" for the full-plane kernel
-      } else {
-        const int by = best / W, bx = best - by * W;
-        float fx = static_cast<float>(bx), fy = static_cast<float>(by);
-        if (interior) {   // _get_subpixel_maximums, float32, op order of heatmap.py:136-165
-          const float l = nb[0], rr = nb[1], u = nb[2], dn = nb[3], c = best_val;
-          const float gx = __fdiv_rn(__fsub_rn(rr, l), 2.0f);
-          const float gy = __fdiv_rn(__fsub_rn(dn, u), 2.0f);
-          float hxx = __fsub_rn(__fadd_rn(rr, l), __fmul_rn(2.0f, c));
-          float hyy = __fsub_rn(__fadd_rn(dn, u), __fmul_rn(2.0f, c));
-          if (hxx == 0.0f) hxx = 1e-6f;
-          if (hyy == 0.0f) hyy = 1e-6f;
-          fx = __fadd_rn(fx, __fdiv_rn(-gx, hxx));
-          fy = __fadd_rn(fy, __fdiv_rn(-gy, hyy));
-        }
-        locs[hm * 2] = fx;
-        locs[hm * 2 + 1] = fy;
-        vals[hm] = score;
-        if (argmax) argmax[hm] = best;
-        if (keypoints) {
-          keypoints[hm * 2] = static_cast<double>(fx) / static_cast<double>(W - 1) * p.input_w;
-          keypoints[hm * 2 + 1] = static_cast<double>(fy) / static_cast<double>(H - 1) * p.input_h;
-        }
+      const int by = fast_div(best, geo.div_W), bx = best - by * W;
+      float fx = static_cast<float>(bx), fy = static_cast<float>(by);
+      if (interior) {   // _get_subpixel_maximums, float32, op order of heatmap.py:136-165
+        const float l = nb[0], rr = nb[1], u = nb[2], dn = nb[3], c = best_val;
+        const float gx = __fdiv_rn(__fsub_rn(rr, l), 2.0f);
+        const float gy = __fdiv_rn(__fsub_rn(dn, u), 2.0f);
+        float hxx = __fsub_rn(__fadd_rn(rr, l), __fmul_rn(2.0f, c));
+        float hyy = __fsub_rn(__fadd_rn(dn, u), __fmul_rn(2.0f, c));
+        if (hxx == 0.0f) hxx = 1e-6f;
+        if (hyy == 0.0f) hyy = 1e-6f;
+        fx = __fadd_rn(fx, __fdiv_rn(-gx, hxx));
+        fy = __fadd_rn(fy, __fdiv_rn(-gy, hyy));
+      }
+      locs[hm * 2] = fx;
+      locs[hm * 2 + 1] = fy;
+      vals[hm] = score;
+      if (argmax) argmax[hm] = best;
+      if (keypoints) {
+        keypoints[hm * 2] = static_cast<double>(fx) / static_cast<double>(W - 1) * p.input_w;
+        keypoints[hm * 2 + 1] = static_cast<double>(fy) / static_cast<double>(H - 1) * p.input_h;
       }
     }
-    __syncthreads();   // tile / scratch are reused by the next heatmap
+    __syncthreads();   // work area / scratch / plane are reused by the next heatmap
+    if (!plane_free && tid == 0 && nxt < N) {
+      fence_proxy_async();
+      mbar_expect_tx(&bar, geo.plane_bytes);
+      tma_load_1d(fsm, heatmaps + nxt * HW, geo.plane_bytes, &bar);
+    }
   }
 }
