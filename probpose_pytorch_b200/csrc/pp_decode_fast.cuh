@@ -136,6 +136,71 @@ __device__ __forceinline__ void conv8_gather(Load load, const float* __restrict_
   }
 }
 
+template <typename T>
+__device__ __forceinline__ void load2(const T* p, float& a, float& b);
+template <>
+__device__ __forceinline__ void load2<float>(const float* p, float& a, float& b) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  a = v.x; b = v.y;
+}
+template <>
+__device__ __forceinline__ void load2<__nv_bfloat16>(const __nv_bfloat16* p, float& a, float& b) {
+  const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+  a = __uint_as_float(v << 16); b = __uint_as_float(v & 0xffff0000u);
+}
+
+// Full-path column pass for two adjacent columns (x even) and 4 rows, taps in chunks of 4:
+//   full[y][kFMarg + x] = sum_j tap[j] h[reflect(y - r + j)][x];
+// columns within r of an edge are mirrored into the pad by the thread that produces them.
+template <typename T, bool kInside>
+__device__ __forceinline__ void full_col_task(const T* __restrict__ plane, float* __restrict__ work,
+                                              const float* __restrict__ g, int nch4, int x, int y0, int r, int H, int W,
+                                              int FS) {
+  float w0[8], w1[8], a0[4], a1[4];
+  const int need = 4 + 2 * r;
+  const T* base = plane + x + (kInside ? (y0 - r) * W : 0);
+  auto fetch = [&](int j, float& u, float& v) {
+    if (j < need) {
+      if (kInside) load2<T>(base + j * W, u, v);
+      else load2<T>(base + reflect1(y0 - r + j, H) * W, u, v);
+    } else {
+      u = 0.0f; v = 0.0f;
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < 4; ++j) fetch(j, w0[j], w1[j]);
+#pragma unroll
+  for (int o = 0; o < 4; ++o) { a0[o] = 0.0f; a1[o] = 0.0f; }
+#pragma unroll 1
+  for (int c = 0; c < nch4; ++c) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fetch(4 * c + 4 + j, w0[4 + j], w1[4 + j]);
+    const float4 t4 = *reinterpret_cast<const float4*>(g + 4 * c);
+    const float t[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        a0[o] = fmaf(t[jj], w0[o + jj], a0[o]);
+        a1[o] = fmaf(t[jj], w1[o + jj], a1[o]);
+      }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { w0[o] = w0[o + 4]; w1[o] = w1[o + 4]; }
+  }
+  const bool left = x < r, left1 = x + 1 < r, right = x >= W - r, right1 = x + 1 >= W - r;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    if (y0 + o < H) {
+      float* row = work + (y0 + o) * FS + kFMarg;
+      *reinterpret_cast<float2*>(row + x) = make_float2(a0[o], a1[o]);
+      if (left) row[-1 - x] = a0[o];
+      if (left1) row[-2 - x] = a1[o];
+      if (right) row[2 * W - 1 - x] = a0[o];
+      if (right1) row[2 * W - 2 - x] = a1[o];
+    }
+  }
+}
+
 // exact value of one convolved pixel: double accumulation of the staged d x d table, float32 result
 // (what scipy stores, heatmap.py:362-364).  Warp-collective; lanes stride the flattened taps, two
 // accumulators shorten the dependency chain.  One out-of-line copy serves every call site.
@@ -349,16 +414,19 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
         for (int i = tid; i < HW / V; i += kFThreads) {
           float f[V];
           unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
-          bool any = false;
+          float m = f[0];
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            if (f[j] >= L) {
-              bx0 = min(bx0, xv * V + j);
-              bx1 = max(bx1, xv * V + j);
-              any = true;
+          for (int j = 1; j < V; ++j) m = fmaxf(m, f[j]);
+          if (m >= L) {   // rare on blob-shaped maps
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              if (f[j] >= L) {
+                bx0 = min(bx0, xv * V + j);
+                bx1 = max(bx1, xv * V + j);
+              }
             }
+            by0 = min(by0, y); by1 = max(by1, y);
           }
-          if (any) { by0 = min(by0, y); by1 = max(by1, y); }
           xv += step_x; y += step_y;
           if (xv >= WV) { xv -= WV; ++y; }
         }
@@ -400,31 +468,15 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       // ---- D': full path, column pass from the plane into the padded float32 plane:
       // full[y][kFMarg + x] = sum_j tap[j] h[reflect(y - r + j)][x]; columns within r of an edge are
       // mirrored into the pad by the thread that produces them.
-      const int yblocks = (H + 7) >> 3;
-      for (int t = tid; t < W * yblocks; t += kFThreads) {
-        const int yb = fast_div(t, geo.div_W), x = t - yb * W;
-        const int y0 = yb * 8;
-        float acc[8];
-        const int need = 8 + 2 * r;
-        const bool inside = y0 - r >= 0 && y0 + 7 + r < H;
-        const T* col = plane + x;
-        conv8_gather(
-            [&](int j) -> float {
-              if (j >= need) return 0.0f;
-              const int yy = inside ? (y0 - r + j) : reflect1(y0 - r + j, H);
-              return Elem<T>::to_f32(col[yy * W]);
-            },
-            sh.gcol, nch_col, acc);
-        const bool left = x < r, right = x >= W - r;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          if (y0 + o < H) {
-            float* row = work + (y0 + o) * FS + kFMarg;
-            row[x] = acc[o];
-            if (left) row[-1 - x] = acc[o];
-            if (right) row[2 * W - 1 - x] = acc[o];
-          }
-        }
+      const int yblocks = (H + 3) >> 2, W2 = W >> 1, nch4 = (d + 3) >> 2;
+      const unsigned mW2 = div_magic(W2);
+      for (int t = tid; t < W2 * yblocks; t += kFThreads) {
+        const int yb = fast_div(t, mW2), x = (t - yb * W2) * 2;
+        const int y0 = yb * 4;
+        if (y0 - r >= 0 && y0 + 3 + r < H)
+          full_col_task<T, true>(plane, work, sh.gcol, nch4, x, y0, r, H, W, FS);
+        else
+          full_col_task<T, false>(plane, work, sh.gcol, nch4, x, y0, r, H, W, FS);
       }
     }
     __syncthreads();
