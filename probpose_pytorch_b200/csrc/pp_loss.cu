@@ -11,6 +11,7 @@
 // shared plane, P = 2 c gx and Q = 2 c gy go to two more planes, and the gradient is the 3x3 adjoint
 // stencil over them.  Supports every mode / weight / mask combination of the reference.
 #include <algorithm>
+#include <cstdlib>
 
 #include "pp_common.cuh"
 #include "pp_loss_fast.cuh"
@@ -265,13 +266,18 @@ int launch_loss(const LossArgs& a, bool fwd, bool grad, cudaStream_t st) {
 }
 
 // ---- fast path dispatch (pp_loss_fast.cuh) ---------------------------------------------------
+int env_int(const char* name, int fallback) {   // tuning overrides for experiments
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : fallback;
+}
+
 bool fast_path_ok(const pp_loss_params& p, const void* output, const void* target, const void* pixel_weights,
                   const void* mask, const void* grad) {
   const int e = p.dtype == PP_F32 ? 4 : 2;
   return p.mode == PP_LOSS_PIXEL_MEAN && !pixel_weights && !mask && !p.skip_empty_channel && p.W % 4 == 0 &&
          p.W / 4 <= 128 && (static_cast<int64_t>(p.H) * p.W * e) % 16 == 0 && pp_aligned16(output) &&
          pp_aligned16(target) && pp_aligned16(grad) &&
-         static_cast<int64_t>(p.H) * p.W * e + 160 <= pp_smem_optin();
+         2 * static_cast<int64_t>(p.H) * p.W * e + 512 <= pp_smem_optin();
 }
 
 template <typename T, bool kFwd, bool kGrad>
@@ -279,7 +285,8 @@ int launch_fast_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cud
   int per_sm = 1;
   auto kern = pp_loss_fast::oks_loss_fast_kernel<T, kFwd, kGrad>;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), threads, smem, &per_sm)) return rc;
-  const int grid = static_cast<int>(std::min<int64_t>(a.N, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  const int64_t units = (a.N + a.G - 1) / a.G;
+  const int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(pp_sm_count()) * per_sm));
   kern<<<grid, threads, smem, st>>>(a);
   PP_CUDA_OK(cudaGetLastError());
   *grid_out = grid;
@@ -297,10 +304,17 @@ int launch_fast(const pp_loss_params& p, const void* output, const void* target,
   a.N = static_cast<long long>(p.B) * p.K;
   a.H = p.H; a.W = p.W;
   a.strips = p.W / 4;
-  int segs = std::max(1, std::min(p.H / 4 > 0 ? p.H / 4 : 1, (112 + a.strips / 2) / a.strips));
+  // a thread owns a strip of 4 columns x T rows (plus a 2-row halo on each side that it recomputes):
+  // T ~ 16 keeps the halo overhead at 25 %; G consecutive heatmaps share a CTA so that it has ~96 threads
+  const int want_T = env_int("PP_LOSS_T", 8);
+  int segs = std::max(1, (p.H + want_T / 2) / want_T);
   a.T = (p.H + segs - 1) / segs;
   a.segs = (p.H + a.T - 1) / a.T;
   while (a.strips * a.segs > 256) { a.T *= 2; a.segs = (p.H + a.T - 1) / a.T; }
+  const int per = a.strips * a.segs;
+  a.G = std::max(1, std::min(4, env_int("PP_LOSS_G", (96 + per / 2) / per)));
+  while (a.G > 1 && per * a.G > 256) --a.G;
+  if (static_cast<long long>(a.G) > static_cast<long long>(p.B) * p.K) a.G = 1;
   a.w_s = static_cast<float>(p.smoothing_weight);
   a.w_g = static_cast<float>(p.gaussian_weight);
   a.w_o = static_cast<float>(1.0 - p.smoothing_weight - p.gaussian_weight);
@@ -311,11 +325,16 @@ int launch_fast(const pp_loss_params& p, const void* output, const void* target,
   else { a.a_o = 0.5f; a.a_t = 0.5f; a.d_a = 0.5f; a.d_b = -1.f; }
   a.inv_count = static_cast<float>(1.0 / (static_cast<double>(a.N) * p.H * p.W));
   a.plane_bytes = static_cast<unsigned>(static_cast<int64_t>(p.H) * p.W * e);
-  a.stage_bytes = (a.plane_bytes + 32 + 127) / 128 * 128;
-  a.stages = (2ull * a.stage_bytes <= static_cast<size_t>(pp_smem_optin()) / 2) ? 2 : 1;
+  for (;; --a.G) {
+    a.tgt_off = (16 + a.G * a.plane_bytes + 16 + 127) / 128 * 128;
+    a.stage_bytes = (a.tgt_off + a.G * a.plane_bytes + 127) / 128 * 128;
+    if (a.stage_bytes <= static_cast<size_t>(pp_smem_optin()) || a.G == 1) break;
+  }
+  // two stages (the next unit lands while the current one is processed) whenever they fit
+  a.stages = env_int("PP_LOSS_STAGES", 2);
   if (static_cast<size_t>(a.stages) * a.stage_bytes > static_cast<size_t>(pp_smem_optin())) a.stages = 1;
   const size_t smem = static_cast<size_t>(a.stages) * a.stage_bytes;
-  const int threads = a.strips * a.segs;
+  const int threads = a.strips * a.segs * a.G;
   const bool g = grad != nullptr;
   if (p.dtype == PP_F32) {
     if (fwd && g) return launch_fast_t<float, true, true>(a, threads, smem, st, grid_out);

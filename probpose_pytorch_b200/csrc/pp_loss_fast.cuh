@@ -15,7 +15,8 @@
 //     and, three rows later, emits one 128-bit gradient store.  The 1-pixel ring of gx/gy a strip needs
 //     from its neighbours is recomputed instead of exchanged, so there is no shared-memory write and no
 //     barrier inside a heatmap;
-//   * `target` is read straight from global memory with 128-bit streaming loads, two rows ahead of use.
+//   * `target` rides in the same TMA stage (second bulk copy on the same mbarrier): no thread ever
+//     waits on a global load.
 #pragma once
 
 #include "pp_common.cuh"
@@ -35,18 +36,17 @@ struct FastArgs {
   float host_scale;
   long long N;
   int H, W, strips, segs, T, stages;
+  int G;                     // consecutive heatmaps processed together by one CTA (one TMA copy)
   float w_s, w_o, w_g, lw;
   float a_o, a_t;            // oks(o, t) = a_o o + a_t t - o t
   float d_a, d_b;            // d oks / d o = d_a + d_b t
   float inv_count;           // 1 / (N H W)
-  unsigned plane_bytes, stage_bytes;
+  unsigned plane_bytes, stage_bytes, tgt_off;   // tgt_off: byte offset of the target planes inside a stage
 };
 
 struct RowState {
   float hd[3][6], hs[3][6];  // row factors of the Sobel pair, rows r-2, r-1, r
   float dP[3][4], sQ[3][4];  // row factors of the adjoint stencil, rows r-3, r-2, r-1
-  float oc[3][4];            // `output` at the strip, rows r-2, r-1, r
-  float tt[3][4];            // `target` at the strip, rows r-2, r-1, r
 };
 
 template <typename T>
@@ -70,16 +70,15 @@ __device__ __forceinline__ void load_strip8<__nv_bfloat16>(const __nv_bfloat16* 
 }
 
 template <typename T>
-__device__ __forceinline__ void load_target4(const T* p, float (&v)[4]);
+__device__ __forceinline__ void load_strip4(const T* p, float (&v)[4]);   // shared memory, strip-aligned
 template <>
-__device__ __forceinline__ void load_target4<float>(const float* p, float (&v)[4]) {
-  const uint4 w = ldg_stream_128(p);
-  v[0] = __uint_as_float(w.x); v[1] = __uint_as_float(w.y); v[2] = __uint_as_float(w.z); v[3] = __uint_as_float(w.w);
+__device__ __forceinline__ void load_strip4<float>(const float* p, float (&v)[4]) {
+  const float4 w = *reinterpret_cast<const float4*>(p);
+  v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
 }
 template <>
-__device__ __forceinline__ void load_target4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
-  uint2 w;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p));
+__device__ __forceinline__ void load_strip4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
   v[0] = __uint_as_float(w.x << 16); v[1] = __uint_as_float(w.x & 0xffff0000u);
   v[2] = __uint_as_float(w.y << 16); v[3] = __uint_as_float(w.y & 0xffff0000u);
 }
@@ -131,9 +130,6 @@ __device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& c
     st.hd[cur][j] = av[j] - av[j + 2];
     st.hs[cur][j] = (av[j] + av[j + 2]) + 2.0f * av[j + 1];
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) st.oc[cur][i] = av[2 + i];
-  if (r >= y0 && r < y1) load_target4<T>(tgt + r * W + x0, st.tt[cur]);  // consumed two steps later
 
   // 2. gx, gy at row r-1, columns x0-1 .. x0+4
   const int rm = r - 1;
@@ -164,10 +160,12 @@ __device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& c
   // 3. emit row r-2
   const int ro = r - 2;
   if (ro >= y0 && ro < y1) {
-    float g[4];
+    float g[4], ov[4], tv[4];
+    load_strip4<T>(plane + ro * W + x0, ov);
+    load_strip4<T>(tgt + ro * W + x0, tv);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float o = st.oc[p2][i], t = st.tt[p2][i];
+      const float o = ov[i], t = tv[i];
       if (kFwd) {
         sums.so += cf.a_o * o + cf.a_t * t - o * t;
         if (cf.has_mse) { const float d = o - t; sums.sm += d * d; }
@@ -197,14 +195,22 @@ oks_loss_fast_kernel(FastArgs a) {
   const int tid = threadIdx.x;
   const int H = a.H, W = a.W;
   const long long HW = static_cast<long long>(H) * W;
-  const int sx = tid % a.strips, sy = tid / a.strips;
+  const int per = a.strips * a.segs;           // threads per heatmap
+  const int g = tid / per, local = tid - g * per;
+  const int sx = local % a.strips, sy = local / a.strips;
   const int x0 = sx * 4, y0 = sy * a.T, y1 = min(y0 + a.T, H);
   const bool left_ok = sx > 0, right_ok = sx < a.strips - 1;
   const T* out = static_cast<const T*>(a.output);
   const T* tgt_all = static_cast<const T*>(a.target);
+  auto tgt_stage_of = [&](int s) { return reinterpret_cast<const T*>(stage_mem + static_cast<size_t>(s) * a.stage_bytes + a.tgt_off); };
   T* grad_all = static_cast<T*>(a.grad);
-  // 16 bytes of slack in front of / behind each plane keep the halo reads of the first / last strip in bounds
-  auto plane_of = [&](int s) { return reinterpret_cast<const T*>(stage_mem + static_cast<size_t>(s) * a.stage_bytes + 16); };
+  // 16 bytes of slack in front of / behind each stage keep the halo reads of the first / last strip in bounds
+  auto stage_of = [&](int s) { return reinterpret_cast<const T*>(stage_mem + static_cast<size_t>(s) * a.stage_bytes + 16); };
+  const long long units = (a.N + a.G - 1) / a.G;
+  auto unit_bytes = [&](long long u) {
+    const long long left = a.N - u * a.G;
+    return static_cast<unsigned>((left < a.G ? left : a.G) * a.plane_bytes);
+  };
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -217,24 +223,26 @@ oks_loss_fast_kernel(FastArgs a) {
   float u = a.host_scale * a.inv_count;
   if (kGrad && a.upstream) u *= a.upstream[0];
 
-  long long hm = blockIdx.x;
-  if (tid == 0 && hm < a.N) {
-    mbar_expect_tx(&bars[0], a.plane_bytes);
-    tma_load_1d(const_cast<T*>(plane_of(0)), out + hm * HW, a.plane_bytes, &bars[0]);
-  }
+  long long unit = blockIdx.x;
+  auto fetch_unit = [&](long long un, int s) {   // `output` and `target` of a unit land in stage s
+    const unsigned bytes = unit_bytes(un);
+    mbar_expect_tx(&bars[s], 2 * bytes);
+    tma_load_1d(const_cast<T*>(stage_of(s)), out + un * a.G * HW, bytes, &bars[s]);
+    tma_load_1d(const_cast<T*>(tgt_stage_of(s)), tgt_all + un * a.G * HW, bytes, &bars[s]);
+  };
+  if (tid == 0 && unit < units) fetch_unit(unit, 0);
 
   double acc = 0.0;
   Sums sums{0.f, 0.f, 0.f, INFINITY, -INFINITY};
   const int nsteps = (y1 - y0) + 4;
 
-  for (int it = 0; hm < a.N; hm += gridDim.x, ++it) {
+  for (int it = 0; unit < units; unit += gridDim.x, ++it) {
     const int s = (a.stages == 2) ? (it & 1) : 0;
-    const long long nxt = hm + gridDim.x;
-    if (a.stages == 2 && tid == 0 && nxt < a.N) {  // prefetch the next heatmap into the other stage
-      mbar_expect_tx(&bars[s ^ 1], a.plane_bytes);
-      tma_load_1d(const_cast<T*>(plane_of(s ^ 1)), out + nxt * HW, a.plane_bytes, &bars[s ^ 1]);
-    }
-    const float m = a.kp_weights ? a.kp_weights[hm] : 1.0f;
+    const long long nxt = unit + gridDim.x;
+    if (a.stages == 2 && tid == 0 && nxt < units) fetch_unit(nxt, s ^ 1);  // prefetch into the other stage
+    const long long hm = unit * a.G + g;
+    const bool active = g < a.G && hm < a.N && sy < a.segs;
+    const float m = (active && a.kp_weights) ? a.kp_weights[hm] : 1.0f;
     Coef cf;
     cf.c2 = 2.0f * a.lw * a.w_s * u * m;
     cf.k_a = a.lw * u * m * a.w_o * a.d_a;
@@ -243,7 +251,6 @@ oks_loss_fast_kernel(FastArgs a) {
     cf.a_o = a.a_o; cf.a_t = a.a_t;
     cf.has_mse = a.w_g != 0.0f;
 
-    const T* tgt = tgt_all + hm * HW;
     T* grad = kGrad ? grad_all + hm * HW : nullptr;
     RowState st;
 #pragma unroll
@@ -251,13 +258,14 @@ oks_loss_fast_kernel(FastArgs a) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) { st.hd[i][j] = 0.f; st.hs[i][j] = 0.f; }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { st.dP[i][j] = 0.f; st.sQ[i][j] = 0.f; st.oc[i][j] = 0.f; st.tt[i][j] = 0.f; }
+      for (int j = 0; j < 4; ++j) { st.dP[i][j] = 0.f; st.sQ[i][j] = 0.f; }
     }
     sums.se = sums.so = sums.sm = 0.f;
 
     mbar_wait(&bars[s], (a.stages == 2) ? ((it >> 1) & 1) : (it & 1));
-    const T* plane = plane_of(s);
-    if (sy < a.segs) {
+    const T* plane = stage_of(s) + static_cast<size_t>(g) * HW;
+    const T* tgt = tgt_stage_of(s) + static_cast<size_t>(g) * HW;
+    if (active) {
       for (int q = 0; q < nsteps; q += 3) {
         row_step<T, kFwd, kGrad, 0>(st, sums, cf, q, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
         if (q + 1 < nsteps)
@@ -265,17 +273,14 @@ oks_loss_fast_kernel(FastArgs a) {
         if (q + 2 < nsteps)
           row_step<T, kFwd, kGrad, 2>(st, sums, cf, q + 2, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
       }
-    }
-    if (kFwd) {
-      // per-pixel loss = (w_s e + w_o oks + w_g mse) m lw (loss.py:122-127, 143), summed per strip
-      const float part = (a.w_s * sums.se + a.w_o * sums.so + a.w_g * sums.sm) * (m * a.lw);
-      acc += static_cast<double>(part);
+      if (kFwd) {
+        // per-pixel loss = (w_s e + w_o oks + w_g mse) m lw (loss.py:122-127, 143), summed per strip
+        const float part = (a.w_s * sums.se + a.w_o * sums.so + a.w_g * sums.sm) * (m * a.lw);
+        acc += static_cast<double>(part);
+      }
     }
     __syncthreads();  // every thread is done with stage s before it is refilled
-    if (a.stages == 1 && tid == 0 && nxt < a.N) {
-      mbar_expect_tx(&bars[0], a.plane_bytes);
-      tma_load_1d(const_cast<T*>(plane_of(0)), out + nxt * HW, a.plane_bytes, &bars[0]);
-    }
+    if (a.stages == 1 && tid == 0 && nxt < units) fetch_unit(nxt, 0);
   }
 
   if (kFwd) {
