@@ -64,8 +64,14 @@ int pp_configure_kernel(const void* kernel, int threads, size_t smem, int* ctas_
       return PP_OK;
     }
   }
-  if (smem > 48 * 1024)
-    PP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // always opt in to the device maximum: a smaller later request must not shrink the limit that an
+  // earlier (cached) configuration of the same kernel relies on
+  cudaFuncAttributes fa{};
+  PP_CUDA_OK(cudaFuncGetAttributes(&fa, kernel));
+  const int64_t dyn_max = pp_smem_optin() - static_cast<int64_t>(fa.sharedSizeBytes);
+  PP_REQUIRE(static_cast<int64_t>(smem) <= dyn_max, PP_ERR_UNSUPPORTED_SHAPE,
+             "kernel needs %zu bytes of dynamic shared memory, only %lld available", smem, static_cast<long long>(dyn_max));
+  PP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_max)));
   int per_sm = 0;
   PP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
   PP_REQUIRE(per_sm >= 1, PP_ERR_UNSUPPORTED_SHAPE, "kernel does not fit on an SM (threads=%d, smem=%zu)", threads, smem);
