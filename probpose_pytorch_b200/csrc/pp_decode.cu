@@ -726,7 +726,8 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
     int fper = 1;
     if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_fast_kernel<T>), kFThreads, fsmem, &fper))
       return rc;
-    const int fgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper));
+    int64_t fgrid64 = std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper);
+    const int fgrid = static_cast<int>(fgrid64);
     decode_expected_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, geo);
     PP_CUDA_OK(cudaGetLastError());
     return PP_OK;
@@ -772,6 +773,18 @@ int check_decode_params(const char* fn, const pp_decode_params* p) {
 }
 
 }  // namespace
+
+#ifdef PP_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int pp_debug_phase_cycles(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -3;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 extern "C" {
 

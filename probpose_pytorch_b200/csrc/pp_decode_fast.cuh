@@ -29,6 +29,22 @@
 // (profiles/r01c: stall_no_inst dominated every line).
 #pragma once
 
+// Developer-only phase timing (build with -DPP_PHASE_TIMING): thread 0 of every CTA accumulates the
+// cycles between phase marks into a device array that tools/decode_phases.py reads back.
+#ifdef PP_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PP_MARK(slot)                                                         \
+  do {                                                                        \
+    if (threadIdx.x == 0) {                                                   \
+      const long long now_ = clock64();                                       \
+      atomicAdd(&g_phase_cycles[slot], static_cast<unsigned long long>(now_ - mark_)); \
+      mark_ = now_;                                                           \
+    }                                                                         \
+  } while (0)
+#else
+#define PP_MARK(slot) do { } while (0)
+#endif
+
 constexpr int kFThreads = 128;
 constexpr int kFWarps = kFThreads / 32;
 constexpr int kFRegion = 24;                    // largest output region side of the tile path
@@ -39,6 +55,8 @@ constexpr int kFTmpRows = kFRegion + 2 * PP_MAX_OKS_RADIUS;          // 42
 constexpr int kFTmpStride = 28;                 // 24 -> multiple of 4 with odd quarter
 constexpr int kFTileFloats = kFTileRows * kFTileStride + (kFTmpRows + 8) * kFTmpStride;
 constexpr int kFTaps = 24;                      // taps padded to 3 chunks of 8
+constexpr int kFMaxChannels = 2048;
+constexpr int kFGroup = 25;                     // threads per exact evaluation (5 evaluations at once)             // per-channel scheduling uses the work area as scratch
 
 struct FastGeom {
   unsigned plane_bytes;   // H*W*sizeof(T)
@@ -57,7 +75,10 @@ struct FastShared {
   __align__(16) float grow[kFTaps];   // row-pass taps, shifted so that the window starts 16-byte aligned
   __align__(16) float gcol[kFTaps];   // column-pass taps
   float nb[4];
-  float L, e0;
+  float L;
+  int p0;
+  int ev_idx[5];      // pixels handed to the grouped exact evaluation
+  float ev_val[5];
   int bbox[4];        // min x, max x, min y, max y of S
   int cand[kMaxCand];
   int cand_count;
@@ -290,6 +311,7 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   extern __shared__ __align__(128) unsigned char fsm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ FastShared sh;
+  __shared__ double ev_part[kFThreads];
 
   const T* plane = reinterpret_cast<const T*>(fsm);
   T* plane_rw = reinterpret_cast<T*>(fsm);
@@ -316,19 +338,67 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   // stale work-area contents only ever meet zero taps or unused outputs, but they must be finite
   for (int i = tid; i < static_cast<int>(geo.work_floats); i += kFThreads) work[i] = 0.0f;
   __syncthreads();
-  int64_t hm = blockIdx.x;
+  // ---- work distribution.  With at least one CTA per keypoint channel, a CTA serves ONE channel k for
+  // its whole life (tables staged once) and the CTAs are shared out between the channels in proportion to
+  // a cost model of their kernel radius (wide kernels take ~1.7x longer per heatmap than narrow ones), so
+  // that all channels finish together.  CTA j of the C_k CTAs of channel k takes images j, j + C_k, ...
+  // Smaller launches fall back to plain striding over the heatmaps.
+  __shared__ int sched[3];   // k, first image, image stride
+  const bool by_channel = static_cast<int>(gridDim.x) >= p.K && p.K <= kFMaxChannels;
+  if (by_channel) {
+    int* wsum = reinterpret_cast<int*>(work);   // scratch: prefix sums of the channel weights
+    for (int kk = tid; kk < p.K; kk += kFThreads) wsum[kk] = 35 + 4 * tab.radius[kk];
+    __syncthreads();
+    if (tid == 0) {
+      long long total = 0;
+      for (int kk = 0; kk < p.K; ++kk) total += wsum[kk];
+      const long long spare = static_cast<long long>(gridDim.x) - p.K;   // beyond one CTA per channel
+      long long acc = 0;
+      int first = 0, found_k = p.K - 1, found_first = 0, found_n = 1;
+      for (int kk = 0; kk < p.K; ++kk) {
+        const long long lo = acc * spare / total;
+        acc += wsum[kk];
+        const long long hi = acc * spare / total;
+        const int n = 1 + static_cast<int>(hi - lo);
+        if (static_cast<int>(blockIdx.x) >= first && static_cast<int>(blockIdx.x) < first + n) {
+          found_k = kk; found_first = first; found_n = n;
+        }
+        first += n;
+      }
+      sched[0] = found_k;
+      sched[1] = static_cast<int>(blockIdx.x) - found_first;
+      sched[2] = found_n;
+    }
+    __syncthreads();
+    for (int kk = tid; kk < p.K; kk += kFThreads) wsum[kk] = 0;   // the work area must hold finite floats
+    __syncthreads();
+  }
+  const int my_k = by_channel ? sched[0] : 0;
+  // heatmap index as a function of the iteration
+  const int64_t hm_first = by_channel ? static_cast<int64_t>(sched[1]) * p.K + my_k : blockIdx.x;
+  const int64_t hm_step = by_channel ? static_cast<int64_t>(sched[2]) * p.K : gridDim.x;
+  int64_t hm = hm_first;
   if (tid == 0 && hm < N) {
     mbar_expect_tx(&bar, geo.plane_bytes);
     tma_load_1d(fsm, heatmaps + hm * HW, geo.plane_bytes, &bar);
   }
 
-  for (int it = 0; hm < N; hm += gridDim.x, ++it) {
-    const int k = static_cast<int>(hm % p.K);
-    const int r = tab.radius[k];
-    const int d = 2 * r + 1;
-    const int padr = (r + 3) & ~3, shift = padr - r;
-    const int nch_row = (shift + d + 7) >> 3, nch_col = (d + 7) >> 3;
-    {
+  int k_loaded = -1, r = 1, d = 3, padr = 4, nch_row = 1, nch_col = 1;
+  const int k_step = by_channel ? 0 : static_cast<int>(gridDim.x % p.K);
+  int k = static_cast<int>(hm % p.K);
+
+#ifdef PP_PHASE_TIMING
+  long long mark_ = clock64();
+#endif
+  for (int it = 0; hm < N; hm += hm_step, ++it) {
+    if (k != k_loaded) {
+      __syncthreads();   // nobody still reads the previous tables
+      r = tab.radius[k];
+      d = 2 * r + 1;
+      padr = (r + 3) & ~3;
+      const int shift = padr - r;
+      nch_row = (shift + d + 7) >> 3;
+      nch_col = (d + 7) >> 3;
       const double* src = tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
       for (int i = tid; i < d * d; i += kFThreads) w2d[i] = src[i];
       const float* t1 = tab.taps_f32 + k * PP_OKS_TAPS;
@@ -336,50 +406,47 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
         sh.gcol[tid] = tid < d ? t1[tid] : 0.0f;
         sh.grow[tid] = (tid >= shift && tid < shift + d) ? t1[tid - shift] : 0.0f;
       }
+      k_loaded = k;
     }
     if (tid == 0) {
       sh.bbox[0] = W; sh.bbox[1] = -1; sh.bbox[2] = H; sh.bbox[3] = -1;
       sh.cand_count = 0;
     }
+    PP_MARK(0);   // loop top / tables
     mbar_wait(&bar, it & 1);
+    PP_MARK(1);   // TMA wait
 
-    // ---- A: one scan of the plane: max (first index) and min.  The head tail (head.py:526-532), when
-    // requested, is applied here once, in place, so that every later phase reads plain values.
-    float xmax = -INFINITY, xmin = INFINITY;
-    int imax = 0x7fffffff;
-#pragma unroll 2
-    for (int i = tid; i < HW / V; i += kFThreads) {
-      float f[V];
-      uint4* vec = reinterpret_cast<uint4*>(plane_rw + i * V);
-      unpack(*vec, f, T());
-      if (tail) {
+    // ---- A: one scan of the plane: max and min (the index of a maximum is looked up afterwards by the
+    // threads that hold it).  The head tail (head.py:526-532), when requested, is applied first, once,
+    // in place, so that every later phase reads plain values.
+    if (tail) {
+      for (int i = tid; i < HW / V; i += kFThreads) {
+        float f[V];
+        uint4* vec = reinterpret_cast<uint4*>(plane_rw + i * V);
+        unpack(*vec, f, T());
 #pragma unroll
         for (int j = 0; j < V; ++j) f[j] = tail_value<T>(f[j], temp);
         *vec = pack(f, T());
       }
-      float m = f[0], lo = f[0];
-#pragma unroll
-      for (int j = 1; j < V; ++j) { m = fmaxf(m, f[j]); lo = fminf(lo, f[j]); }
-      xmin = fminf(xmin, lo);
-      if (m > xmax) {   // rare after the first few vectors
-        xmax = m;
-        int jj = V - 1;
-#pragma unroll
-        for (int j = V - 2; j >= 0; --j) jj = (f[j] == m) ? j : jj;
-        imax = i * V + jj;
-      }
     }
-    warp_argmax(xmax, imax);
+    float xmax = -INFINITY, xmin = INFINITY;
+#pragma unroll 2
+    for (int i = tid; i < HW / V; i += kFThreads) {
+      float f[V];
+      unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+#pragma unroll
+      for (int j = 0; j < V; ++j) { xmax = fmaxf(xmax, f[j]); xmin = fminf(xmin, f[j]); }
+    }
+    const float tmax = xmax;   // this thread's own maximum
+    xmax = warp_max(xmax);
     xmin = -warp_max(-xmin);
-    if (lane == 0) { sh.red_f[0][warp] = xmax; sh.red_f[1][warp] = xmin; sh.red_i[warp] = imax; }
+    if (lane == 0) { sh.red_f[0][warp] = xmax; sh.red_f[1][warp] = xmin; }
+    if (tid == 0) sh.p0 = 0x7fffffff;
     __syncthreads();
-    xmax = sh.red_f[0][0]; xmin = sh.red_f[1][0]; imax = sh.red_i[0];
-#pragma unroll
-    for (int w = 1; w < kFWarps; ++w) {
-      argmax_combine(xmax, imax, sh.red_f[0][w], sh.red_i[w]);
-      xmin = fminf(xmin, sh.red_f[1][w]);
-    }
+    xmax = fmaxf(fmaxf(sh.red_f[0][0], sh.red_f[0][1]), fmaxf(sh.red_f[0][2], sh.red_f[0][3]));
+    xmin = fminf(fminf(sh.red_f[1][0], sh.red_f[1][1]), fminf(sh.red_f[1][2], sh.red_f[1][3]));
     const float vmax = xmax, vmin = xmin;
+    PP_MARK(2);   // scan A
 
     // every flag below is uniform across the CTA
     const bool constant = vmax == vmin;   // e.g. all zeros after the clamp: first index wins, border pixel
@@ -396,15 +463,41 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
     ectx.tile_path = false;
 
     if (!constant) {
-      // ---- B: L = exact convolved value at the raw maximum p0 (minus a few ulp: later evaluations may
-      // sum the same terms in a different order)
+      // ---- B: the raw maximum p0 and a lower bound L of the convolved maximum
+      if (tmax == xmax) {   // lowest index among the pixels that hold the maximum
+        int idx = 0x7fffffff;
+        for (int i = tid; i < HW / V && idx == 0x7fffffff; i += kFThreads) {
+          float f[V];
+          unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+#pragma unroll
+          for (int j = V - 1; j >= 0; --j) idx = (f[j] == xmax) ? i * V + j : idx;
+        }
+        atomicMin(&sh.p0, idx);
+      }
+      __syncthreads();
+      const int imax = sh.p0;
       const int py = fast_div(imax, geo.div_W), px = imax - py * W;
       if (warp == 0) {
-        const float e = exact_eval<T>(ectx, py, px);
-        if (lane == 0) { sh.e0 = e; sh.L = e - fabsf(e) * 2.4e-7f; }
+        // L: a lower bound of R(p0), hence of max R, from the central 5 x 5 taps and "everything else is
+        // at least vmin" (the taps are non-negative and sum to 1):  sum_25 w h + (1 - sum_25 w) vmin.
+        // For the narrowest kernels (d = 5) this is R(p0) itself.
+        const int half = min(2, r), side = 2 * half + 1;
+        double sw = 0.0, swh = 0.0;
+        if (lane < side * side) {
+          const int ti = lane / side, tj = lane - ti * side;
+          const double w = w2d[(r - half + ti) * d + (r - half + tj)];
+          const float v = plane_value<T>(plane, reflect1(py - half + ti, H) * W + reflect1(px - half + tj, W));
+          sw = w; swh = w * static_cast<double>(v);
+        }
+        sw = warp_sum(sw); swh = warp_sum(swh);
+        if (lane == 0) {
+          const float e = static_cast<float>(swh + fmax(1.0 - sw, 0.0) * static_cast<double>(xmin));
+          sh.L = e - fabsf(e) * 1e-6f - 1e-37f;
+        }
       }
       __syncthreads();
       const float L = sh.L;
+      PP_MARK(3);   // B: p0 + exact L
 
       // ---- C: bounding box of S = {h >= L}
       int bx0 = W, bx1 = -1, by0 = H, by1 = -1;
@@ -431,16 +524,27 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
           if (xv >= WV) { xv -= WV; ++y; }
         }
       }
+      {
+        const bool mine = bx1 >= 0;
+        const unsigned holders = __ballot_sync(0xffffffffu, mine);
+        if (holders != 0u && __popc(holders) <= 6) {   // blob-shaped maps: a few lanes publish directly
+          if (mine) {
+            atomicMin(&sh.bbox[0], bx0); atomicMax(&sh.bbox[1], bx1);
+            atomicMin(&sh.bbox[2], by0); atomicMax(&sh.bbox[3], by1);
+          }
+        } else if (holders != 0u) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-        bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-        by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-        by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-      }
-      if (lane == 0 && bx1 >= 0) {
-        atomicMin(&sh.bbox[0], bx0); atomicMax(&sh.bbox[1], bx1);
-        atomicMin(&sh.bbox[2], by0); atomicMax(&sh.bbox[3], by1);
+          for (int o = 16; o > 0; o >>= 1) {
+            bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+            bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+            by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+            by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+          }
+          if (lane == 0) {
+            atomicMin(&sh.bbox[0], bx0); atomicMax(&sh.bbox[1], bx1);
+            atomicMin(&sh.bbox[2], by0); atomicMax(&sh.bbox[3], by1);
+          }
+        }
       }
       __syncthreads();
       // p0 itself is in S (h(p0) = max >= R(p0)), so the box is never empty
@@ -449,6 +553,7 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       OW = min(sh.bbox[1] + r, W - 1) - ox0 + 1;
       OH = min(sh.bbox[3] + r, H - 1) - oy0 + 1;
       tile_path = OW <= kFRegion && OH <= kFRegion;
+      PP_MARK(4);   // C: bounding box
     }
 
     if (!constant && tile_path) {
@@ -480,8 +585,9 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       }
     }
     __syncthreads();
+    PP_MARK(5);   // D: gather / column pass
     const bool plane_free = constant || tile_path;   // the full path still needs the plane for step G
-    const int64_t nxt = hm + gridDim.x;
+    const int64_t nxt = hm + hm_step;
     if (plane_free && tid == 0 && nxt < N) {   // the next heatmap streams in while this one is finished
       fence_proxy_async();
       mbar_expect_tx(&bar, geo.plane_bytes);
@@ -542,6 +648,7 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       pmax = warp_max(pmax);
       if (lane == 0) sh.red_f[0][warp] = pmax;
       __syncthreads();
+      PP_MARK(6);   // E/F: prefilter
       pmax = fmaxf(fmaxf(sh.red_f[0][0], sh.red_f[0][1]), fmaxf(sh.red_f[0][2], sh.red_f[0][3]));
       const float amax = fmaxf(fabsf(vmax), fabsf(vmin));
       const float gamma = static_cast<float>(2 * d + 8) * 1.1920929e-7f;   // (2d + 8) * 2^-23
@@ -576,53 +683,119 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       }
       __syncthreads();
       const int count = sh.cand_count;
+      PP_MARK(7);   // candidates
 
-      // ---- G: exact values of the candidates
+      // ---- G: exact values (double accumulation of the reference's d x d table, float32 result) of the
+      // candidates and of the winner's four neighbours.  Up to five pixels are evaluated at once: group g
+      // (25 threads) strides the taps of pixel sh.ev_idx[g]; the partial sums meet in shared memory and
+      // are added in a fixed order.
       ectx.tile_path = tile_path; ectx.oy0 = oy0; ectx.ox0 = ox0;
-      auto exact_at = [&](int y, int x) -> float { return exact_eval<T>(ectx, y, x); };
-      if (count == 1 && sh.cand[0] == imax) {
-        // the usual case: the convolved maximum sits on the raw maximum, whose exact value is known from B
-        best = imax;
-        best_val = sh.e0;
+      auto run_evals = [&](int n) {
+        __syncthreads();   // sh.ev_idx is visible
+        const int g = tid / kFGroup, gl = tid - g * kFGroup;
+        if (g < n) {
+          const int idx = sh.ev_idx[g], y = fast_div(idx, geo.div_W), x = idx - y * W;
+          const int nt = d * d, q25 = kFGroup / d, r25 = kFGroup - q25 * d;
+          int ti = gl / d, tj = gl - ti * d;
+          double a0 = 0.0, a1 = 0.0;
+          if (tile_path) {
+            const float* base = tile + (y - oy0 + 1) * kFTileStride + (x - ox0 + kFMarg - r);
+#pragma unroll 1
+            for (int i = gl; i < nt; i += 2 * kFGroup) {
+              a0 = fma(w2d[i], static_cast<double>(base[ti * kFTileStride + tj]), a0);
+              tj += r25; ti += q25;
+              if (tj >= d) { tj -= d; ++ti; }
+              if (i + kFGroup < nt) a1 = fma(w2d[i + kFGroup], static_cast<double>(base[ti * kFTileStride + tj]), a1);
+              tj += r25; ti += q25;
+              if (tj >= d) { tj -= d; ++ti; }
+            }
+          } else {
+#pragma unroll 1
+            for (int i = gl; i < nt; i += 2 * kFGroup) {
+              a0 = fma(w2d[i], static_cast<double>(plane_value<T>(plane, reflect1(y + ti - r, H) * W + reflect1(x + tj - r, W))), a0);
+              tj += r25; ti += q25;
+              if (tj >= d) { tj -= d; ++ti; }
+              if (i + kFGroup < nt)
+                a1 = fma(w2d[i + kFGroup], static_cast<double>(plane_value<T>(plane, reflect1(y + ti - r, H) * W + reflect1(x + tj - r, W))), a1);
+              tj += r25; ti += q25;
+              if (tj >= d) { tj -= d; ++ti; }
+            }
+          }
+          ev_part[tid] = a0 + a1;
+        }
+        __syncthreads();
+        if (tid < n) {
+          double sum = 0.0;
+#pragma unroll 5
+          for (int j = 0; j < kFGroup; ++j) sum += ev_part[tid * kFGroup + j];
+          sh.ev_val[tid] = static_cast<float>(sum);
+        }
+        __syncthreads();
+      };
+      auto set_neighbours = [&](int first_slot, int by, int bx) {   // left, right, up, down
+        if (tid < 4) {
+          const int dx = (tid == 0) ? -1 : (tid == 1) ? 1 : 0;
+          const int dy = (tid == 2) ? -1 : (tid == 3) ? 1 : 0;
+          sh.ev_idx[first_slot + tid] = (by + dy) * W + bx + dx;
+        }
+      };
+
+      bool have_nb = false;
+      if (count == 1) {
+        // the usual case: a single pixel can be the maximum; its value and its neighbours in one round
+        best = sh.cand[0];
+        const int by = fast_div(best, geo.div_W), bx = best - by * W;
+        interior = bx > 0 && bx < W - 1 && by > 0 && by < H - 1;
+        if (interior) {
+          if (tid == 0) sh.ev_idx[0] = best;
+          set_neighbours(1, by, bx);
+          run_evals(5);
+          best_val = sh.ev_val[0];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) nb[q] = sh.ev_val[1 + q];
+        }
+        have_nb = true;
+      } else if (count <= kMaxCand) {
+        best_val = -INFINITY; best = 0x7fffffff;
+        for (int base = 0; base < count; base += 5) {
+          const int n = min(5, count - base);
+          if (tid < n) sh.ev_idx[tid] = sh.cand[base + tid];
+          run_evals(n);
+          for (int j = 0; j < n; ++j) argmax_combine(best_val, best, sh.ev_val[j], sh.cand[base + j]);
+        }
       } else {
         float wv = -INFINITY;
         int wi = 0x7fffffff;
-        if (count <= kMaxCand) {
-          for (int c = warp; c < count; c += kFWarps) {
-            const int idx = sh.cand[c], y = fast_div(idx, geo.div_W), x = idx - y * W;
-            argmax_combine(wv, wi, exact_at(y, x), idx);
-          }
-        } else {
-          OverflowCtx oc;
-          oc.src = tile_path ? tmp : work + kFMarg - r;
-          oc.step = tile_path ? kFTmpStride : 1;
-          oc.row_stride = tile_path ? kFTmpStride : FS;
-          oc.x_lo = tile_path ? ox0 : 0; oc.y_lo = tile_path ? oy0 : 0;
-          oc.x_n = tile_path ? OW : W; oc.y_n = tile_path ? OH : H;
-          oc.taps = sh.gcol; oc.thr = thr;
-          overflow_scan<T>(oc, ectx, wv, wi);
-        }
+        OverflowCtx oc;
+        oc.src = tile_path ? tmp : work + kFMarg - r;
+        oc.step = tile_path ? kFTmpStride : 1;
+        oc.row_stride = tile_path ? kFTmpStride : FS;
+        oc.x_lo = tile_path ? ox0 : 0; oc.y_lo = tile_path ? oy0 : 0;
+        oc.x_n = tile_path ? OW : W; oc.y_n = tile_path ? OH : H;
+        oc.taps = sh.gcol; oc.thr = thr;
+        overflow_scan<T>(oc, ectx, wv, wi);
         if (lane == 0) { sh.red_f[0][warp] = wv; sh.red_i[warp] = wi; }
         __syncthreads();
         best_val = sh.red_f[0][0]; best = sh.red_i[0];
 #pragma unroll
         for (int w = 1; w < kFWarps; ++w) argmax_combine(best_val, best, sh.red_f[0][w], sh.red_i[w]);
       }
+      PP_MARK(8);   // G: exact candidates
       const int by = fast_div(best, geo.div_W), bx = best - by * W;
-      interior = bx > 0 && bx < W - 1 && by > 0 && by < H - 1;
-      if (interior) {
-        const int dx = (warp == 0) ? -1 : (warp == 1) ? 1 : 0;
-        const int dy = (warp == 2) ? -1 : (warp == 3) ? 1 : 0;
-        const float e = exact_at(by + dy, bx + dx);
-        if (lane == 0) sh.nb[warp] = e;
-        __syncthreads();
+      if (!have_nb) {
+        interior = bx > 0 && bx < W - 1 && by > 0 && by < H - 1;
+        if (interior) {
+          set_neighbours(0, by, bx);
+          run_evals(4);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) nb[q] = sh.nb[q];
+          for (int q = 0; q < 4; ++q) nb[q] = sh.ev_val[q];
+        }
       }
       score = tile_path ? tile[(by - oy0 + r + 1) * kFTileStride + bx - ox0 + kFMarg]
                         : plane_value<T>(plane, best);
     }
 
+    PP_MARK(9);   // neighbours
     // ---- H: outputs
     if (tid == 0) {
       const int by = fast_div(best, geo.div_W), bx = best - by * W;
@@ -647,11 +820,15 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
         keypoints[hm * 2 + 1] = static_cast<double>(fy) / static_cast<double>(H - 1) * p.input_h;
       }
     }
+    PP_MARK(10);  // H: outputs
     __syncthreads();   // work area / scratch / plane are reused by the next heatmap
+    PP_MARK(11);  // final barrier
     if (!plane_free && tid == 0 && nxt < N) {
       fence_proxy_async();
       mbar_expect_tx(&bar, geo.plane_bytes);
       tma_load_1d(fsm, heatmaps + nxt * HW, geo.plane_bytes, &bar);
     }
+    k += k_step;
+    if (k >= p.K) k -= p.K;
   }
 }
