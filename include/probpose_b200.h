@@ -134,6 +134,23 @@ PP_API int pp_decode_argmax_dark(const pp_decode_params* p,
 /* head tail (head.py:526-532, normalize=None): y = clamp(x / temperature, 0, 1) */
 PP_API int pp_heatmap_tail(const void* x, void* y, int32_t dtype, int64_t numel, float temperature, pp_stream_t stream);
 
+/* backward of the head tail: grad_x = grad_y / temperature where 0 <= x / temperature <= 1, else 0
+ * (what autograd derives for torch.clamp(x / t, 0, 1), head.py:528-531) */
+PP_API int pp_heatmap_tail_backward(const void* x, const void* grad_y, void* grad_x, int32_t dtype, int64_t numel,
+                                    float temperature, pp_stream_t stream);
+
+/* ---- training targets from decoded keypoints: ProbPoseLoss._oks_from_heatmaps (loss.py:550-640, with
+ *      compute_oks(use_area=False, per_kpt=True), loss.py:715-764) and _error_from_heatmaps (loss.py:512-548).
+ *      gt/dt keypoints are the (B, K, 2) float64 outputs of pp_decode_argmax_dark on the target / predicted maps. */
+PP_API int pp_pose_targets(const double* gt_keypoints, const double* dt_keypoints,
+                           const float* weight,    /* (B, K) in_image & annotated (loss.py:394) */
+                           const double* sigmas,   /* (K) */
+                           int32_t B, int32_t K, double heatmap_w, double heatmap_h,
+                           float* oks,             /* out (B, K) or NULL */
+                           float* oks_weight,      /* out (B) or NULL */
+                           double* error,          /* out (B, K) Euclidean error or NULL */
+                           pp_stream_t stream);
+
 /* ---- OKSHeatmapLoss.forward (loss.py:55-143) and its backward ---------- */
 typedef enum pp_loss_mode {
   PP_LOSS_PIXEL_MEAN = 0, /* mean over B*K*H*W of the per-pixel loss: what ProbPoseLoss uses (loss.py:428-431) */

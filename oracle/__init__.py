@@ -52,3 +52,4 @@ from .codec_oracle import (  # noqa: F401
     head_tail,
 )
 from .loss_oracle import oks_heatmap_loss, oks_heatmap_loss_grad_closed_form  # noqa: F401
+from .targets_oracle import error_from_heatmaps, oks_from_heatmaps  # noqa: F401

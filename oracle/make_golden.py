@@ -126,6 +126,15 @@ def main() -> None:
                 loss[f"{vname}/{wname}/{mname}/grad"] = o.grad.numpy()
     np.savez_compressed(OUT / "loss.npz", **loss)
 
+    # ---------------- training targets from heatmaps (ProbPoseLoss helpers) ----------------
+    ploss = rl.ProbPoseLoss(rc.Codec(am))
+    wgt = (np.random.default_rng(90).random((3, 17)) < 0.8).astype(np.int64)
+    wgt[2] = 0                                       # a sample without any valid keypoint
+    t_oks, t_w = ploss._oks_from_heatmaps(torch.from_numpy(clean), torch.from_numpy(blob), torch.from_numpy(wgt),
+                                          heatmap_size=wl.heatmap_size)
+    t_err = ploss._error_from_heatmaps(torch.from_numpy(clean), torch.from_numpy(blob))
+    np.savez_compressed(OUT / "targets.npz", weight=wgt, oks=t_oks.numpy(), oks_weights=t_w.numpy(), error=t_err)
+
     # ---------------- known answers held by the reference's own tests ----------------
     codec = rc.ArgMaxProbMap((768, 768), (192, 192), np.array([0.1] * 20))
     enc = codec.encode(np.array([[[96.0, 96.0]]]), np.array([[1.0]]), np.array([[1.0]]))

@@ -12,9 +12,10 @@ fallback -- calls raise when the library or a GPU is missing.
 """
 
 from .codec import ArgMaxProbMap, Codec, ProbMap, generate_probmaps  # noqa: F401
-from .head import heatmap_tail  # noqa: F401
+from .head import HeatmapTail, heatmap_tail, patch_probmap_head  # noqa: F401
 from .heatmap import get_heatmap_expected_value, get_heatmap_maximum  # noqa: F401
 from .loss import OKSHeatmapLoss  # noqa: F401
 
-__all__ = ["ArgMaxProbMap", "Codec", "ProbMap", "generate_probmaps", "heatmap_tail",
+__all__ = ["ArgMaxProbMap", "Codec", "ProbMap", "generate_probmaps", "heatmap_tail", "HeatmapTail",
+           "patch_probmap_head",
            "get_heatmap_expected_value", "get_heatmap_maximum", "OKSHeatmapLoss"]

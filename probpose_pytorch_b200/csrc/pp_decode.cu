@@ -668,6 +668,31 @@ tail_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t numel, float tem
     y[i] = Elem<T>::from_f32(apply_tail<T>(Elem<T>::to_f32(x[i]), true, temperature));
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+tail_backward_kernel(const T* __restrict__ x, const T* __restrict__ gy, T* __restrict__ gx, int64_t numel,
+                     float temperature, bool vector_ok) {
+  constexpr int V = Elem<T>::kVec;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t nvec = vector_ok ? numel / V : 0;
+  auto one = [&](float xv, float g) -> float {
+    // z is rounded to the tensor dtype like the forward; clamp passes the gradient on [0, 1] inclusive
+    const float z = Elem<T>::to_f32(Elem<T>::from_f32(__fdiv_rn(xv, temperature)));
+    return (z >= 0.0f && z <= 1.0f) ? Elem<T>::to_f32(Elem<T>::from_f32(__fdiv_rn(g, temperature))) : 0.0f;
+  };
+  for (int64_t i = tid; i < nvec; i += stride) {
+    float a[V], b[V];
+    unpack(ldg_stream_128(x + i * V), a, T());
+    unpack(ldg_stream_128(gy + i * V), b, T());
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] = one(a[j], b[j]);
+    stg_stream_128(gx + i * V, pack(a, T()));
+  }
+  for (int64_t i = nvec * V + tid; i < numel; i += stride)
+    gx[i] = Elem<T>::from_f32(one(Elem<T>::to_f32(x[i]), Elem<T>::to_f32(gy[i])));
+}
+
 int pick_threads(int H, int W) {
   // one register-tiled task = kTile outputs; aim for whole rounds of tasks per pass
   const int tasks = round_up(W, kTile) / kTile * H;
@@ -856,6 +881,29 @@ int pp_heatmap_tail(const void* x, void* y, int32_t dtype, int64_t numel, float 
     tail_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), numel, temperature, vec);
   else {
     pp_set_error("pp_heatmap_tail: unsupported dtype %d", dtype);
+    return PP_ERR_INVALID_ARG;
+  }
+  PP_CUDA_OK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_heatmap_tail_backward(const void* x, const void* grad_y, void* grad_x, int32_t dtype, int64_t numel,
+                             float temperature, pp_stream_t stream) {
+  PP_REQUIRE(numel >= 0 && temperature != 0.0f, PP_ERR_INVALID_ARG, "pp_heatmap_tail_backward: bad numel/temperature");
+  if (numel == 0) return PP_OK;
+  PP_REQUIRE(x && grad_y && grad_x, PP_ERR_INVALID_ARG, "pp_heatmap_tail_backward: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = pp_aligned16(x) && pp_aligned16(grad_y) && pp_aligned16(grad_x);
+  const int grid = static_cast<int>(std::min<int64_t>((numel + 2047) / 2048, static_cast<int64_t>(pp_sm_count()) * 16));
+  if (dtype == PP_F32)
+    tail_backward_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(grad_y),
+                                                      static_cast<float*>(grad_x), numel, temperature, vec);
+  else if (dtype == PP_BF16)
+    tail_backward_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                              static_cast<const __nv_bfloat16*>(grad_y),
+                                                              static_cast<__nv_bfloat16*>(grad_x), numel, temperature, vec);
+  else {
+    pp_set_error("pp_heatmap_tail_backward: unsupported dtype %d", dtype);
     return PP_ERR_INVALID_ARG;
   }
   PP_CUDA_OK(cudaGetLastError());

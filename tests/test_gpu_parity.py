@@ -560,3 +560,74 @@ def test_codec_decode_tuple(pp):
     assert rec.shape == (B, K, 7) and np.array_equal(rec[..., :2].cpu().numpy(), kp)
     hk, hs = codec.decode_heatmap(torch.from_numpy(maps[0]).cuda())
     assert hk.shape == (1, K, 2) and np.array_equal(hk[0], kp[0])
+
+
+def test_head_tail_autograd_and_patch(pp):
+    """The fused tail against torch.clamp(x / t, 0, 1) incl. autograd (head.py:526-532), and the patch helper
+    on a stand-in module with the reference head's attribute names."""
+    torch.manual_seed(4)
+    x = (torch.randn(3, 5, 16, 12, device="cuda") * 0.4)
+    x[0, 0, 0, :4] = torch.tensor([0.0, 0.5, -0.0, 0.25], device="cuda")   # boundary values: gradient passes at 0 and 1
+    for dtype, tol in ((torch.float32, 0.0), (torch.bfloat16, 0.0)):
+        a = x.to(dtype).clone().requires_grad_(True)
+        b = x.to(dtype).clone().requires_grad_(True)
+        up = torch.rand_like(a)
+        ya = pp.heatmap_tail(a, 0.5)
+        yb = torch.clamp(b / 0.5, 0, 1)
+        assert torch.equal(ya, yb)
+        (ya * up).sum().backward()
+        (yb * up).sum().backward()
+        assert torch.equal(a.grad, b.grad)
+    t3 = torch.clamp(x / 0.3, 0, 1)
+    # torch's CUDA kernel multiplies by the reciprocal of a scalar divisor; the kernel divides (IEEE), 1 ulp apart
+    torch.testing.assert_close(pp.heatmap_tail(x, 0.3), t3, rtol=1e-6, atol=1e-7)
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.deconv_layers = torch.nn.Identity()
+            self.conv_layers = torch.nn.Conv2d(5, 5, 1)
+            self.final_layer = torch.nn.Identity()
+            self.temperature = 0.5
+            self.normalize = None
+
+        def forward_heatmap(self, x):
+            x = self.final_layer(self.conv_layers(self.deconv_layers(x)))
+            B, C, H, W = x.shape
+            x = x.reshape((B, C, H * W)) / self.temperature
+            return torch.clamp(x, 0, 1).reshape((B, C, H, W))
+
+    m = Stub().cuda()
+    want = m.forward_heatmap(x)
+    got = pp.patch_probmap_head(m).forward_heatmap(x)
+    assert torch.equal(got, want)
+    got.sum().backward()
+    assert m.conv_layers.weight.grad is not None
+
+
+def test_pose_targets_from_heatmaps(pp, golden_dir):
+    """Device-side ProbPoseLoss._oks_from_heatmaps / _error_from_heatmaps against the reference's outputs."""
+    from probpose_pytorch_b200.pose_targets import error_from_heatmaps, oks_from_heatmaps
+    g = np.load(golden_dir / "decode.npz")
+    t = np.load(golden_dir / "targets.npz")
+    wl = synth.WORKLOADS[3]
+    codec = pp.Codec(pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas))
+    gt, dt = torch.from_numpy(g["clean"]).cuda(), torch.from_numpy(g["blob"]).cuda()
+    oks, w = oks_from_heatmaps(codec, gt, dt, torch.from_numpy(t["weight"]).cuda(), heatmap_size=wl.heatmap_size)
+    assert oks.dtype == torch.float32 and tuple(oks.shape) == t["oks"].shape
+    assert np.array_equal(w.cpu().numpy(), t["oks_weights"])
+    # OKS of noisy predictions inherits the DARK decoder's conditioning; most keypoints agree to 1e-5
+    got, want = oks.cpu().numpy(), t["oks"]
+    close = np.abs(got - want) <= RTOL32 * np.abs(want) + 1e-7
+    assert close.mean() >= 0.9 and np.abs(got - want).max() <= 2e-2, (close.mean(), np.abs(got - want).max())
+    assert (got[t["weight"] == 0] == 0).all()
+    err = error_from_heatmaps(codec, gt, dt).cpu().numpy()
+    live = g["blob_peaks"][:, :, 0] >= 0
+    ok = np.abs(err - t["error"]) <= RTOL32 * np.maximum(t["error"], 1.0) + 1e-3
+    assert ok[live].mean() >= 0.9
+    # the same through the oracle restatement (numpy blur) on the identical inputs, tighter on clean maps
+    o2, w2 = oc.oks_from_heatmaps(g["clean"], g["clean"], t["weight"], wl.sigmas, wl.input_size, wl.heatmap_size,
+                                  area_size=wl.heatmap_size)
+    o3, w3 = oks_from_heatmaps(codec, gt, gt, torch.from_numpy(t["weight"]).cuda(), heatmap_size=wl.heatmap_size)
+    np.testing.assert_allclose(o3.cpu().numpy(), o2, rtol=RTOL32, atol=1e-6)
+    assert np.array_equal(w3.cpu().numpy(), w2)

@@ -152,3 +152,16 @@ def test_head_tail():
     x = np.random.default_rng(0).normal(0, 0.4, (2, 3, 8, 6)).astype(np.float32)
     want = torch.clamp(torch.from_numpy(x) / 0.5, 0, 1).numpy()
     assert np.array_equal(oc.head_tail(x, 0.5), want)
+
+
+def test_pose_targets(golden_dir):
+    """ProbPoseLoss._oks_from_heatmaps / _error_from_heatmaps (inputs: the decode fixture's maps)."""
+    g = np.load(golden_dir / "decode.npz")
+    t = np.load(golden_dir / "targets.npz")
+    wl = synth.WORKLOADS[3]
+    oks, w = oc.oks_from_heatmaps(g["clean"], g["blob"], t["weight"], wl.sigmas, wl.input_size, wl.heatmap_size,
+                                  area_size=wl.heatmap_size, backend="cv2")
+    assert oks.dtype == np.float32 and np.array_equal(oks, t["oks"]) and np.array_equal(w, t["oks_weights"])
+    assert w[2] == 0 and not oks[2].any()
+    err = oc.error_from_heatmaps(g["clean"], g["blob"], wl.input_size, wl.heatmap_size, backend="cv2")
+    assert np.array_equal(err, t["error"])
