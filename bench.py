@@ -280,15 +280,27 @@ def run_product(args):
             rec, loss, _ = results[j]
         else:
             rec, loss, _ = step_device(sets[j])
-        if world > 1:   # the only exchange on the path: keypoint records + loss partial (one collective)
-            return ppd.exchange_step_results(rec, loss)
+        if world > 1:
+            # the only exchange on the path: keypoint records + loss partial in ONE all-gather, issued
+            # asynchronously so that it overlaps the next step's kernels (bounded number in flight)
+            pending.append(ppd.exchange_step_results(rec, loss, async_op=True))
+            if len(pending) > 4:
+                pending.popleft().wait()
         return rec, loss
+
+    import collections
+    pending = collections.deque()
+
+    def drain():
+        while pending:
+            pending.popleft().wait()
 
     sampler = ClockSampler(local)
     sampler.start()
     sampler.mark = "warm"
     for i in range(max(args.warmup, 3)):
         run_step(i)
+    drain()
     torch.cuda.synchronize()
 
     # ---- timed region: EXACTLY args.steps steps, barrier + synchronize on both sides
@@ -300,6 +312,7 @@ def run_product(args):
     ev0.record()
     for i in range(args.steps):
         run_step(i)
+    drain()          # the main stream waits for the last exchanges: they are inside the timed region
     ev1.record()
     torch.cuda.synchronize()
     sampler.mark = "post"

@@ -72,15 +72,45 @@ def all_gather_keypoints(records: Tensor) -> Tensor:
     return torch.cat([out[r * m: r * m + s] for r, s in enumerate(sizes)])
 
 
-def exchange_step_results(records: Tensor, loss_mean_local: Tensor) -> tuple[Tensor, Tensor]:
+class StepExchange:
+    """Result of :func:`exchange_step_results`: ``records`` (gathered, rank order) and ``loss`` (global
+    mean).  With ``async_op=True`` the collective runs on NCCL's own stream, overlapped with whatever
+    the caller enqueues next; ``wait()`` makes the current stream wait for it before the results are read."""
+
+    def __init__(self, gathered: Tensor, n_local: int, rec_shape, loss_dtype, work=None):
+        self._gathered, self._n, self._shape, self._dtype, self._work = gathered, n_local, rec_shape, loss_dtype, work
+
+    def wait(self) -> "StepExchange":
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self
+
+    @property
+    def records(self) -> Tensor:
+        self.wait()
+        ws = self._gathered.shape[0]
+        return self._gathered[:, :-1].reshape((ws * self._n,) + tuple(self._shape[1:]))
+
+    @property
+    def loss(self) -> Tensor:
+        self.wait()
+        return self._gathered[:, -1].mean().to(self._dtype)
+
+    def __iter__(self):   # (records, loss) = exchange_step_results(...)
+        yield self.records
+        yield self.loss
+
+
+def exchange_step_results(records: Tensor, loss_mean_local: Tensor, async_op: bool = False):
     """One collective per step: every rank contributes its (B_local, K, C) records and its local
-    mean loss (equal B_local on all ranks); returns the gathered records and the global mean loss."""
+    mean loss (equal B_local on all ranks); yields the gathered records and the global mean loss.
+    Returns a :class:`StepExchange` (unpacks like a ``(records, loss)`` tuple)."""
     ws, _ = world()
     if ws == 1:
         return records, loss_mean_local
     flat = torch.cat([records.reshape(-1), loss_mean_local.detach().reshape(1).to(records.dtype)])
     out = flat.new_empty(ws * flat.numel())
-    dist.all_gather_into_tensor(out, flat)
-    out = out.view(ws, flat.numel())
-    rec = out[:, :-1].reshape((ws * records.shape[0],) + tuple(records.shape[1:]))
-    return rec, out[:, -1].mean().to(loss_mean_local.dtype)
+    work = dist.all_gather_into_tensor(out, flat, async_op=async_op)
+    return StepExchange(out.view(ws, flat.numel()), records.shape[0], records.shape, loss_mean_local.dtype,
+                        work if async_op else None)

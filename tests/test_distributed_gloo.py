@@ -38,6 +38,9 @@ def _worker(rank, world, port, B, ragged):
             rec, loss = ppd.exchange_step_results(mine.clone(), per_image_loss[lo:hi].mean())
             assert torch.equal(rec, records)
             assert abs(float(loss) - float(per_image_loss.mean())) < 1e-6
+            ex = ppd.exchange_step_results(mine.clone(), per_image_loss[lo:hi].mean(), async_op=True)   # overlapped form
+            assert torch.equal(ex.wait().records, records)
+            assert abs(float(ex.loss) - float(per_image_loss.mean())) < 1e-6
     finally:
         dist.destroy_process_group()
 
