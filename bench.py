@@ -33,6 +33,11 @@ UNIT = "heatmaps/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
 
+def workload_text(wl):
+    return (wl.name + " -- heatmap path only (target encode + expected-OKS decode + OKS loss fwd/bwd); "
+            "the ViT backbone / head convolutions are not on the path")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -125,9 +130,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 (f64 encode/convolution)", "data": "synthetic",
-        "config": {"workload": wl.name, "heatmap": list(wl.heatmap_size), "keypoints": wl.num_keypoints,
-                   "images_per_step": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_text(wl), "heatmap": list(wl.heatmap_size), "keypoints": wl.num_keypoints,
+                   "images_per_step": sample, "arithmetic": "f32 maps; f64 encode / convolution accumulation (NumPy, SciPy)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} images x {wl.num_keypoints} keypoints per step, {args.steps} steps; "
                                    "oracle port (NumPy encode, scipy.ndimage decode, torch-CPU loss+autograd), "
@@ -456,10 +461,11 @@ def run_product(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (f64 for the encode exponentials and the exact argmax check)" if args.dtype == "fp32" else "bf16 storage, f32 arithmetic",
+            "dtype": "f32" if args.dtype == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": wl.name + " -- heatmap path only (encode + expected-OKS decode + OKS loss fwd/bwd); "
-                                             "the ViT backbone is not on the path",
+            "config": {"workload": workload_text(wl),
+                       "arithmetic": "f32 maps; f64 for the encode exponentials and the exact argmax check"
+                                     if args.dtype == "fp32" else "bf16 maps, f32 arithmetic",
                        "batch_per_gpu": B, "keypoints": K, "heatmap": [W, H], "heatmaps_per_step_per_gpu": n_hm,
                        "l2": f"rotating {args.sets} buffer sets x {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
                        "launch": "CUDA graph replay" if use_graph else "eager",

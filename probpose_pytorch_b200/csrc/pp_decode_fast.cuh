@@ -560,14 +560,14 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       // ---- D: gather the region (+ radius + 1 halo, reflect-extended, tail applied) into the tile
       const int rows = OH + 2 * (r + 1);
       const int c_lo = kFMarg - (r + 1), c_hi = kFMarg + OW + r;   // inclusive
-      int xx0 = 0, xx1 = 0;
-      const int c0 = c_lo + lane, c1 = c0 + 32;
-      if (c0 <= c_hi) xx0 = reflect1(ox0 - kFMarg + c0, W);
-      if (c1 <= c_hi) xx1 = reflect1(ox0 - kFMarg + c1, W);
-      for (int ty = warp; ty < rows; ty += kFWarps) {
-        const int yy = reflect1(oy0 - (r + 1) + ty, H);
-        if (c0 <= c_hi) tile[ty * kFTileStride + c0] = plane_value<T>(plane, yy * W + xx0);
-        if (c1 <= c_hi) tile[ty * kFTileStride + c1] = plane_value<T>(plane, yy * W + xx1);
+      // flattened over (row, column) so that every thread has several independent copies in flight
+      const int ncols = c_hi - c_lo + 1, total = rows * ncols;
+      const unsigned mcols = div_magic(ncols);
+#pragma unroll 4
+      for (int e = tid; e < total; e += kFThreads) {
+        const int ty = fast_div(e, mcols), c = c_lo + (e - ty * ncols);
+        const int yy = reflect1(oy0 - (r + 1) + ty, H), xx = reflect1(ox0 - kFMarg + c, W);
+        tile[ty * kFTileStride + c] = plane_value<T>(plane, yy * W + xx);
       }
     } else if (!constant) {
       // ---- D': full path, column pass from the plane into the padded float32 plane:
@@ -796,28 +796,26 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
     }
 
     PP_MARK(9);   // neighbours
-    // ---- H: outputs
-    if (tid == 0) {
+    // ---- H: outputs.  The x and y halves of the sub-pixel fit (heatmap.py:136-165, float32, the
+    // reference's operation order) are independent: thread 0 does x, thread 32 does y.
+    if (tid == 0 || tid == 32) {
       const int by = fast_div(best, geo.div_W), bx = best - by * W;
-      float fx = static_cast<float>(bx), fy = static_cast<float>(by);
-      if (interior) {   // _get_subpixel_maximums, float32, op order of heatmap.py:136-165
-        const float l = nb[0], rr = nb[1], u = nb[2], dn = nb[3], c = best_val;
-        const float gx = __fdiv_rn(__fsub_rn(rr, l), 2.0f);
-        const float gy = __fdiv_rn(__fsub_rn(dn, u), 2.0f);
-        float hxx = __fsub_rn(__fadd_rn(rr, l), __fmul_rn(2.0f, c));
-        float hyy = __fsub_rn(__fadd_rn(dn, u), __fmul_rn(2.0f, c));
-        if (hxx == 0.0f) hxx = 1e-6f;
-        if (hyy == 0.0f) hyy = 1e-6f;
-        fx = __fadd_rn(fx, __fdiv_rn(-gx, hxx));
-        fy = __fadd_rn(fy, __fdiv_rn(-gy, hyy));
+      const bool is_y = tid == 32;
+      float f = static_cast<float>(is_y ? by : bx);
+      if (interior) {
+        const float lo = is_y ? nb[2] : nb[0], hi = is_y ? nb[3] : nb[1], c = best_val;   // left/up, right/down
+        const float g = __fdiv_rn(__fsub_rn(hi, lo), 2.0f);
+        float h = __fsub_rn(__fadd_rn(hi, lo), __fmul_rn(2.0f, c));
+        if (h == 0.0f) h = 1e-6f;
+        f = __fadd_rn(f, __fdiv_rn(-g, h));
       }
-      locs[hm * 2] = fx;
-      locs[hm * 2 + 1] = fy;
-      vals[hm] = score;
-      if (argmax) argmax[hm] = best;
-      if (keypoints) {
-        keypoints[hm * 2] = static_cast<double>(fx) / static_cast<double>(W - 1) * p.input_w;
-        keypoints[hm * 2 + 1] = static_cast<double>(fy) / static_cast<double>(H - 1) * p.input_h;
+      locs[hm * 2 + (is_y ? 1 : 0)] = f;
+      if (keypoints)   // float32 / int -> float64, then * input_size (codec.py:237)
+        keypoints[hm * 2 + (is_y ? 1 : 0)] =
+            static_cast<double>(f) / static_cast<double>(is_y ? H - 1 : W - 1) * (is_y ? p.input_h : p.input_w);
+      if (is_y) {
+        vals[hm] = score;
+        if (argmax) argmax[hm] = best;
       }
     }
     PP_MARK(10);  // H: outputs
