@@ -99,7 +99,11 @@ typedef struct pp_decode_params {
 } pp_decode_params;
 
 /* get_heatmap_expected_value (heatmap.py:291-395) + ProbMap.decode scaling (codec.py:214-239).
- * conv_out != NULL additionally returns the OKS-convolved maps (return_heatmap=True). */
+ * conv_out != NULL additionally returns the OKS-convolved maps (return_heatmap=True).
+ * scratch: pp_decode_expected_scratch_bytes() bytes of device memory (contents undefined) that hold the
+ * kernel's work-queue counter; NULL is allowed (the heatmaps are then split statically, ~25 % slower on
+ * mixed inputs). */
+PP_API int64_t pp_decode_expected_scratch_bytes(void);
 PP_API int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* table,
                        const void* heatmaps,
                        float* locs,        /* out (N, 2) sub-pixel argmax, heatmap px */
@@ -107,6 +111,7 @@ PP_API int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* tab
                        int32_t* argmax,    /* out (N) flat index y*W+x of the convolved maximum, or NULL */
                        double* keypoints,  /* out (N, 2) input-space coordinates, or NULL */
                        float* conv_out,    /* out (N, H, W) or NULL */
+                       void* scratch, int64_t scratch_bytes,
                        pp_stream_t stream);
 
 /* Number of floats of `conv_out` work space pp_decode_expected needs for this shape even when the

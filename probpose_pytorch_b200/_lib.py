@@ -23,7 +23,7 @@ PP_UPSTREAM_SCALAR, PP_UPSTREAM_FULL = 0, 1
 #: every symbol include/probpose_b200.h declares
 EXPORTS = (
     "pp_version", "pp_last_error_string", "pp_device_info", "pp_encode", "pp_decode_expected",
-    "pp_decode_expected_workspace_floats",
+    "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes",
     "pp_heatmap_maximum", "pp_decode_argmax_dark", "pp_heatmap_tail", "pp_heatmap_tail_backward",
     "pp_oks_loss_scratch_bytes",
     "pp_oks_loss_forward", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
@@ -72,7 +72,9 @@ def lib() -> C.CDLL:
     L.pp_last_error_string.restype = C.c_char_p
     L.pp_device_info.argtypes = [vp, vp, vp, vp]
     L.pp_encode.argtypes = [C.POINTER(EncodeParams), vp, vp, vp, vp, vp, vp, vp, vp]
-    L.pp_decode_expected.argtypes = [C.POINTER(DecodeParams), C.POINTER(OksTable), vp, vp, vp, vp, vp, vp, vp]
+    L.pp_decode_expected.argtypes = [C.POINTER(DecodeParams), C.POINTER(OksTable), vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.pp_decode_expected_scratch_bytes.argtypes = []
+    L.pp_decode_expected_scratch_bytes.restype = i64
     L.pp_decode_expected_workspace_floats.argtypes = [C.POINTER(DecodeParams)]
     L.pp_decode_expected_workspace_floats.restype = i64
     L.pp_heatmap_maximum.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, vp]
@@ -88,7 +90,7 @@ def lib() -> C.CDLL:
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("pp_version", "pp_last_error_string", "pp_oks_loss_scratch_bytes",
-                        "pp_decode_expected_workspace_floats"):
+                        "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes"):
             fn.restype = C.c_int
     if L.pp_version() != 1:
         raise RuntimeError(f"{LIB_PATH}: ABI version {L.pp_version()} != 1; rebuild the extension")

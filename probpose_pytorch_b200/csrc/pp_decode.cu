@@ -707,7 +707,8 @@ int pick_threads(int H, int W) {
 
 template <typename T>
 int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, const void* heatmaps, float* locs,
-                           float* vals, int32_t* argmax, double* keypoints, float* conv_out, cudaStream_t st) {
+                           float* vals, int32_t* argmax, double* keypoints, float* conv_out, void* scratch,
+                           int64_t scratch_bytes, cudaStream_t st) {
   const int64_t N = static_cast<int64_t>(p.B) * p.K;
   const T* hm = static_cast<const T*>(heatmaps);
   const PlaneGeom g = plane_geom(p.H, p.W, 0);
@@ -753,7 +754,9 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
       return rc;
     int64_t fgrid64 = std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper);
     const int fgrid = static_cast<int>(fgrid64);
-    decode_expected_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, geo);
+    unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;
+    if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+    decode_expected_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, geo, counter);
     PP_CUDA_OK(cudaGetLastError());
     return PP_OK;
   }
@@ -813,16 +816,19 @@ extern "C" __attribute__((visibility("default"))) int pp_debug_phase_cycles(unsi
 
 extern "C" {
 
+int64_t pp_decode_expected_scratch_bytes(void) { return 16; }
+
 int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* table, const void* heatmaps, float* locs,
-                       float* vals, int32_t* argmax, double* keypoints, float* conv_out, pp_stream_t stream) {
+                       float* vals, int32_t* argmax, double* keypoints, float* conv_out, void* scratch,
+                       int64_t scratch_bytes, pp_stream_t stream) {
   if (int rc = check_decode_params("pp_decode_expected", p)) return rc;
   if (p->B == 0) return PP_OK;
   PP_REQUIRE(table && table->radius && table->taps_f32 && table->kernel2d && heatmaps && locs && vals,
              PP_ERR_INVALID_ARG, "pp_decode_expected: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->heatmap_dtype == PP_F32)
-    return launch_decode_expected<float>(*p, *table, heatmaps, locs, vals, argmax, keypoints, conv_out, st);
-  return launch_decode_expected<__nv_bfloat16>(*p, *table, heatmaps, locs, vals, argmax, keypoints, conv_out, st);
+    return launch_decode_expected<float>(*p, *table, heatmaps, locs, vals, argmax, keypoints, conv_out, scratch, scratch_bytes, st);
+  return launch_decode_expected<__nv_bfloat16>(*p, *table, heatmaps, locs, vals, argmax, keypoints, conv_out, scratch, scratch_bytes, st);
 }
 
 int64_t pp_decode_expected_workspace_floats(const pp_decode_params* p) {

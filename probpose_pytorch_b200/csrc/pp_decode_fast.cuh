@@ -307,7 +307,7 @@ template <typename T>
 __global__ void __launch_bounds__(kFThreads, 6)
 decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict__ heatmaps,
                             float* __restrict__ locs, float* __restrict__ vals, int32_t* __restrict__ argmax,
-                            double* __restrict__ keypoints, FastGeom geo) {
+                            double* __restrict__ keypoints, FastGeom geo, unsigned* __restrict__ work_counter) {
   extern __shared__ __align__(128) unsigned char fsm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ FastShared sh;
@@ -338,59 +338,41 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   // stale work-area contents only ever meet zero taps or unused outputs, but they must be finite
   for (int i = tid; i < static_cast<int>(geo.work_floats); i += kFThreads) work[i] = 0.0f;
   __syncthreads();
-  // ---- work distribution.  With at least one CTA per keypoint channel, a CTA serves ONE channel k for
-  // its whole life (tables staged once) and the CTAs are shared out between the channels in proportion to
-  // a cost model of their kernel radius (wide kernels take ~1.7x longer per heatmap than narrow ones), so
-  // that all channels finish together.  CTA j of the C_k CTAs of channel k takes images j, j + C_k, ...
-  // Smaller launches fall back to plain striding over the heatmaps.
-  __shared__ int sched[3];   // k, first image, image stride
-  const bool by_channel = static_cast<int>(gridDim.x) >= p.K && p.K <= kFMaxChannels;
-  if (by_channel) {
-    int* wsum = reinterpret_cast<int*>(work);   // scratch: prefix sums of the channel weights
-    for (int kk = tid; kk < p.K; kk += kFThreads) wsum[kk] = 35 + 4 * tab.radius[kk];
-    __syncthreads();
-    if (tid == 0) {
-      long long total = 0;
-      for (int kk = 0; kk < p.K; ++kk) total += wsum[kk];
-      const long long spare = static_cast<long long>(gridDim.x) - p.K;   // beyond one CTA per channel
-      long long acc = 0;
-      int first = 0, found_k = p.K - 1, found_first = 0, found_n = 1;
-      for (int kk = 0; kk < p.K; ++kk) {
-        const long long lo = acc * spare / total;
-        acc += wsum[kk];
-        const long long hi = acc * spare / total;
-        const int n = 1 + static_cast<int>(hi - lo);
-        if (static_cast<int>(blockIdx.x) >= first && static_cast<int>(blockIdx.x) < first + n) {
-          found_k = kk; found_first = first; found_n = n;
-        }
-        first += n;
-      }
-      sched[0] = found_k;
-      sched[1] = static_cast<int>(blockIdx.x) - found_first;
-      sched[2] = found_n;
+  // ---- work distribution.  Heatmaps cost between ~4 ns (constant maps) and ~25 ns (flat maps, wide
+  // kernels) each and a CTA only sees a handful of them, so a static split leaves the slowest CTA ~1.5x
+  // behind the average.  CTAs therefore pull work items one at a time from a global counter.  Items are
+  // numbered channel-major (item j -> channel j / B, image j % B): a CTA changes channel at most a few
+  // times in its life, so the per-channel tables are staged almost once.  Without a counter (no scratch)
+  // the heatmaps are strided statically.
+  __shared__ long long next_item, next_hm;
+  const bool dynamic = work_counter != nullptr;
+  auto item_to_hm = [&](long long j) -> long long {   // thread 0 only (64-bit division)
+    if (!dynamic) return j;
+    const long long kk = j / p.B, b = j - kk * p.B;
+    return b * p.K + kk;
+  };
+  auto pull = [&]() -> long long {   // thread 0 only
+    return dynamic ? static_cast<long long>(atomicAdd(work_counter, 1u)) : -1;
+  };
+  if (tid == 0) {
+    next_item = dynamic ? pull() : static_cast<long long>(blockIdx.x);
+    next_hm = next_item < N ? item_to_hm(next_item) : N;
+    if (next_item < N) {
+      mbar_expect_tx(&bar, geo.plane_bytes);
+      tma_load_1d(fsm, heatmaps + next_hm * HW, geo.plane_bytes, &bar);
     }
-    __syncthreads();
-    for (int kk = tid; kk < p.K; kk += kFThreads) wsum[kk] = 0;   // the work area must hold finite floats
-    __syncthreads();
   }
-  const int my_k = by_channel ? sched[0] : 0;
-  // heatmap index as a function of the iteration
-  const int64_t hm_first = by_channel ? static_cast<int64_t>(sched[1]) * p.K + my_k : blockIdx.x;
-  const int64_t hm_step = by_channel ? static_cast<int64_t>(sched[2]) * p.K : gridDim.x;
-  int64_t hm = hm_first;
-  if (tid == 0 && hm < N) {
-    mbar_expect_tx(&bar, geo.plane_bytes);
-    tma_load_1d(fsm, heatmaps + hm * HW, geo.plane_bytes, &bar);
-  }
+  __syncthreads();
+  long long item = next_item;
+  int64_t hm = next_hm;
 
   int k_loaded = -1, r = 1, d = 3, padr = 4, nch_row = 1, nch_col = 1;
-  const int k_step = by_channel ? 0 : static_cast<int>(gridDim.x % p.K);
-  int k = static_cast<int>(hm % p.K);
 
 #ifdef PP_PHASE_TIMING
   long long mark_ = clock64();
 #endif
-  for (int it = 0; hm < N; hm += hm_step, ++it) {
+  for (int it = 0; item < N; ++it) {
+    const int k = static_cast<int>(hm % p.K);
     if (k != k_loaded) {
       __syncthreads();   // nobody still reads the previous tables
       r = tab.radius[k];
@@ -587,12 +569,18 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
     __syncthreads();
     PP_MARK(5);   // D: gather / column pass
     const bool plane_free = constant || tile_path;   // the full path still needs the plane for step G
-    const int64_t nxt = hm + hm_step;
-    if (plane_free && tid == 0 && nxt < N) {   // the next heatmap streams in while this one is finished
-      fence_proxy_async();
-      mbar_expect_tx(&bar, geo.plane_bytes);
-      tma_load_1d(fsm, heatmaps + nxt * HW, geo.plane_bytes, &bar);
-    }
+    auto fetch_next = [&]() {   // thread 0: claim the next work item and start its copy
+      const long long j = dynamic ? pull() : item + static_cast<long long>(gridDim.x);
+      const long long h = j < N ? item_to_hm(j) : N;
+      next_item = j;
+      next_hm = h;
+      if (j < N) {
+        fence_proxy_async();
+        mbar_expect_tx(&bar, geo.plane_bytes);
+        tma_load_1d(fsm, heatmaps + h * HW, geo.plane_bytes, &bar);
+      }
+    };
+    if (plane_free && tid == 0) fetch_next();   // the next heatmap streams in while this one is finished
 
     if (!constant) {
       // ---- E/F: separable float32 prefilter
@@ -821,12 +809,11 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
     PP_MARK(10);  // H: outputs
     __syncthreads();   // work area / scratch / plane are reused by the next heatmap
     PP_MARK(11);  // final barrier
-    if (!plane_free && tid == 0 && nxt < N) {
-      fence_proxy_async();
-      mbar_expect_tx(&bar, geo.plane_bytes);
-      tma_load_1d(fsm, heatmaps + nxt * HW, geo.plane_bytes, &bar);
+    if (!plane_free) {
+      if (tid == 0) fetch_next();
+      __syncthreads();   // publish next_item
     }
-    k += k_step;
-    if (k >= p.K) k -= p.K;
+    item = next_item;
+    hm = next_hm;
   }
 }

@@ -125,9 +125,11 @@ def expected_value_device(heatmaps: torch.Tensor, sigmas, *, input_size=None, re
         if return_heatmap:
             out["conv"] = conv
     t = _lib.OksTable(tab.radius.data_ptr(), tab.taps.data_ptr(), tab.kernel2d.data_ptr())
+    scratch = torch.empty(4, dtype=torch.int32, device=dev)   # work-queue counter of the kernel
     with torch.cuda.device(dev):
         rc = _lib.lib().pp_decode_expected(p, t, _lib.ptr(hm), _lib.ptr(out["locs"]), _lib.ptr(out["vals"]),
-                                           _lib.ptr(out["argmax"]), _lib.ptr(kp), _lib.ptr(conv), _lib.stream_ptr(dev))
+                                           _lib.ptr(out["argmax"]), _lib.ptr(kp), _lib.ptr(conv), _lib.ptr(scratch),
+                                           scratch.numel() * 4, _lib.stream_ptr(dev))
     _lib.check(rc, "pp_decode_expected")
     return out
 

@@ -48,7 +48,7 @@ def test_invalid_arguments_return_status_not_crash(lib):
     lib.pp_last_error_string.restype = ctypes.c_char_p
     assert lib.pp_encode(None, None, None, None, None, None, None, None, None) == -1
     assert b"pp_encode" in lib.pp_last_error_string()
-    assert lib.pp_decode_expected(None, None, None, None, None, None, None, None, None) == -1
+    assert lib.pp_decode_expected(None, None, None, None, None, None, None, None, None, ctypes.c_int64(0), None) == -1
     assert lib.pp_heatmap_tail(None, None, 0, ctypes.c_int64(4), ctypes.c_float(0.5), None) == -1
 
 
