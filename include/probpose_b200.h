@@ -88,6 +88,8 @@ typedef struct pp_oks_table {
   const float* taps_f32;    /* (K, PP_OKS_TAPS) normalised 1-D taps, tap j at column j (j < 2r+1) */
   const double* kernel2d;   /* (K, PP_OKS_TAPS*PP_OKS_TAPS) the reference's normalised d x d kernel,
                                packed row-major with row stride d = 2r+1 */
+  const int32_t* order;     /* (K) channels sorted by decreasing radius (longest jobs first in the kernel's
+                               work queue), or NULL for 0..K-1 */
 } pp_oks_table;
 
 typedef struct pp_decode_params {

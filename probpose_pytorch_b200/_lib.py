@@ -37,7 +37,7 @@ class EncodeParams(C.Structure):
 
 
 class OksTable(C.Structure):
-    _fields_ = [("radius", C.c_void_p), ("taps_f32", C.c_void_p), ("kernel2d", C.c_void_p)]
+    _fields_ = [("radius", C.c_void_p), ("taps_f32", C.c_void_p), ("kernel2d", C.c_void_p), ("order", C.c_void_p)]
 
 
 class DecodeParams(C.Structure):
@@ -63,9 +63,13 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not LIB_PATH.exists():
-        raise RuntimeError(
-            f"{LIB_PATH} is missing: the CUDA extension has not been built "
-            "(run `python -m probpose_pytorch_b200.build`).  There is no CPU fallback.")
+        try:  # a fresh checkout on a box with nvcc: build once, in-tree
+            from .build import build
+            build()
+        except Exception as e:
+            raise RuntimeError(
+                f"{LIB_PATH} is missing and could not be built ({e}): run `python -m probpose_pytorch_b200.build`.  "
+                "There is no CPU fallback.") from e
     L = C.CDLL(str(LIB_PATH))
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     L.pp_version.restype = C.c_int

@@ -61,6 +61,8 @@ class OksKernelTable:
         self.taps = torch.from_numpy(taps).to(device)
         self.kernel2d = torch.from_numpy(k2d).to(device)
         self.max_radius = int(radius.max())
+        # work-queue order of the decoder: widest kernels (most expensive heatmaps) first
+        self.order = torch.from_numpy(np.argsort(-radius, kind="stable").astype(np.int32)).to(device)
 
 
 def gaussian_taps(ksize: int) -> np.ndarray:

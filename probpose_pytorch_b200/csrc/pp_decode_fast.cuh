@@ -348,7 +348,8 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   const bool dynamic = work_counter != nullptr;
   auto item_to_hm = [&](long long j) -> long long {   // thread 0 only (64-bit division)
     if (!dynamic) return j;
-    const long long kk = j / p.B, b = j - kk * p.B;
+    const long long slot = j / p.B, b = j - slot * p.B;
+    const long long kk = tab.order ? tab.order[slot] : slot;   // widest kernels first
     return b * p.K + kk;
   };
   auto pull = [&]() -> long long {   // thread 0 only

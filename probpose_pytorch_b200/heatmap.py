@@ -124,7 +124,7 @@ def expected_value_device(heatmaps: torch.Tensor, sigmas, *, input_size=None, re
         conv = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
         if return_heatmap:
             out["conv"] = conv
-    t = _lib.OksTable(tab.radius.data_ptr(), tab.taps.data_ptr(), tab.kernel2d.data_ptr())
+    t = _lib.OksTable(tab.radius.data_ptr(), tab.taps.data_ptr(), tab.kernel2d.data_ptr(), tab.order.data_ptr())
     scratch = torch.empty(4, dtype=torch.int32, device=dev)   # work-queue counter of the kernel
     with torch.cuda.device(dev):
         rc = _lib.lib().pp_decode_expected(p, t, _lib.ptr(hm), _lib.ptr(out["locs"]), _lib.ptr(out["vals"]),

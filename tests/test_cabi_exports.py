@@ -57,7 +57,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.EncodeParams) == 44
     assert ctypes.sizeof(_lib.DecodeParams) == 48
     assert ctypes.sizeof(_lib.LossParams) == 72
-    assert ctypes.sizeof(_lib.OksTable) == 24
+    assert ctypes.sizeof(_lib.OksTable) == 32
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
