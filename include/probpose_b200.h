@@ -136,6 +136,7 @@ PP_API int pp_decode_argmax_dark(const pp_decode_params* p,
                           float* scores,      /* out (N) raw maxima */
                           float* refined,     /* out (N, 2) refined heatmap-space coordinates */
                           double* keypoints,  /* out (N, 2) input-space coordinates, or NULL */
+                          void* scratch, int64_t scratch_bytes, /* as for pp_decode_expected (may be NULL) */
                           pp_stream_t stream);
 
 /* head tail (head.py:526-532, normalize=None): y = clamp(x / temperature, 0, 1) */

@@ -82,7 +82,7 @@ def lib() -> C.CDLL:
     L.pp_decode_expected_workspace_floats.argtypes = [C.POINTER(DecodeParams)]
     L.pp_decode_expected_workspace_floats.restype = i64
     L.pp_heatmap_maximum.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, vp]
-    L.pp_decode_argmax_dark.argtypes = [C.POINTER(DecodeParams), vp, i32, vp, vp, vp, vp, vp, vp]
+    L.pp_decode_argmax_dark.argtypes = [C.POINTER(DecodeParams), vp, i32, vp, vp, vp, vp, vp, vp, i64, vp]
     L.pp_heatmap_tail.argtypes = [vp, vp, i32, i64, f32, vp]
     L.pp_heatmap_tail_backward.argtypes = [vp, vp, vp, i32, i64, f32, vp]
     L.pp_oks_loss_scratch_bytes.argtypes = [C.POINTER(LossParams)]

@@ -273,11 +273,12 @@ class ArgMaxProbMap(_ProbMapBase):
         p = _lib.DecodeParams(B, K, H, W, _lib.dtype_code(hm.dtype), int(temperature is not None),
                               float(temperature or 1.0), float(self.input_size[0]), float(self.input_size[1]))
         taps = self._blur_taps(dev)
+        scratch = torch.empty(4, dtype=torch.int32, device=dev)   # work-queue counter of the kernel
         with torch.cuda.device(dev):
             rc = _lib.lib().pp_decode_argmax_dark(p, _lib.ptr(taps), int(self.blur_kernel_size), _lib.ptr(hm),
                                                   _lib.ptr(out["peaks"]), _lib.ptr(out["scores"]),
                                                   _lib.ptr(out["locs"]), _lib.ptr(out["keypoints"]),
-                                                  _lib.stream_ptr(dev))
+                                                  _lib.ptr(scratch), scratch.numel() * 4, _lib.stream_ptr(dev))
         _lib.check(rc, "pp_decode_argmax_dark")
         return out
 

@@ -555,6 +555,8 @@ __device__ __forceinline__ void pinv_sym2(double a, double b, double c, double& 
   ic = i1 * vy * vy + i2 * vx * vx;
 }
 
+#include "pp_dark_fast.cuh"
+
 template <typename T>
 __global__ void __launch_bounds__(512)
 decode_dark_kernel(pp_decode_params p, const float* __restrict__ blur_taps, int ksize, const T* __restrict__ heatmaps,
@@ -705,6 +707,31 @@ int pick_threads(int H, int W) {
   return best;
 }
 
+// Shared-memory layout of the persistent decoder kernels; false when the shape / alignment rules them out.
+template <typename T>
+bool fast_geometry(const pp_decode_params& p, const void* heatmaps, int max_radius, FastGeom* out, size_t* smem_bytes) {
+  FastGeom geo{};
+  geo.plane_bytes = static_cast<unsigned>(sizeof(T) * static_cast<size_t>(p.H) * p.W);
+  geo.W8 = round_up(p.W, kTile);
+  geo.full_stride = conflict_free_stride(kFMarg + geo.W8 + kFMarg);
+  geo.work_off = (geo.plane_bytes + 127) / 128 * 128;
+  // + 32 floats of slack: the last window of the last row reads a little past its row (zero taps only)
+  geo.work_floats = static_cast<unsigned>(
+      round_up(static_cast<int>(std::max<size_t>(kFTileFloats, static_cast<size_t>(p.H) * geo.full_stride)) + 32, 4));
+  geo.taskmax_off = geo.work_off + static_cast<unsigned>(sizeof(float)) * geo.work_floats;
+  geo.w2d_off = geo.taskmax_off + static_cast<unsigned>(sizeof(float) * round_up((geo.W8 / kTile) * p.H, 4));
+  const size_t fsmem = geo.w2d_off + sizeof(double) * PP_OKS_TAPS * PP_OKS_TAPS;
+  const bool ok = geo.plane_bytes % 16 == 0 && pp_aligned16(heatmaps) && p.W % Elem<T>::kVec == 0 &&
+                  (!p.apply_tail || p.temperature > 0.0f) && fsmem + 4096 <= static_cast<size_t>(pp_smem_optin()) &&
+                  p.W > max_radius + 1 && p.H > max_radius + 1 && static_cast<int64_t>(p.H) * p.W < (1 << 20);
+  geo.div_WV = div_magic(static_cast<unsigned>(std::max(1, p.W / Elem<T>::kVec)));
+  geo.div_W = div_magic(static_cast<unsigned>(p.W));
+  geo.div_H = div_magic(static_cast<unsigned>(p.H));
+  *out = geo;
+  *smem_bytes = fsmem;
+  return ok;
+}
+
 template <typename T>
 int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, const void* heatmaps, float* locs,
                            float* vals, int32_t* argmax, double* keypoints, float* conv_out, void* scratch,
@@ -732,23 +759,9 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
 
   // main kernel: TMA-staged plane, convolution pruned to the neighbourhood of {h >= L} when possible
   FastGeom geo{};
-  geo.plane_bytes = static_cast<unsigned>(sizeof(T) * static_cast<size_t>(p.H) * p.W);
-  geo.W8 = round_up(p.W, kTile);
-  geo.full_stride = conflict_free_stride(kFMarg + geo.W8 + kFMarg);
-  geo.work_off = (geo.plane_bytes + 127) / 128 * 128;
-  // + 32 floats of slack: the last window of the last row reads a little past its row (zero taps only)
-  geo.work_floats = static_cast<unsigned>(
-      round_up(static_cast<int>(std::max<size_t>(kFTileFloats, static_cast<size_t>(p.H) * geo.full_stride)) + 32, 4));
-  geo.taskmax_off = geo.work_off + static_cast<unsigned>(sizeof(float)) * geo.work_floats;
-  geo.w2d_off = geo.taskmax_off + static_cast<unsigned>(sizeof(float) * round_up((geo.W8 / kTile) * p.H, 4));
-  const size_t fsmem = geo.w2d_off + sizeof(double) * PP_OKS_TAPS * PP_OKS_TAPS;
-  const bool fast = geo.plane_bytes % 16 == 0 && pp_aligned16(heatmaps) && p.W % Elem<T>::kVec == 0 &&
-                    (!p.apply_tail || p.temperature > 0.0f) && fsmem <= static_cast<size_t>(pp_smem_optin()) &&
-                    p.W > PP_MAX_OKS_RADIUS + 1 && p.H > PP_MAX_OKS_RADIUS + 1 && static_cast<int64_t>(p.H) * p.W < (1 << 20);
+  size_t fsmem = 0;
+  const bool fast = fast_geometry<T>(p, heatmaps, PP_MAX_OKS_RADIUS, &geo, &fsmem);
   if (fast) {
-    geo.div_WV = div_magic(static_cast<unsigned>(p.W / Elem<T>::kVec));
-    geo.div_W = div_magic(static_cast<unsigned>(p.W));
-    geo.div_H = div_magic(static_cast<unsigned>(p.H));
     int fper = 1;
     if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_fast_kernel<T>), kFThreads, fsmem, &fper))
       return rc;
@@ -770,9 +783,26 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
 
 template <typename T>
 int launch_decode_dark(const pp_decode_params& p, const float* taps, int ksize, const void* heatmaps, float* peaks,
-                       float* scores, float* refined, double* keypoints, cudaStream_t st) {
+                       float* scores, float* refined, double* keypoints, void* scratch, int64_t scratch_bytes,
+                       cudaStream_t st) {
   const int64_t N = static_cast<int64_t>(p.B) * p.K;
   const int r = ksize / 2;
+  {
+    FastGeom geo{};
+    size_t fsmem = 0;
+    if (r <= PP_MAX_OKS_RADIUS && fast_geometry<T>(p, heatmaps, r, &geo, &fsmem)) {
+      int fper = 1;
+      if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_dark_fast_kernel<T>), kFThreads, fsmem, &fper))
+        return rc;
+      const int fgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper));
+      unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;
+      if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+      decode_dark_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, taps, ksize, static_cast<const T*>(heatmaps), peaks,
+                                                                scores, refined, keypoints, geo, counter);
+      PP_CUDA_OK(cudaGetLastError());
+      return PP_OK;
+    }
+  }
   const PlaneGeom g = plane_geom(p.H, p.W, r == 5 ? 2 * r + kTile : 0);
   const size_t smem = sizeof(float) * (static_cast<size_t>(g.raw_floats) + g.tmp_floats + g.out_floats);
   PP_REQUIRE(smem <= static_cast<size_t>(pp_smem_optin()), PP_ERR_UNSUPPORTED_SHAPE,
@@ -862,7 +892,8 @@ int pp_heatmap_maximum(const void* heatmaps, int32_t heatmap_dtype, int64_t N, i
 }
 
 int pp_decode_argmax_dark(const pp_decode_params* p, const float* blur_taps, int32_t blur_ksize, const void* heatmaps,
-                          float* peaks, float* scores, float* refined, double* keypoints, pp_stream_t stream) {
+                          float* peaks, float* scores, float* refined, double* keypoints, void* scratch,
+                          int64_t scratch_bytes, pp_stream_t stream) {
   if (int rc = check_decode_params("pp_decode_argmax_dark", p)) return rc;
   PP_REQUIRE(blur_ksize % 2 == 1 && blur_ksize >= 3 && blur_ksize <= PP_MAX_BLUR_KSIZE, PP_ERR_INVALID_ARG,
              "pp_decode_argmax_dark: blur kernel size %d must be odd and in [3, %d]", blur_ksize, PP_MAX_BLUR_KSIZE);
@@ -870,8 +901,8 @@ int pp_decode_argmax_dark(const pp_decode_params* p, const float* blur_taps, int
   PP_REQUIRE(blur_taps && heatmaps && scores && refined, PP_ERR_INVALID_ARG, "pp_decode_argmax_dark: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->heatmap_dtype == PP_F32)
-    return launch_decode_dark<float>(*p, blur_taps, blur_ksize, heatmaps, peaks, scores, refined, keypoints, st);
-  return launch_decode_dark<__nv_bfloat16>(*p, blur_taps, blur_ksize, heatmaps, peaks, scores, refined, keypoints, st);
+    return launch_decode_dark<float>(*p, blur_taps, blur_ksize, heatmaps, peaks, scores, refined, keypoints, scratch, scratch_bytes, st);
+  return launch_decode_dark<__nv_bfloat16>(*p, blur_taps, blur_ksize, heatmaps, peaks, scores, refined, keypoints, scratch, scratch_bytes, st);
 }
 
 int pp_heatmap_tail(const void* x, void* y, int32_t dtype, int64_t numel, float temperature, pp_stream_t stream) {

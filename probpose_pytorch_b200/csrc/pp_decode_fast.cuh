@@ -173,7 +173,7 @@ __device__ __forceinline__ void load2<__nv_bfloat16>(const __nv_bfloat16* p, flo
 // Full-path column pass for two adjacent columns (x even) and 4 rows, taps in chunks of 4:
 //   full[y][kFMarg + x] = sum_j tap[j] h[reflect(y - r + j)][x];
 // columns within r of an edge are mirrored into the pad by the thread that produces them.
-template <typename T, bool kInside>
+template <typename T, bool kInside, bool kZeroPad = false>
 __device__ __forceinline__ void full_col_task(const T* __restrict__ plane, float* __restrict__ work,
                                               const float* __restrict__ g, int nch4, int x, int y0, int r, int H, int W,
                                               int FS) {
@@ -182,8 +182,15 @@ __device__ __forceinline__ void full_col_task(const T* __restrict__ plane, float
   const T* base = plane + x + (kInside ? (y0 - r) * W : 0);
   auto fetch = [&](int j, float& u, float& v) {
     if (j < need) {
-      if (kInside) load2<T>(base + j * W, u, v);
-      else load2<T>(base + reflect1(y0 - r + j, H) * W, u, v);
+      if (kInside) {
+        load2<T>(base + j * W, u, v);
+      } else if (kZeroPad) {   // zero padding (the DARK blur): rows outside the map contribute nothing
+        const int yy = y0 - r + j;
+        if (yy >= 0 && yy < H) load2<T>(base + yy * W, u, v);
+        else { u = 0.0f; v = 0.0f; }
+      } else {
+        load2<T>(base + reflect1(y0 - r + j, H) * W, u, v);
+      }
     } else {
       u = 0.0f; v = 0.0f;
     }
@@ -208,7 +215,8 @@ __device__ __forceinline__ void full_col_task(const T* __restrict__ plane, float
 #pragma unroll
     for (int o = 0; o < 4; ++o) { w0[o] = w0[o + 4]; w1[o] = w1[o + 4]; }
   }
-  const bool left = x < r, left1 = x + 1 < r, right = x >= W - r, right1 = x + 1 >= W - r;
+  const bool left = !kZeroPad && x < r, left1 = !kZeroPad && x + 1 < r;
+  const bool right = !kZeroPad && x >= W - r, right1 = !kZeroPad && x + 1 >= W - r;
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     if (y0 + o < H) {

@@ -301,11 +301,16 @@ def test_dark_decoder_matches_golden_reference(pp, golden_dir, name):
     n_strict = n_total = 0
     for b in range(arr.shape[0]):
         live = g[f"{name}_peaks"][b, :, 0] >= 0
+        # DARK is only meaningful (and only reproducible: cv2 vs any other float32 blur differ by 1e-2 px there)
+        # on blob-shaped maps; channels that hold nothing but the U(0, 0.02) noise floor are checked for
+        # argmax / score parity above and for finiteness here ("parity inputs must be blob-shaped")
+        blobby = live & (arr[b].reshape(arr.shape[1], -1).max(axis=1) >= 0.1)
+        assert np.isfinite(got[b][live]).all()
         tol = _dark_tolerance(arr[b], g[f"{name}_peaks"][b], wl, RTOL32)
         err = np.abs(got[b] - want[b])
         bound = RTOL32 * np.maximum(np.abs(want[b]), 1.0) + tol
-        assert (err[live] <= bound[live]).all(), (b, np.max(err[live] / bound[live]))
-        strict = err[live] <= RTOL32 * np.maximum(np.abs(want[b][live]), 1.0)
+        assert (err[blobby] <= bound[blobby]).all(), (b, np.max(err[blobby] / bound[blobby]))
+        strict = err[blobby] <= RTOL32 * np.maximum(np.abs(want[b][blobby]), 1.0)
         n_strict += strict.sum(); n_total += strict.size
         # empty channels keep the sentinel (documented deviation from the reference's out-of-range reads)
         assert (dev["locs"][b].cpu().numpy()[~live] == -1).all()
@@ -435,11 +440,11 @@ def test_loss_closed_form_gradient_c4_shape(pp):
     want = oc.oks_heatmap_loss_grad_closed_form(pred, tgt, w[:, :, None, None], **kw)
     _close(o.grad.cpu().numpy(), want, RTOL32)
     l_ref = oc.oks_heatmap_loss(torch.from_numpy(pred), torch.from_numpy(tgt), torch.from_numpy(w), per_pixel=True, **kw).mean()
-    assert abs(float(l) - float(l_ref)) <= RTOL32 * abs(float(l_ref))
+    assert abs(l.item() - l_ref.item()) <= RTOL32 * abs(l_ref.item())
     o2 = torch.from_numpy(pred).cuda().requires_grad_(True)
     l2 = mod.forward_mean(o2, torch.from_numpy(tgt).cuda(), torch.from_numpy(w).cuda())
     (l2 * 0.25).backward()
-    assert float(l2) == float(l)                                         # deterministic reduction
+    assert l2.item() == l.item()                                         # deterministic reduction
     _close(o2.grad.cpu().numpy() * 4.0, o.grad.cpu().numpy(), 1e-6)      # linear in the upstream gradient
 
 

@@ -49,8 +49,9 @@ def main():
     for name, t in (("clean blobs", clean), ("blobs + U(0,.02) noise", blob_noise), ("noise only U(0,.02)", noise),
                     ("uniform U(0,1)", uniform), ("all zero", zeros)):
         us, _ = timed(lambda: pm.decode_device(t))
-        print(f"{name:26s} {us:8.1f} us  {us * 1e3 / n:7.1f} ns/heatmap  {n / us:8.1f} M heatmaps/s  "
-              f"{n * t[0, 0].numel() * t.element_size() / us / 1e3:7.1f} GB/s")
+        ud, _ = timed(lambda: am.decode_device(t))
+        print(f"{name:26s} expected {us:8.1f} us {us * 1e3 / n:6.1f} ns/hm {n * t[0, 0].numel() * t.element_size() / us / 1e3:7.1f} GB/s"
+              f" | dark {ud:8.1f} us {ud * 1e3 / n:6.1f} ns/hm {n * t[0, 0].numel() * t.element_size() / ud / 1e3:7.1f} GB/s")
     for k in (0, 5, 9, 11):
         sub = noise[:, k:k + 1].expand(-1, wl.num_keypoints, -1, -1).contiguous()
         # decode every channel with channel k's kernel by repeating sigma k
