@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--sample", type=int, default=0, help="reference arm: images per step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--serial", action="store_true", help="run decode after encode on one stream (no fork/join)")
     return ap.parse_args()
 
 
@@ -254,13 +255,24 @@ def run_product(args):
     set_bytes = 3 * n_hm * hm_bytes
     torch.cuda.synchronize()
 
+    side = torch.cuda.Stream(device=dev)
+
     def step_device(s):
-        """The hot path on device-resident inputs."""
+        """The hot path on device-resident inputs.  The decode only depends on the prediction, so it runs on
+        a second stream next to encode -> loss (fork / join; inside the captured graph these are two branches)."""
+        cur = torch.cuda.current_stream(dev)
+        if not args.serial:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                rec = codec.decode_device((s["pred"], *s["heads"]))
         enc = am.encode_batch(s["kps"], s["vis"], dtype=tdtype)
-        rec = codec.decode_device((s["pred"], *s["heads"]))
+        if args.serial:
+            rec = codec.decode_device((s["pred"], *s["heads"]))
         out = s["pred"].detach().requires_grad_(True)
         loss = loss_fn.forward_mean(out, enc["heatmaps"], enc["keypoint_weights"])
         loss.backward()
+        if not args.serial:
+            cur.wait_stream(side)
         return rec, loss.detach(), out.grad
 
     # ---- CUDA graphs of the step, one per buffer set
@@ -468,7 +480,8 @@ def run_product(args):
                                      if args.dtype == "fp32" else "bf16 maps, f32 arithmetic",
                        "batch_per_gpu": B, "keypoints": K, "heatmap": [W, H], "heatmaps_per_step_per_gpu": n_hm,
                        "l2": f"rotating {args.sets} buffer sets x {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
-                       "launch": "CUDA graph replay" if use_graph else "eager",
+                       "launch": ("CUDA graph replay" if use_graph else "eager")
+                                 + (", one stream" if args.serial else ", decode on a second stream beside encode->loss"),
                        "parallelism": f"dp{world} (batch sharded by image)"},
             "roofline": roofline, "kernels": kernels, "e2e": e2e, "cpu_baseline": cpu_baseline,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
