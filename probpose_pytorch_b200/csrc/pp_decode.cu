@@ -719,7 +719,9 @@ bool fast_geometry(const pp_decode_params& p, const void* heatmaps, int max_radi
   geo.work_floats = static_cast<unsigned>(
       round_up(static_cast<int>(std::max<size_t>(kFTileFloats, static_cast<size_t>(p.H) * geo.full_stride)) + 32, 4));
   geo.taskmax_off = geo.work_off + static_cast<unsigned>(sizeof(float)) * geo.work_floats;
-  geo.w2d_off = geo.taskmax_off + static_cast<unsigned>(sizeof(float) * round_up((geo.W8 / kTile) * p.H, 4));
+  // per-task maxima of the full path; the same bytes later hold kFThreads doubles of partial sums
+  geo.w2d_off = geo.taskmax_off + static_cast<unsigned>(std::max<size_t>(sizeof(float) * round_up((geo.W8 / kTile) * p.H, 4),
+                                                                         sizeof(double) * kFThreads));
   const size_t fsmem = geo.w2d_off + sizeof(double) * PP_OKS_TAPS * PP_OKS_TAPS;
   const bool ok = geo.plane_bytes % 16 == 0 && pp_aligned16(heatmaps) && p.W % Elem<T>::kVec == 0 &&
                   (!p.apply_tail || p.temperature > 0.0f) && fsmem + 4096 <= static_cast<size_t>(pp_smem_optin()) &&

@@ -319,7 +319,6 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   extern __shared__ __align__(128) unsigned char fsm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ FastShared sh;
-  __shared__ double ev_part[kFThreads];
 
   const T* plane = reinterpret_cast<const T*>(fsm);
   T* plane_rw = reinterpret_cast<T*>(fsm);
@@ -328,6 +327,8 @@ decode_expected_fast_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   float* tmp = work + kFTileRows * kFTileStride;
   float* task_max = reinterpret_cast<float*>(fsm + geo.taskmax_off);
   double* w2d = reinterpret_cast<double*>(fsm + geo.w2d_off);
+  // partial sums of the grouped exact evaluation: the per-task maxima are dead by then, reuse their space
+  double* ev_part = reinterpret_cast<double*>(fsm + geo.taskmax_off);
 
   constexpr int V = Elem<T>::kVec;
   const int H = p.H, W = p.W, HW = H * W, WV = W / V, FS = geo.full_stride;
