@@ -277,13 +277,13 @@ bool fast_path_ok(const pp_loss_params& p, const void* output, const void* targe
   return p.mode == PP_LOSS_PIXEL_MEAN && !pixel_weights && !mask && !p.skip_empty_channel && p.W % 4 == 0 &&
          p.W / 4 <= 128 && (static_cast<int64_t>(p.H) * p.W * e) % 16 == 0 && pp_aligned16(output) &&
          pp_aligned16(target) && pp_aligned16(grad) &&
-         2 * static_cast<int64_t>(p.H) * p.W * e + 512 <= pp_smem_optin();
+         static_cast<int64_t>(p.H) * p.W * e + 512 <= pp_smem_optin();
 }
 
-template <typename T, bool kFwd, bool kGrad>
-int launch_fast_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
+template <typename T, bool kFwd, bool kGrad, bool kTgtSmem>
+int launch_fast_tt(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
   int per_sm = 1;
-  auto kern = pp_loss_fast::oks_loss_fast_kernel<T, kFwd, kGrad>;
+  auto kern = pp_loss_fast::oks_loss_fast_kernel<T, kFwd, kGrad, kTgtSmem>;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), threads, smem, &per_sm)) return rc;
   const int64_t units = (a.N + a.G - 1) / a.G;
   const int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(pp_sm_count()) * per_sm));
@@ -291,6 +291,12 @@ int launch_fast_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cud
   PP_CUDA_OK(cudaGetLastError());
   *grid_out = grid;
   return PP_OK;
+}
+
+template <typename T, bool kFwd, bool kGrad>
+int launch_fast_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
+  if (a.tgt_off != 0) return launch_fast_tt<T, kFwd, kGrad, true>(a, threads, smem, st, grid_out);
+  return launch_fast_tt<T, kFwd, kGrad, false>(a, threads, smem, st, grid_out);
 }
 
 // Runs the fused mean-mode kernel; *grid_out = number of per-CTA partial sums written (forward).
@@ -329,6 +335,11 @@ int launch_fast(const pp_loss_params& p, const void* output, const void* target,
     a.tgt_off = (16 + a.G * a.plane_bytes + 16 + 127) / 128 * 128;
     a.stage_bytes = (a.tgt_off + a.G * a.plane_bytes + 127) / 128 * 128;
     if (a.stage_bytes <= static_cast<size_t>(pp_smem_optin()) || a.G == 1) break;
+  }
+  if (a.stage_bytes > static_cast<size_t>(pp_smem_optin())) {
+    // very large maps: only the output plane is staged, the target is read from global memory (tgt_off = 0)
+    a.tgt_off = 0;
+    a.stage_bytes = (16 + a.plane_bytes + 16 + 127) / 128 * 128;
   }
   // two stages (the next unit lands while the current one is processed) whenever they fit
   a.stages = env_int("PP_LOSS_STAGES", 2);

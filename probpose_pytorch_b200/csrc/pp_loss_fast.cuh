@@ -108,7 +108,24 @@ struct Sums {
 };
 
 // One row step of the pipeline; PH = step index mod 3 selects the rotating register slots.
-template <typename T, bool kFwd, bool kGrad, int PH>
+template <typename T>
+__device__ __forceinline__ void load_strip4_global(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load_strip4_global<float>(const float* p, float (&v)[4]) {
+  const uint4 w = ldg_stream_128(p);
+  v[0] = __uint_as_float(w.x); v[1] = __uint_as_float(w.y); v[2] = __uint_as_float(w.z); v[3] = __uint_as_float(w.w);
+}
+template <>
+__device__ __forceinline__ void load_strip4_global<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+  uint2 w;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p));
+  v[0] = __uint_as_float(w.x << 16); v[1] = __uint_as_float(w.x & 0xffff0000u);
+  v[2] = __uint_as_float(w.y << 16); v[3] = __uint_as_float(w.y & 0xffff0000u);
+}
+
+// kTgtSmem: the target plane was staged in shared memory with the output plane (the normal case); otherwise
+// (maps so large that only one plane fits) it is read from global memory where it is consumed.
+template <typename T, bool kFwd, bool kGrad, bool kTgtSmem, int PH>
 __device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& cf, int q, int y0, int y1, int H, int W,
                                          int x0, bool left_ok, bool right_ok, const T* __restrict__ plane,
                                          const T* __restrict__ tgt, T* __restrict__ grad) {
@@ -162,7 +179,8 @@ __device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& c
   if (ro >= y0 && ro < y1) {
     float g[4], ov[4], tv[4];
     load_strip4<T>(plane + ro * W + x0, ov);
-    load_strip4<T>(tgt + ro * W + x0, tv);
+    if (kTgtSmem) load_strip4<T>(tgt + ro * W + x0, tv);
+    else load_strip4_global<T>(tgt + ro * W + x0, tv);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float o = ov[i], t = tv[i];
@@ -184,7 +202,7 @@ __device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& c
   }
 }
 
-template <typename T, bool kFwd, bool kGrad>
+template <typename T, bool kFwd, bool kGrad, bool kTgtSmem>
 __global__ void __launch_bounds__(256)
 oks_loss_fast_kernel(FastArgs a) {
   extern __shared__ __align__(128) unsigned char stage_mem[];
@@ -226,9 +244,9 @@ oks_loss_fast_kernel(FastArgs a) {
   long long unit = blockIdx.x;
   auto fetch_unit = [&](long long un, int s) {   // `output` and `target` of a unit land in stage s
     const unsigned bytes = unit_bytes(un);
-    mbar_expect_tx(&bars[s], 2 * bytes);
+    mbar_expect_tx(&bars[s], kTgtSmem ? 2 * bytes : bytes);
     tma_load_1d(const_cast<T*>(stage_of(s)), out + un * a.G * HW, bytes, &bars[s]);
-    tma_load_1d(const_cast<T*>(tgt_stage_of(s)), tgt_all + un * a.G * HW, bytes, &bars[s]);
+    if (kTgtSmem) tma_load_1d(const_cast<T*>(tgt_stage_of(s)), tgt_all + un * a.G * HW, bytes, &bars[s]);
   };
   if (tid == 0 && unit < units) fetch_unit(unit, 0);
 
@@ -264,14 +282,14 @@ oks_loss_fast_kernel(FastArgs a) {
 
     mbar_wait(&bars[s], (a.stages == 2) ? ((it >> 1) & 1) : (it & 1));
     const T* plane = stage_of(s) + static_cast<size_t>(g) * HW;
-    const T* tgt = tgt_stage_of(s) + static_cast<size_t>(g) * HW;
+    const T* tgt = kTgtSmem ? tgt_stage_of(s) + static_cast<size_t>(g) * HW : tgt_all + hm * HW;
     if (active) {
       for (int q = 0; q < nsteps; q += 3) {
-        row_step<T, kFwd, kGrad, 0>(st, sums, cf, q, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+        row_step<T, kFwd, kGrad, kTgtSmem, 0>(st, sums, cf, q, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
         if (q + 1 < nsteps)
-          row_step<T, kFwd, kGrad, 1>(st, sums, cf, q + 1, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+          row_step<T, kFwd, kGrad, kTgtSmem, 1>(st, sums, cf, q + 1, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
         if (q + 2 < nsteps)
-          row_step<T, kFwd, kGrad, 2>(st, sums, cf, q + 2, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+          row_step<T, kFwd, kGrad, kTgtSmem, 2>(st, sums, cf, q + 2, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
       }
       if (kFwd) {
         // per-pixel loss = (w_s e + w_o oks + w_g mse) m lw (loss.py:122-127, 143), summed per strip

@@ -636,3 +636,135 @@ def test_pose_targets_from_heatmaps(pp, golden_dir):
     o3, w3 = oks_from_heatmaps(codec, gt, gt, torch.from_numpy(t["weight"]).cuda(), heatmap_size=wl.heatmap_size)
     np.testing.assert_allclose(o3.cpu().numpy(), o2, rtol=RTOL32, atol=1e-6)
     assert np.array_equal(w3.cpu().numpy(), w2)
+
+
+# --------------------------------------------------------------------------- shape / content sweep
+def _sweep_maps(rng, K, H, W):
+    """Heatmaps that stress the pruned kernels: blobs hugging borders and corners, two competing blobs,
+    saturated plateaus, pure noise, a single hot pixel, negative values."""
+    ys, xs = np.mgrid[0:H, 0:W]
+    maps = np.zeros((K, H, W), dtype=np.float32)
+    for k in range(K):
+        kind = k % 7
+        cx, cy = rng.uniform(-1, W), rng.uniform(-1, H)
+        if kind == 0:    # blob near a border / corner
+            cx, cy = rng.choice([0.3, W - 1.2, rng.uniform(0, W - 1)]), rng.choice([0.4, H - 1.3, rng.uniform(0, H - 1)])
+        s = rng.uniform(0.6, 3.0)
+        blob = np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * s)).astype(np.float32)
+        if kind in (0, 1):
+            maps[k] = blob * rng.uniform(0.3, 1.0)
+        elif kind == 2:  # two blobs of similar height, far apart
+            cx2, cy2 = W - 1 - cx, H - 1 - cy
+            maps[k] = 0.8 * blob + 0.79 * np.exp(-((xs - cx2) ** 2 + (ys - cy2) ** 2) / (2 * s)).astype(np.float32)
+        elif kind == 3:  # saturated plateau
+            maps[k] = np.clip(blob * 4.0, 0, 1)
+        elif kind == 4:  # noise floor only
+            maps[k] = rng.random((H, W), dtype=np.float32) * 0.02
+        elif kind == 5:  # one hot pixel on a constant background
+            maps[k] = 0.125
+            maps[k, rng.integers(0, H), rng.integers(0, W)] = 0.75
+        else:            # blob with negative surroundings
+            maps[k] = blob - 0.25
+        if kind in (0, 1, 2, 6):
+            maps[k] += rng.random((H, W), dtype=np.float32) * 0.01
+    return maps
+
+
+@pytest.mark.parametrize("H,W", [(12, 12), (16, 20), (24, 20), (33, 28), (40, 36), (64, 48), (80, 64), (96, 72), (128, 96)])
+def test_decoders_shape_sweep(pp, H, W):
+    rng = np.random.default_rng(H * 1000 + W)
+    K = 14
+    sigmas = rng.uniform(0.02, 0.12, size=K)          # radii 2 .. 9
+    maps = np.stack([_sweep_maps(rng, K, H, W) for _ in range(2)])
+    pm = pp.ProbMap((W * 4, H * 4), (W, H), sigmas)
+    am = pp.ArgMaxProbMap((W * 4, H * 4), (W, H), sigmas)
+    t = torch.from_numpy(maps).cuda()
+    dev = pm.decode_device(t)
+    dark = am.decode_device(t)
+    # the same maps through the fallback kernels (a mis-aligned view rules the TMA kernels out)
+    buf = torch.empty(maps.size + 1, device="cuda")
+    mis = buf[1:].view(maps.shape)
+    mis.copy_(t)
+    dev_v1 = pm.decode_device(mis)
+    dark_v1 = am.decode_device(mis)
+    for b in range(maps.shape[0]):
+        locs, vals, conv = oc.heatmap_expected_value(maps[b], sigmas, return_heatmap=True, conv="scipy")
+        am_ref = conv.reshape(K, -1).argmax(1)
+        for name, d in (("tma", dev), ("fallback", dev_v1)):
+            assert np.array_equal(d["argmax"][b].cpu().numpy(), am_ref), (name, H, W, b)
+            np.testing.assert_allclose(d["locs"][b].cpu().numpy(), locs, rtol=RTOL32, atol=1e-5, err_msg=name)
+            assert np.array_equal(d["vals"][b].cpu().numpy(), vals), name
+        peaks, scores = oc.heatmap_maximum(maps[b])
+        for name, d in (("tma", dark), ("fallback", dark_v1)):
+            assert np.array_equal(d["peaks"][b].cpu().numpy(), peaks), (name, H, W, b)
+            assert np.array_equal(d["scores"][b].cpu().numpy(), scores), name
+        # the two DARK kernels blur with different operation orders on flat maps; on blob-shaped channels
+        # (kinds 0-3, 6) they must agree closely
+        blobby = np.array([k % 7 in (0, 1, 3) for k in range(K)]) & (peaks[:, 0] >= 0)
+        a, c = dark["locs"][b].cpu().numpy(), dark_v1["locs"][b].cpu().numpy()
+        assert np.abs(a - c)[blobby].max() <= 2e-3, (H, W, b, np.abs(a - c)[blobby].max())
+        assert np.isfinite(a).all()
+
+
+def test_expected_decoder_small_and_odd_shapes(pp):
+    """Shapes the TMA kernels do not take (odd widths, tiny maps) still decode exactly."""
+    rng = np.random.default_rng(77)
+    for H, W in ((7, 9), (10, 10), (19, 27), (21, 30)):
+        K = 6
+        sigmas = rng.uniform(0.02, 0.06, size=K)
+        maps = _sweep_maps(rng, K, H, W)
+        r_max = int(np.ceil(3 * oc.oks_variance_table(sigmas, H, W)).max())
+        if r_max >= min(H, W):      # scipy reflects repeatedly there; not a shape the codec is used with
+            continue
+        l, v = pp.get_heatmap_expected_value(maps, sigmas)
+        l_ref, v_ref, conv = oc.heatmap_expected_value(maps, sigmas, return_heatmap=True, conv="scipy")
+        np.testing.assert_allclose(l, l_ref, rtol=RTOL32, atol=1e-5)
+        assert np.array_equal(v, v_ref)
+
+
+@pytest.mark.parametrize("H,W", [(4, 4), (5, 8), (16, 12), (33, 28), (64, 48), (96, 72), (192, 192)])
+def test_loss_fast_path_shape_sweep(pp, H, W):
+    """Fused mean-mode kernel (TMA fast path) against the oracle and against the general kernel, across shapes
+    incl. tiny maps, a strip count that is not a multiple of anything, and a map that needs single-stage TMA."""
+    torch.manual_seed(H * 100 + W)
+    B, K = (2, 3) if H * W > 20000 else (3, 5)
+    out, tgt = torch.rand(B, K, H, W), torch.rand(B, K, H, W)
+    tw = (torch.rand(B, K) < 0.7).float()
+    for kw in (dict(smoothing_weight=0.05, oks_type="minus"),
+               dict(smoothing_weight=0.2, gaussian_weight=0.15, oks_type="both", loss_weight=1.7)):
+        o_ref = out.clone().requires_grad_(True)
+        l_ref = oc.oks_heatmap_loss(o_ref, tgt, tw, per_pixel=True, **kw).mean()
+        l_ref.backward()
+        mod = pp.OKSHeatmapLoss(use_target_weight=True, **kw)
+        o = out.cuda().requires_grad_(True)
+        l = mod.forward_mean(o, tgt.cuda(), tw.cuda())
+        (l * 2.0).backward()
+        assert abs(l.item() - l_ref.item()) <= RTOL32 * abs(l_ref.item()) + 1e-9
+        _close(o.grad.cpu().numpy(), 2.0 * o_ref.grad.numpy(), RTOL32)
+        # general kernel, same mode through per_pixel + mean
+        o2 = out.cuda().requires_grad_(True)
+        if 3 * (H + 2) * (W + 2) * 4 <= 200 * 1024:
+            l2 = mod(o2, tgt.cuda(), tw.cuda(), per_pixel=True).mean()
+            l2.backward()
+            assert abs(l2.item() - l_ref.item()) <= RTOL32 * abs(l_ref.item()) + 1e-9
+            _close(o2.grad.cpu().numpy(), o_ref.grad.numpy(), RTOL32)
+    # forward only (no grad requested) and backward through the non-fused route
+    with torch.no_grad():
+        l3 = pp.OKSHeatmapLoss(smoothing_weight=0.05)(out.cuda(), tgt.cuda(), tw.cuda(), per_pixel=False)
+    l3_ref = oc.oks_heatmap_loss(out, tgt, tw, smoothing_weight=0.05)
+    assert abs(l3.item() - l3_ref.item()) <= RTOL32 * abs(l3_ref.item()) + 1e-9
+
+
+@pytest.mark.parametrize("H,W", [(8, 8), (17, 23), (64, 48), (100, 60), (192, 192), (300, 8)])
+def test_encode_shape_sweep(pp, H, W):
+    rng = np.random.default_rng(H + 7 * W)
+    K, B = 9, 3
+    wl = synth.Workload(8, "sweep", B, K, (W * 4, H * 4), (W, H), True)
+    kps, vis, _ = synth.make_keypoints(wl, seed=H * W)
+    sig = rng.uniform(0.02, 0.12, size=K)
+    for kind, cls, sigma in (("probmap", pp.ProbMap, 2.0), ("argmax", pp.ArgMaxProbMap, -1), ("argmax", pp.ArgMaxProbMap, 0.8)):
+        codec = cls(wl.input_size, wl.heatmap_size, sig, sigma=sigma)
+        got = codec.encode_batch(kps, vis)
+        want = np.stack([oc.encode(kind, wl.input_size, wl.heatmap_size, sig, kps[b:b + 1], vis[b:b + 1], sigma=sigma)["heatmaps"]
+                         for b in range(B)])
+        _assert_maps_close(got["heatmaps"].cpu().numpy(), want, RTOL32)
