@@ -649,6 +649,87 @@ decode_dark_kernel(pp_decode_params p, const float* __restrict__ blur_taps, int 
   }
 }
 
+// Generic DARK path for maps that do not fit shared memory: everything from global memory (L1/L2).
+// blurred(y, x) is evaluated per pixel as "row sums first, then the column combination", i.e. with the
+// operation order of the separable passes, so the values are identical to the shared-memory kernels'.
+template <typename T>
+__device__ __forceinline__ float blur_at(const T* __restrict__ src, int H, int W, int y, int x, const float* taps,
+                                         int r, bool tail, float temp) {
+  float acc = 0.0f;
+  for (int i = 0; i <= 2 * r; ++i) {
+    const int yy = y + i - r;
+    float rowsum = 0.0f;
+    if (yy >= 0 && yy < H) {
+      for (int j = 0; j <= 2 * r; ++j) {
+        const int xx = x + j - r;
+        const float v = (xx >= 0 && xx < W) ? apply_tail<T>(Elem<T>::to_f32(src[yy * W + xx]), tail, temp) : 0.0f;
+        rowsum = fmaf(taps[j], v, rowsum);
+      }
+    }
+    acc = fmaf(taps[i], rowsum, acc);
+  }
+  return acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_dark_generic_kernel(pp_decode_params p, const float* __restrict__ blur_taps, int ksize,
+                           const T* __restrict__ heatmaps, float* __restrict__ peaks, float* __restrict__ scores,
+                           float* __restrict__ refined, double* __restrict__ keypoints) {
+  __shared__ BlockScratch bs;
+  __shared__ float taps[PP_MAX_BLUR_KSIZE];
+  __shared__ float stencil[8];
+  const int H = p.H, W = p.W, HW = H * W, r = ksize / 2;
+  const bool tail = p.apply_tail != 0;
+  const int64_t N = static_cast<int64_t>(p.B) * p.K;
+  for (int i = threadIdx.x; i < ksize; i += blockDim.x) taps[i] = blur_taps[i];
+  __syncthreads();
+  for (int64_t hm = blockIdx.x; hm < N; hm += gridDim.x) {
+    const T* src = heatmaps + hm * HW;
+    float top = -INFINITY;
+    int at = 0x7fffffff;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x)
+      argmax_combine(top, at, apply_tail<T>(Elem<T>::to_f32(src[i]), tail, p.temperature), i);
+    block_argmax(top, at, bs);
+    const bool empty = !(top > 0.0f);
+    float fx = -1.0f, fy = -1.0f;
+    const int px = at % W, py = at / W;
+    if (!empty) {
+      float bmax = -INFINITY;
+      for (int i = threadIdx.x; i < HW; i += blockDim.x)
+        bmax = fmaxf(bmax, blur_at<T>(src, H, W, i / W, i % W, taps, r, tail, p.temperature));
+      bmax = block_max(bmax, bs);
+      if (threadIdx.x < 7) {
+        const int dxs[7] = {0, 1, -1, 0, 0, 1, -1}, dys[7] = {0, 0, 0, 1, -1, 1, -1};
+        const int yy = min(max(py + dys[threadIdx.x], 0), H - 1), xx = min(max(px + dxs[threadIdx.x], 0), W - 1);
+        stencil[threadIdx.x] = blur_at<T>(src, H, W, yy, xx, taps, r, tail, p.temperature);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const float ratio = __fdiv_rn(top, __fadd_rn(bmax, 1e-12f));
+        float b[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) b[q] = dark_log(stencil[q], ratio);
+        dark_shift(b, px, py, fx, fy);
+      }
+    }
+    if (threadIdx.x == 0) {
+      if (peaks) {
+        peaks[hm * 2] = empty ? -1.0f : static_cast<float>(px);
+        peaks[hm * 2 + 1] = empty ? -1.0f : static_cast<float>(py);
+      }
+      scores[hm] = top;
+      refined[hm * 2] = fx;
+      refined[hm * 2 + 1] = fy;
+      if (keypoints) {
+        keypoints[hm * 2] = static_cast<double>(fx) / static_cast<double>(W - 1) * p.input_w;
+        keypoints[hm * 2 + 1] = static_cast<double>(fy) / static_cast<double>(H - 1) * p.input_h;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------
 // head tail, stand-alone
 // ---------------------------------------------------------------------------
@@ -807,9 +888,13 @@ int launch_decode_dark(const pp_decode_params& p, const float* taps, int ksize, 
   }
   const PlaneGeom g = plane_geom(p.H, p.W, r == 5 ? 2 * r + kTile : 0);
   const size_t smem = sizeof(float) * (static_cast<size_t>(g.raw_floats) + g.tmp_floats + g.out_floats);
-  PP_REQUIRE(smem <= static_cast<size_t>(pp_smem_optin()), PP_ERR_UNSUPPORTED_SHAPE,
-             "pp_decode_argmax_dark: %dx%d maps need %zu bytes of shared memory (> %lld)", p.H, p.W, smem,
-             static_cast<long long>(pp_smem_optin()));
+  if (smem + 4096 > static_cast<size_t>(pp_smem_optin())) {   // too large for shared memory: global-memory path
+    const int ggrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * 8));
+    decode_dark_generic_kernel<T><<<ggrid, 256, 0, st>>>(p, taps, ksize, static_cast<const T*>(heatmaps), peaks, scores,
+                                                         refined, keypoints);
+    PP_CUDA_OK(cudaGetLastError());
+    return PP_OK;
+  }
   const bool vec = (p.W % Elem<T>::kVec == 0) && pp_aligned16(heatmaps);
   const int threads = pick_threads(p.H, p.W);
   int per_sm = 1;

@@ -57,7 +57,7 @@ __device__ __forceinline__ float oks_term_grad(int type, float t) {
 
 template <typename T>
 __global__ void __launch_bounds__(kLossThreads)
-oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad) {
+oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad, int band_h) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_f[8];
   __shared__ double red_d[3][8];
@@ -65,10 +65,13 @@ oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad) {
 
   const pp_loss_params& p = a.p;
   const int H = p.H, W = p.W, HW = H * W, S = W + 2;
-  const int plane = (H + 2) * S;
+  // The heatmap is processed in horizontal bands of band_h rows (one band when it fits shared memory):
+  //   A : rows y0-2 .. y1+1 of `output` (zero outside the map), (band_h + 4) x S
+  //   P, Q : 2 c gx, 2 c gy on rows y0-1 .. y1 (zero outside the map),  (band_h + 2) x S each
+  // Column 0 and column W+1 of every plane stay zero (the 'same' zero padding of the Sobel stencils).
   float* A = smem;
-  float* P = A + plane;
-  float* Q = P + plane;
+  float* P = A + (band_h + 4) * S;
+  float* Q = P + (band_h + 2) * S;
   const int64_t N = static_cast<int64_t>(p.B) * p.K;
   const T* out = static_cast<const T*>(a.output);
   const T* tgt = static_cast<const T*>(a.target);
@@ -80,8 +83,8 @@ oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad) {
   const float lw = static_cast<float>(p.loss_weight);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // zero borders once; interiors are rewritten per heatmap
-  for (int i = threadIdx.x; i < (want_grad ? 3 : 1) * plane; i += kLossThreads) smem[i] = 0.0f;
+  const int total_floats = (band_h + 4) * S + (want_grad ? 2 * (band_h + 2) * S : 0);
+  for (int i = threadIdx.x; i < total_floats; i += kLossThreads) smem[i] = 0.0f;
   __syncthreads();
 
   int bad_target = 0;
@@ -91,6 +94,8 @@ oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad) {
     const T* t_ptr = tgt + hm * HW;
     const T* m_ptr = mask ? mask + b * p.mask_stride_b + k * p.mask_stride_k : nullptr;
     const T* pw_ptr = pixw ? pixw + hm * HW : nullptr;
+    const T* up_ptr = (want_grad && a.upstream_kind == kUpPerPixel) ? static_cast<const T*>(a.upstream) + hm * HW : nullptr;
+    T* g_ptr = want_grad ? static_cast<T*>(a.grad) + hm * HW : nullptr;
 
     float m_k = a.kp_weights ? a.kp_weights[hm] : 1.0f;
     if (p.skip_empty_channel) {  // (target != 0).any() per channel, loss.py:180-183
@@ -99,12 +104,6 @@ oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad) {
       nz = __syncthreads_or(nz);
       if (!nz) m_k = 0.0f;
     }
-
-    for (int i = threadIdx.x; i < HW; i += kLossThreads) {
-      const int y = i / W, x = i - y * W;
-      A[(y + 1) * S + x + 1] = Elem<T>::to_f32(o_ptr[i]);
-    }
-    __syncthreads();
 
     // upstream coefficient shared by the whole heatmap
     float u_k = 1.0f;
@@ -119,47 +118,87 @@ oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad) {
       }
       if (p.mode == PP_LOSS_PER_KEYPOINT) peak = a.peak_in[hm];
     }
+    const float wg_grad = (p.mode == PP_LOSS_PER_KEYPOINT) ? w_g / static_cast<float>(HW) : w_g;  // mean over pixels
 
     double sum_l = 0.0, sum_oks = 0.0, sum_mse = 0.0;
     float max_e = -INFINITY;
     int max_i = 0x7fffffff;
 
-    for (int i = threadIdx.x; i < HW; i += kLossThreads) {
-      const int y = i / W, x = i - y * W;
-      const float* c = A + (y + 1) * S + x + 1;
-      const float o = c[0];
-      const float t = Elem<T>::to_f32(t_ptr[i]);
-      // Sobel cross-correlations (loss.py:106-109)
-      const float gx = (c[-S - 1] - c[-S + 1]) + 2.0f * (c[-1] - c[1]) + (c[S - 1] - c[S + 1]);
-      const float gy = (c[-S - 1] + 2.0f * c[-S] + c[-S + 1]) - (c[S - 1] + 2.0f * c[S] + c[S + 1]);
-      float m = m_k;
-      if (pw_ptr) m *= Elem<T>::to_f32(pw_ptr[i]);
-      if (m_ptr) m *= Elem<T>::to_f32(m_ptr[i]);
+    for (int y0 = 0; y0 < H; y0 += band_h) {
+      const int y1 = min(y0 + band_h, H), bh = y1 - y0;
+      // stage rows y0-2 .. y1+1
+      for (int i = threadIdx.x; i < (bh + 4) * W; i += kLossThreads) {
+        const int lr = i / W, x = i - lr * W, y = y0 - 2 + lr;
+        A[lr * S + x + 1] = (y >= 0 && y < H) ? Elem<T>::to_f32(o_ptr[y * W + x]) : 0.0f;
+      }
+      __syncthreads();
 
-      if (want_fwd) {
-        bad_target |= !(t >= 0.0f && t <= 1.0f);
-        const float e = __fmul_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), m);
-        const float ok = __fmul_rn(oks_term(p.oks_type, o, t), m);
-        const float d = __fsub_rn(o, t);
-        const float ms = __fmul_rn(__fmul_rn(d, d), m);
-        if (p.mode == PP_LOSS_PER_KEYPOINT) {
-          sum_oks += ok;
-          sum_mse += ms;
-          if (e > max_e) { max_e = e; max_i = i; }
-        } else {
-          const float l = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(w_s, e), __fmul_rn(w_o, ok)), __fmul_rn(w_g, ms)), lw);
-          if (p.mode == PP_LOSS_PER_PIXEL) static_cast<T*>(a.loss_map)[hm * HW + i] = Elem<T>::from_f32(l);
-          else sum_l += l;
+      // phase 1: Sobel pair on rows y0-1 .. y1; forward terms on the band's own rows
+      for (int i = threadIdx.x; i < (bh + 2) * W; i += kLossThreads) {
+        const int pr = i / W, x = i - pr * W, y = y0 - 1 + pr;
+        const bool inside = y >= 0 && y < H;
+        const float* c = A + (pr + 1) * S + x + 1;
+        // Sobel cross-correlations (loss.py:106-109)
+        const float gx = (c[-S - 1] - c[-S + 1]) + 2.0f * (c[-1] - c[1]) + (c[S - 1] - c[S + 1]);
+        const float gy = (c[-S - 1] + 2.0f * c[-S] + c[-S + 1]) - (c[S - 1] + 2.0f * c[S] + c[S + 1]);
+        const int pix = y * W + x;
+        float m = m_k;
+        if (inside) {
+          if (pw_ptr) m *= Elem<T>::to_f32(pw_ptr[pix]);
+          if (m_ptr) m *= Elem<T>::to_f32(m_ptr[pix]);
+        }
+        if (want_fwd && y >= y0 && y < y1) {
+          const float o = c[0];
+          const float t = Elem<T>::to_f32(t_ptr[pix]);
+          bad_target |= !(t >= 0.0f && t <= 1.0f);
+          const float e = __fmul_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), m);
+          const float ok = __fmul_rn(oks_term(p.oks_type, o, t), m);
+          const float d = __fsub_rn(o, t);
+          const float ms = __fmul_rn(__fmul_rn(d, d), m);
+          if (p.mode == PP_LOSS_PER_KEYPOINT) {
+            sum_oks += ok;
+            sum_mse += ms;
+            if (e > max_e) { max_e = e; max_i = pix; }
+          } else {
+            const float l = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(w_s, e), __fmul_rn(w_o, ok)), __fmul_rn(w_g, ms)), lw);
+            if (p.mode == PP_LOSS_PER_PIXEL) static_cast<T*>(a.loss_map)[hm * HW + pix] = Elem<T>::from_f32(l);
+            else sum_l += l;
+          }
+        }
+        if (want_grad) {
+          float cs = 0.0f;
+          if (inside) {
+            const float u = up_ptr ? Elem<T>::to_f32(up_ptr[pix]) : u_k;
+            cs = lw * w_s * u * m;
+            if (p.mode == PP_LOSS_PER_KEYPOINT && pix != peak) cs = 0.0f;  // max() routes to one pixel
+          }
+          P[pr * S + x + 1] = 2.0f * cs * gx;
+          Q[pr * S + x + 1] = 2.0f * cs * gy;
         }
       }
+
       if (want_grad) {
-        float u = u_k;
-        if (a.upstream_kind == kUpPerPixel) u = Elem<T>::to_f32(static_cast<const T*>(a.upstream)[hm * HW + i]);
-        float cs = lw * w_s * u * m;
-        if (p.mode == PP_LOSS_PER_KEYPOINT && i != peak) cs = 0.0f;  // max() routes to one pixel
-        P[(y + 1) * S + x + 1] = 2.0f * cs * gx;
-        Q[(y + 1) * S + x + 1] = 2.0f * cs * gy;
+        __syncthreads();
+        // phase 2: adjoint stencil on the band's own rows
+        for (int i = threadIdx.x; i < bh * W; i += kLossThreads) {
+          const int lr = i / W, x = i - lr * W, y = y0 + lr;
+          const int at = (lr + 1) * S + x + 1;   // row y in P / Q coordinates
+          const float* pc = P + at;
+          const float* qc = Q + at;
+          const float sx = (pc[-S - 1] - pc[-S + 1]) + 2.0f * (pc[-1] - pc[1]) + (pc[S - 1] - pc[S + 1]);
+          const float sy = (qc[-S - 1] + 2.0f * qc[-S] + qc[-S + 1]) - (qc[S - 1] + 2.0f * qc[S] + qc[S + 1]);
+          const int pix = y * W + x;
+          const float o = A[(lr + 2) * S + x + 1];
+          const float t = Elem<T>::to_f32(t_ptr[pix]);
+          float m = m_k;
+          if (pw_ptr) m *= Elem<T>::to_f32(pw_ptr[pix]);
+          if (m_ptr) m *= Elem<T>::to_f32(m_ptr[pix]);
+          const float u = up_ptr ? Elem<T>::to_f32(up_ptr[pix]) : u_k;
+          const float direct = lw * u * m * (w_o * oks_term_grad(p.oks_type, t) + wg_grad * 2.0f * (o - t));
+          g_ptr[pix] = Elem<T>::from_f32(direct - sx - sy);
+        }
       }
+      __syncthreads();   // the planes are rewritten by the next band / heatmap
     }
 
     if (want_fwd && p.mode != PP_LOSS_PER_PIXEL) {
@@ -183,32 +222,8 @@ oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad) {
           a.partials[hm] = sl;
         }
       }
-    }
-
-    if (want_grad) {
       __syncthreads();
-      T* g_ptr = static_cast<T*>(a.grad) + hm * HW;
-      for (int i = threadIdx.x; i < HW; i += kLossThreads) {
-        const int y = i / W, x = i - y * W;
-        const int at = (y + 1) * S + x + 1;
-        const float* pc = P + at;
-        const float* qc = Q + at;
-        const float sx = (pc[-S - 1] - pc[-S + 1]) + 2.0f * (pc[-1] - pc[1]) + (pc[S - 1] - pc[S + 1]);
-        const float sy = (qc[-S - 1] + 2.0f * qc[-S] + qc[-S + 1]) - (qc[S - 1] + 2.0f * qc[S] + qc[S + 1]);
-        const float o = A[at];
-        const float t = Elem<T>::to_f32(t_ptr[i]);
-        float m = m_k;
-        if (pw_ptr) m *= Elem<T>::to_f32(pw_ptr[i]);
-        if (m_ptr) m *= Elem<T>::to_f32(m_ptr[i]);
-        float u = u_k;
-        if (a.upstream_kind == kUpPerPixel) u = Elem<T>::to_f32(static_cast<const T*>(a.upstream)[hm * HW + i]);
-        float wg = w_g;
-        if (p.mode == PP_LOSS_PER_KEYPOINT) wg = w_g / static_cast<float>(HW);  // mean over pixels
-        const float direct = lw * u * m * (w_o * oks_term_grad(p.oks_type, t) + wg * 2.0f * (o - t));
-        g_ptr[i] = Elem<T>::from_f32(direct - sx - sy);
-      }
     }
-    __syncthreads();
   }
   if (a.range_flag && bad_target) atomicOr(a.range_flag, 1);
 }
@@ -248,29 +263,33 @@ int check_loss_params(const char* fn, const pp_loss_params* p) {
   return PP_OK;
 }
 
+int env_int(const char* name, int fallback) {   // tuning overrides for experiments and tests
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : fallback;
+}
+
 template <typename T>
 int launch_loss(const LossArgs& a, bool fwd, bool grad, cudaStream_t st) {
   const pp_loss_params& p = a.p;
   const int64_t N = static_cast<int64_t>(p.B) * p.K;
-  const size_t plane = sizeof(float) * static_cast<size_t>(p.H + 2) * (p.W + 2);
-  const size_t smem = plane * (grad ? 3 : 1);
-  PP_REQUIRE(smem <= static_cast<size_t>(pp_smem_optin()), PP_ERR_UNSUPPORTED_SHAPE,
-             "pp_oks_loss: %dx%d maps need %zu bytes of shared memory (> %lld)", p.H, p.W, smem,
-             static_cast<long long>(pp_smem_optin()));
+  // bands of band_h rows: (band_h + 4) rows of `output` and, with a gradient, 2 x (band_h + 2) rows of P / Q
+  const size_t row = sizeof(float) * static_cast<size_t>(p.W + 2);
+  const size_t budget = static_cast<size_t>(pp_smem_optin()) - 4096;
+  const size_t fixed = row * (grad ? 8 : 4);
+  PP_REQUIRE(fixed + row * (grad ? 3 : 1) <= budget, PP_ERR_UNSUPPORTED_SHAPE,
+             "pp_oks_loss: rows of %d pixels are too wide for shared memory", p.W);
+  int band_h = static_cast<int>(std::min<size_t>(p.H, (budget - fixed) / (row * (grad ? 3 : 1))));
+  if (const int cap = env_int("PP_LOSS_BAND", 0); cap > 0) band_h = std::min(band_h, cap);   // test hook: force several bands
+  const size_t smem = fixed + row * (grad ? 3 : 1) * band_h;
   int per_sm = 1;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(oks_loss_kernel<T>), kLossThreads, smem, &per_sm)) return rc;
   const int grid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * per_sm));
-  oks_loss_kernel<T><<<grid, kLossThreads, smem, st>>>(a, fwd, grad);
+  oks_loss_kernel<T><<<grid, kLossThreads, smem, st>>>(a, fwd, grad, band_h);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }
 
 // ---- fast path dispatch (pp_loss_fast.cuh) ---------------------------------------------------
-int env_int(const char* name, int fallback) {   // tuning overrides for experiments
-  const char* v = std::getenv(name);
-  return (v && *v) ? std::atoi(v) : fallback;
-}
-
 bool fast_path_ok(const pp_loss_params& p, const void* output, const void* target, const void* pixel_weights,
                   const void* mask, const void* grad) {
   const int e = p.dtype == PP_F32 ? 4 : 2;
