@@ -1,4 +1,5 @@
 // Library-level entry points of the C ABI: version, error string, device info.
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 
@@ -49,6 +50,11 @@ int pp_sm_count() {
 int64_t pp_smem_optin() {
   const DevInfo* d = dev_info();
   return d ? d->smem_optin : 227 * 1024;
+}
+
+int pp_env_int(const char* name, int fallback) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : fallback;
 }
 
 int pp_configure_kernel(const void* kernel, int threads, size_t smem, int* ctas_per_sm) {

@@ -36,6 +36,9 @@ int64_t pp_smem_optin();      // opt-in dynamic shared memory per block
 // threads fit per SM.  Cached per (kernel, device, threads, smem) in thread-local storage.
 int pp_configure_kernel(const void* kernel, int threads, size_t smem, int* ctas_per_sm);
 
+// Integer tuning override from the environment (experiments / tests); `fallback` when unset.
+int pp_env_int(const char* name, int fallback);
+
 static inline bool pp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------

@@ -848,6 +848,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
     int fper = 1;
     if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_fast_kernel<T>), kFThreads, fsmem, &fper))
       return rc;
+    if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) fper = std::min(fper, cap);
     int64_t fgrid64 = std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper);
     const int fgrid = static_cast<int>(fgrid64);
     unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;

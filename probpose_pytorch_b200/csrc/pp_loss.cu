@@ -263,10 +263,7 @@ int check_loss_params(const char* fn, const pp_loss_params* p) {
   return PP_OK;
 }
 
-int env_int(const char* name, int fallback) {   // tuning overrides for experiments and tests
-  const char* v = std::getenv(name);
-  return (v && *v) ? std::atoi(v) : fallback;
-}
+int env_int(const char* name, int fallback) { return pp_env_int(name, fallback); }
 
 template <typename T>
 int launch_loss(const LossArgs& a, bool fwd, bool grad, cudaStream_t st) {
@@ -304,6 +301,7 @@ int launch_fast_tt(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cu
   int per_sm = 1;
   auto kern = pp_loss_fast::oks_loss_fast_kernel<T, kFwd, kGrad, kTgtSmem>;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), threads, smem, &per_sm)) return rc;
+  if (const int cap = env_int("PP_LOSS_CTAS", 0); cap > 0) per_sm = std::min(per_sm, cap);
   const int64_t units = (a.N + a.G - 1) / a.G;
   const int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(pp_sm_count()) * per_sm));
   kern<<<grid, threads, smem, st>>>(a);
