@@ -820,3 +820,29 @@ def test_dark_decoder_large_maps_generic_path(pp):
     k2_ref, s2_ref = oc.decode_expected(maps, (768, 768), (W, H), np.array([0.1] * 4), conv="scipy")
     np.testing.assert_allclose(k2, k2_ref, rtol=RTOL32, atol=1e-5)
     assert np.array_equal(s2, s2_ref)
+
+
+def test_host_pipeline_orders_results_and_reuses_buffers(pp):
+    """host_io.pipelined_steps: results come back in order, one per batch, although input buffers are reused
+    and copies overlap the kernels; the step is the real encode -> decode round trip."""
+    from probpose_pytorch_b200.host_io import pipelined_steps
+    wl = synth.WORKLOADS[1]
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    batches, want = [], []
+    for i in range(7):
+        kps, vis, _ = synth.make_keypoints(wl, batch=4, seed=300 + i)
+        batches.append((torch.from_numpy(kps).pin_memory(), torch.from_numpy(vis).pin_memory()))
+        enc = am.encode_batch(torch.from_numpy(kps).cuda(), torch.from_numpy(vis).cuda())
+        want.append(am.decode_device(enc["heatmaps"])["keypoints"].cpu())
+
+    def step(kps, vis):
+        enc = am.encode_batch(kps, vis)
+        return am.decode_device(enc["heatmaps"])["keypoints"], enc["keypoint_weights"].sum()
+
+    got = list(pipelined_steps(iter(batches), step, torch.device("cuda:0")))
+    assert len(got) == len(batches)
+    for (rec, wsum), w, (kps, vis) in zip(got, want, batches):
+        assert torch.equal(rec, w)
+    assert list(pipelined_steps(iter([]), step, torch.device("cuda:0"))) == []
+    with pytest.raises(ValueError):
+        list(pipelined_steps(iter([(torch.zeros(1, 17, 2), torch.zeros(1, 17))]), step, torch.device("cuda:0")))
