@@ -389,16 +389,36 @@ def run_product(args):
             prep_cache[key] = _Prepared(loss_fn, s["pred"], s["tgt"], s["w"], None, _lib.PP_LOSS_PIXEL_MEAN)
         return prep_cache[key].forward(want_grad=True)
 
+    # head tails (section 8 a10 / f-2), not part of the step: logits with the spread of a trained head
+    for s in sets:
+        s["logits"] = ((s["pred"].float() - 0.3) * 4.0).to(tdtype).requires_grad_(True)
+        s["up"] = torch.rand_like(s["pred"])
+
+    def k_tail(s):
+        return pp.heatmap_tail(s["logits"].detach(), 0.5)
+
+    def k_sparse_fwd(s):
+        return pp.heatmap_tail(s["logits"].detach(), 0.5, normalize=1.0)
+
+    def k_sparse_fwd_bwd(s):
+        s["logits"].grad = None
+        y = pp.heatmap_tail(s["logits"], 0.5, normalize=1.0)
+        y.backward(s["up"])
+        return y, s["logits"].grad
+
     sampler.mark = "kernels"
     iters = max(20, min(400, args.steps))
     kt = {"encode": time_kernel(k_encode, iters), "decode_expected": time_kernel(k_decode, iters),
-          "decode_dark": time_kernel(k_dark, iters), "loss_fwd_bwd": time_kernel(k_loss, iters)}
+          "decode_dark": time_kernel(k_dark, iters), "loss_fwd_bwd": time_kernel(k_loss, iters),
+          "head_tail": time_kernel(k_tail, iters), "sparsemax_tail_fwd": time_kernel(k_sparse_fwd, iters),
+          "sparsemax_tail_fwd_bwd": time_kernel(k_sparse_fwd_bwd, iters)}
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    alg = {"encode": 1, "decode_expected": 1, "decode_dark": 1, "loss_fwd_bwd": 3}
+    alg = {"encode": 1, "decode_expected": 1, "decode_dark": 1, "loss_fwd_bwd": 3, "head_tail": 2,
+           "sparsemax_tail_fwd": 2, "sparsemax_tail_fwd_bwd": 5}
     kernels = {k: {"ms": 1e3 * t, "GBps": alg[k] * n_hm * hm_bytes / t / 1e9,
                    "frac": alg[k] * n_hm * hm_bytes / t / 1e9 / peak,
                    "heatmaps_per_s": n_hm / t} for k, t in kt.items()}

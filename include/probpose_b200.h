@@ -147,6 +147,19 @@ PP_API int pp_heatmap_tail(const void* x, void* y, int32_t dtype, int64_t numel,
 PP_API int pp_heatmap_tail_backward(const void* x, const void* grad_y, void* grad_x, int32_t dtype, int64_t numel,
                                     float temperature, pp_stream_t stream);
 
+/* Sparsemax-normalised head tail (head.py:237-245, 526-532 with normalize != None; the projection itself is the
+ * PyPI package sparsemax==0.1.9, `Sparsemax(dim=-1)` over the H*W pixels of each heatmap):
+ *   y = clamp(sparsemax(x / temperature) * normalize, 0, 1).
+ * aux (n_heatmaps, 2) float32 receives (max, tau) per heatmap for the backward; may be NULL at inference. */
+PP_API int pp_sparsemax_tail(const void* x, void* y, float* aux, int32_t dtype, int64_t n_heatmaps, int64_t hw,
+                             float temperature, float normalize, pp_stream_t stream);
+
+/* backward of pp_sparsemax_tail: through the clamp (inclusive), the scale, the projection
+ * (g_z = [p != 0] (g_p - mean over the support of g_p)) and the division by the temperature */
+PP_API int pp_sparsemax_tail_backward(const void* x, const void* grad_y, const float* aux, void* grad_x, int32_t dtype,
+                                      int64_t n_heatmaps, int64_t hw, float temperature, float normalize,
+                                      pp_stream_t stream);
+
 /* ---- training targets from decoded keypoints: ProbPoseLoss._oks_from_heatmaps (loss.py:550-640, with
  *      compute_oks(use_area=False, per_kpt=True), loss.py:715-764) and _error_from_heatmaps (loss.py:512-548).
  *      gt/dt keypoints are the (B, K, 2) float64 outputs of pp_decode_argmax_dark on the target / predicted maps. */

@@ -30,7 +30,9 @@ Third-party arithmetic that the reference calls but does not contain:
     here) -> restated in ``blur_zero_pad_f32`` (separable float32 taps of
     ``getGaussianKernel(11, 0)``); agreement with cv2 is ~2e-7 relative, which
     is the precision at which cv2 itself is reproducible;
-  * ``numpy.linalg.pinv`` on 2x2 symmetric matrices -> closed form.
+  * ``numpy.linalg.pinv`` on 2x2 symmetric matrices -> closed form;
+  * ``sparsemax.Sparsemax`` (sparsemax==0.1.9 pinned, not installed, no reference test) -> published
+    algorithm restated in ``sparsemax_oracle`` -- PARITY UNPINNED, see that module's header.
 """
 
 from .codec_oracle import (  # noqa: F401
@@ -52,4 +54,5 @@ from .codec_oracle import (  # noqa: F401
     head_tail,
 )
 from .loss_oracle import oks_heatmap_loss, oks_heatmap_loss_grad_closed_form  # noqa: F401
+from .sparsemax_oracle import head_tail_sparsemax, sparsemax, sparsemax_f64  # noqa: F401
 from .targets_oracle import error_from_heatmaps, oks_from_heatmaps  # noqa: F401

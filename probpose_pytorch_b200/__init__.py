@@ -4,7 +4,7 @@ Drop-in, same call signatures as zir-vision/ProbPose_pytorch for:
   * ``codec``   : ``generate_probmaps``, ``ProbMap``, ``ArgMaxProbMap``, ``Codec``
   * ``heatmap`` : ``get_heatmap_maximum``, ``get_heatmap_expected_value``
   * ``loss``    : ``OKSHeatmapLoss``
-  * ``head``    : ``heatmap_tail`` (tail of ``ProbMapHead.forward_heatmap``)
+  * ``head``    : ``heatmap_tail`` (tail of ``ProbMapHead.forward_heatmap``), ``Sparsemax``
 
 Everything computes in hand-written sm_100a CUDA behind the C ABI of
 ``include/probpose_b200.h`` (``csrc/libprobpose_b200.so``); there is no CPU
@@ -12,10 +12,10 @@ fallback -- calls raise when the library or a GPU is missing.
 """
 
 from .codec import ArgMaxProbMap, Codec, ProbMap, generate_probmaps  # noqa: F401
-from .head import HeatmapTail, heatmap_tail, patch_probmap_head  # noqa: F401
+from .head import HeatmapTail, Sparsemax, heatmap_tail, patch_probmap_head  # noqa: F401
 from .heatmap import get_heatmap_expected_value, get_heatmap_maximum  # noqa: F401
 from .loss import OKSHeatmapLoss  # noqa: F401
 
 __all__ = ["ArgMaxProbMap", "Codec", "ProbMap", "generate_probmaps", "heatmap_tail", "HeatmapTail",
-           "patch_probmap_head",
+           "patch_probmap_head", "Sparsemax",
            "get_heatmap_expected_value", "get_heatmap_maximum", "OKSHeatmapLoss"]

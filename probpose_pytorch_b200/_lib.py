@@ -25,6 +25,7 @@ EXPORTS = (
     "pp_version", "pp_last_error_string", "pp_device_info", "pp_encode", "pp_decode_expected",
     "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes",
     "pp_heatmap_maximum", "pp_decode_argmax_dark", "pp_heatmap_tail", "pp_heatmap_tail_backward",
+    "pp_sparsemax_tail", "pp_sparsemax_tail_backward",
     "pp_oks_loss_scratch_bytes",
     "pp_oks_loss_forward", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
 )
@@ -85,6 +86,8 @@ def lib() -> C.CDLL:
     L.pp_decode_argmax_dark.argtypes = [C.POINTER(DecodeParams), vp, i32, vp, vp, vp, vp, vp, vp, i64, vp]
     L.pp_heatmap_tail.argtypes = [vp, vp, i32, i64, f32, vp]
     L.pp_heatmap_tail_backward.argtypes = [vp, vp, vp, i32, i64, f32, vp]
+    L.pp_sparsemax_tail.argtypes = [vp, vp, vp, i32, i64, i64, f32, f32, vp]
+    L.pp_sparsemax_tail_backward.argtypes = [vp, vp, vp, vp, i32, i64, i64, f32, f32, vp]
     L.pp_oks_loss_scratch_bytes.argtypes = [C.POINTER(LossParams)]
     L.pp_oks_loss_scratch_bytes.restype = i64
     L.pp_oks_loss_forward.argtypes = [C.POINTER(LossParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, i64, vp]

@@ -846,3 +846,80 @@ def test_host_pipeline_orders_results_and_reuses_buffers(pp):
     assert list(pipelined_steps(iter([]), step, torch.device("cuda:0"))) == []
     with pytest.raises(ValueError):
         list(pipelined_steps(iter([(torch.zeros(1, 17, 2), torch.zeros(1, 17))]), step, torch.device("cuda:0")))
+
+
+# ---- Sparsemax-normalised head tail (oracle = published algorithm, parity unpinned) --------
+# The projection's outputs are O(1 / support); the float32 sort + cumsum of the published algorithm carries
+# ~1e-7 of absolute noise in tau, so values are compared at atol 1e-6 (of a [0, 1] range) + rtol 1e-5, and
+# against the float64 evaluation of the same projection at the same bar.
+SPARSE_ATOL = 1e-6
+
+
+@pytest.mark.parametrize("shape,scale", [((3, 5, 64, 48), 3.0), ((2, 17, 64, 48), 0.05), ((2, 3, 7, 5), 1.0),
+                                         ((1, 2, 96, 72), 20.0), ((1, 2, 100, 100), 1.0), ((1, 2, 250, 240), 2.0)])
+def test_sparsemax_tail_forward_backward(pp, shape, scale):
+    """clamp(sparsemax(x / T) * normalize, 0, 1) and its gradient: dense supports (small logits), sparse
+    supports (large logits), a map larger than shared memory (250 x 240: logits re-read from L2)."""
+    torch.manual_seed(shape[-1] + int(scale * 10))
+    x = torch.randn(shape) * scale
+    x[0, 0].view(-1)[:6] = x[0, 0].max() + 0.3           # exact ties at the maximum
+    up = torch.rand(shape)
+    for T, normalize in ((0.5, 1.0), (0.5, 2.5), (1.0, 0.5)):
+        a = x.clone().requires_grad_(True)
+        ya = oc.head_tail_sparsemax(a, T, normalize)
+        (ya * up).sum().backward()
+        b = x.cuda().requires_grad_(True)
+        yb = pp.heatmap_tail(b, T, normalize=normalize)
+        (yb * up.cuda()).sum().backward()
+        torch.testing.assert_close(yb.detach().cpu(), ya.detach(), rtol=RTOL32, atol=SPARSE_ATOL)
+        p64 = oc.sparsemax_f64((x / T).reshape(*shape[:2], -1).numpy()).reshape(shape)
+        np.testing.assert_allclose(yb.detach().cpu().numpy(), np.clip(p64 * normalize, 0, 1), rtol=RTOL32, atol=SPARSE_ATOL)
+        # the support (and with it the routing of the gradient) may differ on pixels whose output is ~1e-7
+        ga, gb = a.grad.numpy(), b.grad.cpu().numpy()
+        agree = np.abs(ga - gb) <= 1e-4 * np.abs(ga) + 1e-5 * np.abs(ga).max()
+        assert agree.mean() >= 0.999, agree.mean()
+        if normalize == 1.0:
+            s = yb.detach().reshape(*shape[:2], -1).sum(-1)
+            torch.testing.assert_close(s, torch.ones_like(s), rtol=0, atol=1e-4)
+    # inference call: no aux, no graph
+    with torch.no_grad():
+        assert torch.equal(pp.heatmap_tail(x.cuda(), 0.5, normalize=1.0), pp.heatmap_tail(x.cuda().requires_grad_(True), 0.5, normalize=1.0))
+
+
+def test_sparsemax_module_bf16_and_patched_head(pp):
+    torch.manual_seed(9)
+    x = torch.randn(4, 6, 300)
+    y = pp.Sparsemax(dim=-1)(x.cuda())
+    torch.testing.assert_close(y.cpu(), oc.sparsemax(x), rtol=RTOL32, atol=SPARSE_ATOL)
+    y1 = pp.Sparsemax(dim=1)(x.cuda())                    # any axis, as the package allows
+    torch.testing.assert_close(y1.cpu(), oc.sparsemax(x.movedim(1, -1)).movedim(-1, 1), rtol=RTOL32, atol=SPARSE_ATOL)
+    # bf16: oracle = float32 algorithm on the bf16-rounded logits (SURVEY.md 8c), result rounded to bf16
+    xb = (torch.randn(2, 3, 16, 12) * 2).bfloat16()
+    want = oc.head_tail_sparsemax((xb.float() / 0.5).bfloat16().float(), 1.0, 1.0)
+    got = pp.heatmap_tail(xb.cuda(), 0.5, normalize=1.0)
+    assert got.dtype == torch.bfloat16
+    torch.testing.assert_close(got.float().cpu(), want, rtol=RTOL16, atol=1e-3)
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.deconv_layers = torch.nn.Identity()
+            self.conv_layers = torch.nn.Conv2d(5, 5, 1)
+            self.final_layer = torch.nn.Identity()
+            self.temperature = 0.5
+            self.normalize = 1.0
+            self.normalize_layer = lambda z: oc.sparsemax(z.cpu()).to(z.device)   # stands in for the package
+
+        def forward_heatmap(self, x):
+            x = self.final_layer(self.conv_layers(self.deconv_layers(x)))
+            B, C, H, W = x.shape
+            x = self.normalize_layer(x.reshape(B, C, H * W) / self.temperature) * self.normalize
+            return torch.clamp(x, 0, 1).reshape(B, C, H, W)
+
+    m = Stub().cuda()
+    xin = torch.randn(2, 5, 16, 12, device="cuda") * 3
+    want = m.forward_heatmap(xin)
+    got = pp.patch_probmap_head(m).forward_heatmap(xin)
+    torch.testing.assert_close(got, want, rtol=RTOL32, atol=SPARSE_ATOL)
+    got.square().sum().backward()
+    assert m.conv_layers.weight.grad is not None and torch.isfinite(m.conv_layers.weight.grad).all()

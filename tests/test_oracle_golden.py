@@ -165,3 +165,25 @@ def test_pose_targets(golden_dir):
     assert w[2] == 0 and not oks[2].any()
     err = oc.error_from_heatmaps(g["clean"], g["blob"], wl.input_size, wl.heatmap_size, backend="cv2")
     assert np.array_equal(err, t["error"])
+
+
+def test_sparsemax_oracle_is_the_simplex_projection():
+    """The Sparsemax restatement (parity unpinned: the package is absent) against the projection's defining
+    properties and a float64 evaluation; autograd of the custom backward against finite differences."""
+    import torch
+    rng = np.random.default_rng(5)
+    for scale in (0.05, 1.0, 10.0):
+        z = (rng.standard_normal((4, 700)) * scale).astype(np.float32)
+        p = oc.sparsemax(torch.from_numpy(z)).numpy()
+        assert (p >= 0).all()
+        np.testing.assert_allclose(p.sum(-1), 1.0, atol=2e-5)
+        np.testing.assert_allclose(p, oc.sparsemax_f64(z), atol=1e-6)
+        # KKT: on the support p = z - tau with one tau per row; off the support z <= tau
+        for r in range(z.shape[0]):
+            s = p[r] > 0
+            tau = (z[r][s] - p[r][s])
+            assert np.ptp(tau) < 1e-5 and (z[r][~s] <= tau.mean() + 1e-6).all()
+    z = torch.from_numpy(rng.standard_normal((3, 9))).double().requires_grad_(True)
+    assert torch.autograd.gradcheck(oc.sparsemax, (z,), eps=1e-7, atol=1e-5)
+    y = oc.head_tail_sparsemax(torch.from_numpy(rng.standard_normal((2, 3, 4, 5)).astype(np.float32)), 0.5, 2.0)
+    assert y.shape == (2, 3, 4, 5) and float(y.max()) <= 1.0 and float(y.min()) >= 0.0
