@@ -231,6 +231,26 @@ PP_API int pp_oks_loss_backward(const pp_loss_params* p,
  * reused by autograd without a host sync; a no-op launch in the usual case. */
 PP_API int pp_scale_inplace(void* data, int32_t dtype, int64_t numel, const float* scale_dev, pp_stream_t stream);
 
+/* ---- validation metrics on (N, K)-sized arrays; one small launch each ---- */
+
+/* keypoint_pck_accuracy (loss.py:825-866) over _calc_distances / _distance_acc (heatmap.py:55-111).
+ * pred / gt: (N, K, 2) float32 coordinates (pp_heatmap_maximum's `locs`); mask: (N, K) bytes;
+ * norm_factor: (N, 2) float32 or float64 (norm_dtype = PP_F32 | PP_F64; the arithmetic runs in that type,
+ * as NumPy's promotion does).  Out: acc (K) float64 (-1 = no valid instance), avg_acc, cnt; optionally the
+ * (K, N) float32 distances (-1 = masked). */
+PP_API int pp_pck_accuracy(const float* pred, const float* gt, const uint8_t* mask, const void* norm_factor,
+                           int32_t norm_dtype, int32_t N, int32_t K, double thr, double* acc, double* avg_acc,
+                           int32_t* cnt, float* distances /* or NULL */, pp_stream_t stream);
+
+/* ProbPoseLoss.get_binary_accuracy, force_balanced=False (loss.py:653-697): best accuracy over the given
+ * thresholds among the mask-selected entries.  out = (best_acc, best_threshold); counts (n_thresholds + 1, the
+ * last entry is the number of selected samples) may be NULL. */
+PP_API int pp_binary_accuracy(const float* dt, const float* gt, const uint8_t* mask, int64_t n, const double* thresholds,
+                              int32_t n_thresholds, float* out, int64_t* counts, pp_stream_t stream);
+
+/* ProbPoseLoss.get_mae (loss.py:699-712): mean |dt - gt| over the mask-selected entries */
+PP_API int pp_masked_mae(const float* dt, const float* gt, const uint8_t* mask, int64_t n, float* out, pp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

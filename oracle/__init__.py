@@ -54,5 +54,6 @@ from .codec_oracle import (  # noqa: F401
     head_tail,
 )
 from .loss_oracle import oks_heatmap_loss, oks_heatmap_loss_grad_closed_form  # noqa: F401
+from . import metrics_oracle  # noqa: F401
 from .sparsemax_oracle import head_tail_sparsemax, sparsemax, sparsemax_f64  # noqa: F401
 from .targets_oracle import error_from_heatmaps, oks_from_heatmaps  # noqa: F401

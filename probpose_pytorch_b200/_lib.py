@@ -28,6 +28,7 @@ EXPORTS = (
     "pp_sparsemax_tail", "pp_sparsemax_tail_backward",
     "pp_oks_loss_scratch_bytes",
     "pp_oks_loss_forward", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
+    "pp_pck_accuracy", "pp_binary_accuracy", "pp_masked_mae",
 )
 
 
@@ -86,6 +87,9 @@ def lib() -> C.CDLL:
     L.pp_decode_argmax_dark.argtypes = [C.POINTER(DecodeParams), vp, i32, vp, vp, vp, vp, vp, vp, i64, vp]
     L.pp_heatmap_tail.argtypes = [vp, vp, i32, i64, f32, vp]
     L.pp_heatmap_tail_backward.argtypes = [vp, vp, vp, i32, i64, f32, vp]
+    L.pp_pck_accuracy.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.c_double, vp, vp, vp, vp, vp]
+    L.pp_binary_accuracy.argtypes = [vp, vp, vp, i64, vp, i32, vp, vp, vp]
+    L.pp_masked_mae.argtypes = [vp, vp, vp, i64, vp, vp]
     L.pp_sparsemax_tail.argtypes = [vp, vp, vp, i32, i64, i64, f32, f32, vp]
     L.pp_sparsemax_tail_backward.argtypes = [vp, vp, vp, vp, i32, i64, i64, f32, f32, vp]
     L.pp_oks_loss_scratch_bytes.argtypes = [C.POINTER(LossParams)]

@@ -923,3 +923,59 @@ def test_sparsemax_module_bf16_and_patched_head(pp):
     torch.testing.assert_close(got, want, rtol=RTOL32, atol=SPARSE_ATOL)
     got.square().sum().backward()
     assert m.conv_layers.weight.grad is not None and torch.isfinite(m.conv_layers.weight.grad).all()
+
+
+# ---- validation metrics ------------------------------------------------------------------
+def test_pck_metrics_match_reference_outputs(pp, golden_dir):
+    """pose_pck_accuracy / keypoint_pck_accuracy / get_binary_accuracy / get_mae against the reference's own
+    outputs (tests/golden/metrics.npz): per-keypoint accuracies and counts bit-exact, the average to 1e-12."""
+    from probpose_pytorch_b200 import metrics
+    m = np.load(golden_dir / "metrics.npz")
+    g = np.load(golden_dir / "decode.npz")
+    for thr in (0.05, 0.2):
+        acc, avg, cnt = metrics.pose_pck_accuracy(g["blob"], g["clean"], m["mask"], thr=thr)
+        assert np.array_equal(acc, m[f"pose/{thr}/acc"]) and cnt == m[f"pose/{thr}/cnt"]
+        assert abs(avg - m[f"pose/{thr}/avg"]) <= 1e-12
+    norm = m["norm64"].copy()
+    acc, avg, cnt = metrics.pose_pck_accuracy(torch.from_numpy(g["blob"]).cuda(), torch.from_numpy(g["clean"]).cuda(),
+                                              m["mask"], thr=0.1, normalize=norm)
+    assert np.array_equal(acc, m["pose/norm64/acc"]) and cnt == m["pose/norm64/cnt"] and abs(avg - m["pose/norm64/avg"]) <= 1e-12
+    assert np.array_equal(norm, m["norm64"])                       # the caller's array is left alone
+    acc, avg, cnt = metrics.keypoint_pck_accuracy(m["pred"], m["gt"], m["mask"], 0.05, m["norm32"])
+    assert np.array_equal(acc, m["kpt/acc"]) and cnt == m["kpt/cnt"] and abs(avg - m["kpt/avg"]) <= 1e-12
+    acc, avg, cnt = metrics.keypoint_pck_accuracy(m["pred"], m["gt"], np.zeros_like(m["mask"]), 0.05, m["norm32"])
+    assert (acc == -1).all() and avg == 0.0 and cnt == 0
+    # distances against the oracle, both arithmetic types
+    for norm in (m["norm32"], m["norm64"]):
+        d = metrics.keypoint_pck_accuracy_device(m["pred"], m["gt"], m["mask"], 0.05, norm, return_distances=True)[3]
+        assert np.array_equal(d.cpu().numpy(), oc.metrics_oracle.calc_distances(m["pred"], m["gt"], m["mask"], norm))
+    with pytest.raises(ValueError):
+        metrics.pose_pck_accuracy(g["blob"], g["clean"], m["mask"], method="median")
+    a, t = metrics.get_binary_accuracy(torch.from_numpy(m["scalar_dt"]).cuda(), torch.from_numpy(m["scalar_gt"]).cuda(),
+                                       torch.from_numpy(m["mask"]).cuda())
+    assert a.item() == m["binary/acc"] and t.item() == m["binary/thr"]
+    mae = metrics.get_mae(torch.from_numpy(m["scalar_dt"]).cuda(), torch.from_numpy(m["scalar_gt"]).cuda(),
+                          torch.from_numpy(m["mask"]).cuda())
+    assert abs(mae.item() - float(m["mae"])) <= 1e-6 * float(m["mae"])
+    pa = metrics.get_pose_accuracy(torch.from_numpy(g["blob"]).cuda(), torch.from_numpy(g["clean"]).cuda(), m["mask"])
+    assert pa.is_cuda and abs(pa.item() - m["pose/0.05/avg"]) <= 1e-12
+
+
+def test_pck_metrics_wholebody_batch_against_oracle(pp):
+    """K = 133, N = 64: more keypoints than warps, more instances than lanes; random masks and factors."""
+    from probpose_pytorch_b200 import metrics
+    rng = np.random.default_rng(12)
+    N, K = 64, 133
+    pred = rng.uniform(0, 48, size=(N, K, 2)).astype(np.float32)
+    gt = (pred + rng.normal(0, 3.0, size=pred.shape)).astype(np.float32)
+    mask = rng.random((N, K)) < 0.7
+    for norm in (np.tile(np.array([[64, 48]]), (N, 1)), rng.uniform(-5, 60, size=(N, 2)), rng.uniform(1, 60, size=(N, 2)).astype(np.float32)):
+        for thr in (0.05, 0.5):
+            acc, avg, cnt = metrics.keypoint_pck_accuracy(pred, gt, mask, thr, norm)
+            acc_o, avg_o, cnt_o = oc.metrics_oracle.keypoint_pck_accuracy(pred, gt, mask, thr, norm)
+            assert np.array_equal(acc, acc_o) and cnt == cnt_o and abs(avg - avg_o) <= 1e-12
+    dt = rng.random((N, K)).astype(np.float32)
+    gb = (rng.random((N, K)) < 0.3).astype(np.float32)
+    a, t = metrics.get_binary_accuracy(dt, gb, mask)
+    a_o, t_o = oc.metrics_oracle.binary_accuracy(dt, gb, mask)
+    assert a.item() == a_o and t.item() == t_o

@@ -187,3 +187,22 @@ def test_sparsemax_oracle_is_the_simplex_projection():
     assert torch.autograd.gradcheck(oc.sparsemax, (z,), eps=1e-7, atol=1e-5)
     y = oc.head_tail_sparsemax(torch.from_numpy(rng.standard_normal((2, 3, 4, 5)).astype(np.float32)), 0.5, 2.0)
     assert y.shape == (2, 3, 4, 5) and float(y.max()) <= 1.0 and float(y.min()) >= 0.0
+
+
+def test_metrics_oracle_matches_reference_outputs(golden_dir):
+    """PCK / binary accuracy / MAE restatements against the reference's outputs (tests/golden/metrics.npz)."""
+    mo = oc.metrics_oracle
+    m = np.load(golden_dir / "metrics.npz")
+    g = np.load(golden_dir / "decode.npz")
+    for thr in (0.05, 0.2):
+        acc, avg, cnt = mo.pose_pck_accuracy(g["blob"], g["clean"], m["mask"], thr=thr)
+        assert np.array_equal(acc, m[f"pose/{thr}/acc"]) and avg == m[f"pose/{thr}/avg"] and cnt == m[f"pose/{thr}/cnt"]
+    acc, avg, cnt = mo.pose_pck_accuracy(g["blob"], g["clean"], m["mask"], thr=0.1, normalize=m["norm64"])
+    assert np.array_equal(acc, m["pose/norm64/acc"]) and avg == m["pose/norm64/avg"] and cnt == m["pose/norm64/cnt"]
+    acc, avg, cnt = mo.keypoint_pck_accuracy(m["pred"], m["gt"], m["mask"], 0.05, m["norm32"])
+    assert np.array_equal(acc, m["kpt/acc"]) and avg == m["kpt/avg"] and cnt == m["kpt/cnt"]
+    acc, avg, cnt = mo.keypoint_pck_accuracy(m["pred"], m["gt"], np.zeros_like(m["mask"]), 0.05, m["norm32"])
+    assert np.array_equal(acc, m["kpt_none/acc"]) and avg == 0.0 and cnt == 0
+    a, t = mo.binary_accuracy(m["scalar_dt"], m["scalar_gt"], m["mask"])
+    assert a == m["binary/acc"] and t == m["binary/thr"]
+    assert mo.masked_mae(m["scalar_dt"], m["scalar_gt"], m["mask"]) == m["mae"]
