@@ -979,3 +979,35 @@ def test_pck_metrics_wholebody_batch_against_oracle(pp):
     a, t = metrics.get_binary_accuracy(dt, gb, mask)
     a_o, t_o = oc.metrics_oracle.binary_accuracy(dt, gb, mask)
     assert a.item() == a_o and t.item() == t_o
+
+
+@pytest.mark.parametrize("name,freeze,kwargs", [("frozen", True, {}), ("live", False, {}),
+                                                ("zeros", False, dict(learn_heatmaps_from_zeros=True)),
+                                                ("weights", True, dict(keypoint_weights=True))])
+def test_probpose_loss_matches_reference_forward_and_backward(pp, golden_dir, name, freeze, kwargs):
+    """The training-step caller: ProbPoseLoss.forward(gt dict, 5-tuple) -> five losses (+ five accuracies) and the
+    gradients of their sum, against the reference's own run (tests/golden/probpose_loss.npz)."""
+    g = np.load(golden_dir / "probpose_loss.npz")
+    wl = synth.WORKLOADS[3]
+    mod = pp.ProbPoseLoss(pp.Codec(pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)), freeze_error=freeze)
+    gt = {k.split("/", 1)[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith("gt/")}     # host tensors, as a DataLoader yields
+    pred = [torch.from_numpy(g[k]).cuda().requires_grad_(True) for k in ("dt_heatmaps", "dt_probs", "dt_vis", "dt_oks", "dt_errs")]
+    if kwargs.get("keypoint_weights"):
+        kwargs = dict(keypoint_weights=torch.from_numpy(g["keypoint_weights"]).cuda())
+    np.random.seed(99)
+    losses, acc = mod(gt, tuple(pred), compute_acc=True, **kwargs)
+    sum(losses.values()).backward()
+    for k, v in losses.items():
+        want = float(g[f"{name}/loss/{k}"])
+        assert abs(v.item() - want) <= RTOL32 * abs(want) + 1e-8, (k, v.item(), want)
+    for k, v in acc.items():
+        want = float(g[f"{name}/acc/{k}"])
+        assert abs(float(v) - want) <= 1e-5 * abs(want) + 1e-8, (k, float(v), want)
+    for n, p_ in zip(("heatmaps", "probs", "vis", "oks", "errs"), pred):
+        want = g[f"{name}/grad/{n}"]
+        if n == "heatmaps":
+            _close(p_.grad.cpu().numpy(), want, RTOL32)
+        else:   # the OKS / error targets come out of a DARK decode (1e-6 apart): 1e-5 of the gradient's scale
+            np.testing.assert_allclose(p_.grad.cpu().numpy(), want, rtol=RTOL32, atol=RTOL32 * np.abs(want).max())
+    # without accuracies the call returns the dictionary alone
+    assert set(mod(gt, tuple(p_.detach() for p_ in pred))) == {"kpt", "probability", "visibility", "oks", "error"}
