@@ -9,7 +9,10 @@ changes is where the work happens:
 * OKS / error targets (``_oks_from_heatmaps`` / ``_error_from_heatmaps``, loss.py:512-640): two DARK
   decodes + a (B, K) kernel on the device instead of a device->host copy of both heatmap stacks and
   2 B per-sample NumPy / OpenCV decodes per step (``pose_targets``);
-* accuracy read-outs (``compute_acc=True``, loss.py:463-508): ``metrics`` kernels.
+* accuracy read-outs (``compute_acc=True``, loss.py:463-508): ``metrics`` kernels;
+* the ground-truth dict (dataset.py:130-135) may carry ``keypoints`` (B, K, 2) instead of ``heatmaps``: the
+  targets are then encoded on the device (``encode_batch``), so the DataLoader workers no longer encode and the
+  per-step host->device copy of the (B, K, H, W) target stack (loss.py:376) disappears.
 
 The four scalar heads' losses (BCE / MSE / smooth-L1-of-logs on (B, K) values, loss.py:194-339) are a few
 torch element-wise calls on 4 K numbers: plumbing, kept in torch on the device.
@@ -125,6 +128,13 @@ class ProbPoseLoss(nn.Module):
         def dev(x, dtype):
             return torch.as_tensor(x).to(device, dtype=dtype)
 
+        if "heatmaps" not in gt:
+            # keypoint front end: the loader ships (B, K, 2) input-space keypoints and the
+            # target planes are encoded here, on the device -- B*K*3 numbers cross PCIe instead of B*K*H*W
+            enc = self.codec.probmap.encode_batch(torch.as_tensor(gt["keypoints"]).reshape(B, C, -1),
+                                                  torch.as_tensor(gt["keypoints_visible"]).reshape(B, C).to(torch.float32),
+                                                  dtype=dt_heatmaps.dtype, device=device)
+            gt = dict(gt, heatmaps=enc["heatmaps"], in_image=gt.get("in_image", enc["in_image"]))
         gt_heatmaps = dev(gt["heatmaps"], dt_heatmaps.dtype).view((B, C, H, W))
         gt_probs = dev(gt["in_image"], torch.int64).view((B, C))
         gt_annotated = dev(gt["keypoints_visible"], torch.int64).view((B, C))

@@ -465,7 +465,7 @@ def test_loss_bf16(pp):
     l = mod.forward_mean(o, tgt.cuda(), tw.cuda())
     l.backward()
     assert o.grad.dtype == torch.bfloat16
-    assert abs(float(l) - float(l_ref)) <= RTOL16 * abs(float(l_ref))
+    assert abs(l.item() - l_ref.item()) <= RTOL16 * abs(l_ref.item())
     _close(o.grad.float().cpu().numpy(), o_ref.grad.numpy(), RTOL16)
 
 
@@ -1011,3 +1011,27 @@ def test_probpose_loss_matches_reference_forward_and_backward(pp, golden_dir, na
             np.testing.assert_allclose(p_.grad.cpu().numpy(), want, rtol=RTOL32, atol=RTOL32 * np.abs(want).max())
     # without accuracies the call returns the dictionary alone
     assert set(mod(gt, tuple(p_.detach() for p_ in pred))) == {"kpt", "probability", "visibility", "oks", "error"}
+
+
+def test_probpose_loss_keypoint_ground_truth_front_end(pp):
+    """A GT dict that carries keypoints instead of heatmaps (section 8 f-3) gives the same losses as the
+    reference-layout dict built by per-sample ``encode`` on the host."""
+    wl = synth.WORKLOADS[3]
+    B = 5
+    kps, vis, visibility = synth.make_keypoints(wl, batch=B, seed=21)
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    mod = pp.ProbPoseLoss(pp.Codec(am), freeze_error=False)
+    enc = [am.encode(kps[b:b + 1], vis[b:b + 1] > 0.5) for b in range(B)]
+    gt_ref = dict(heatmaps=torch.from_numpy(np.stack([e["heatmaps"] for e in enc])),
+                  in_image=torch.from_numpy(np.concatenate([e["in_image"] for e in enc])),
+                  keypoints_visible=torch.from_numpy(vis > 0.5), keypoints_visibility=torch.from_numpy(visibility > 0.5))
+    gt_kp = dict(keypoints=torch.from_numpy(kps), keypoints_visible=gt_ref["keypoints_visible"],
+                 keypoints_visibility=gt_ref["keypoints_visibility"])
+    jit = torch.from_numpy(synth.jitter_keypoints(wl, kps, seed=22)).cuda()
+    hm = (am.encode_batch(jit, None)["heatmaps"] * 0.7 + 0.002).clamp(0, 1)
+    torch.manual_seed(2)
+    heads = [torch.rand(B, 17, 1, 1, device="cuda") * 0.9 + 0.05 for _ in range(4)]
+    a = mod(gt_ref, (hm, *heads))
+    b = mod(gt_kp, (hm, *heads))
+    for k in a:
+        assert abs(a[k].item() - b[k].item()) <= 1e-6 * abs(a[k].item()) + 1e-9, k
