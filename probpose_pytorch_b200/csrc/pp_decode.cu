@@ -420,6 +420,7 @@ decode_expected_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict
 }
 
 #include "pp_decode_fast.cuh"
+#include "pp_decode_dense.cuh"
 
 // ---------------------------------------------------------------------------
 // generic exact path: full convolved map (return_heatmap=True, or maps too large for shared memory)
@@ -815,6 +816,37 @@ bool fast_geometry(const pp_decode_params& p, const void* heatmaps, int max_radi
   return ok;
 }
 
+// Shared-memory layout of the dense decoder; false when the shape / alignment rules it out.
+template <typename T>
+bool dense_geometry(const pp_decode_params& p, const void* heatmaps, DenseGeom* out, size_t* smem_bytes) {
+  DenseGeom geo{};
+  geo.plane_bytes = static_cast<unsigned>(sizeof(T) * static_cast<size_t>(p.H) * p.W);
+  geo.raw_stride = (geo.plane_bytes + 127) / 128 * 128;
+  geo.Wp = round_up(p.W, 8);
+  geo.Hp = round_up(p.H, 8);
+  geo.PS = conflict_free_stride(kDMargin + geo.Wp + kDMargin);
+  geo.QS = conflict_free_stride(geo.Wp);
+  geo.p_off = 2 * geo.raw_stride;
+  const size_t p_floats = static_cast<size_t>(geo.PS) * geo.Hp + 32;
+  geo.q_off = static_cast<unsigned>((geo.p_off + sizeof(float) * p_floats + 127) / 128 * 128);
+  geo.q_floats = static_cast<unsigned>(static_cast<size_t>(geo.QS) * (geo.Hp + 2 * kDMargin) + 32);
+  geo.w2d_off = static_cast<unsigned>((geo.q_off + sizeof(float) * geo.q_floats + 127) / 128 * 128);
+  geo.part_off = geo.w2d_off + 2u * static_cast<unsigned>(sizeof(double)) * PP_OKS_TAPS * PP_OKS_TAPS;
+  const size_t smem = geo.part_off + sizeof(double) * kDThreads;
+  geo.div_WV = div_magic(static_cast<unsigned>(std::max(1, p.W / Elem<T>::kVec)));
+  geo.div_W = div_magic(static_cast<unsigned>(p.W));
+  geo.div_H = div_magic(static_cast<unsigned>(p.H));
+  geo.div_Wp = div_magic(static_cast<unsigned>(geo.Wp));
+  geo.div_Wp4 = div_magic(static_cast<unsigned>(geo.Wp / 4));
+  const bool ok = geo.plane_bytes % 16 == 0 && pp_aligned16(heatmaps) && p.W % Elem<T>::kVec == 0 &&
+                  (!p.apply_tail || p.temperature > 0.0f) && 2 * (smem + 2048) <= static_cast<size_t>(pp_smem_optin()) &&
+                  p.W > PP_MAX_OKS_RADIUS + 1 && p.H > PP_MAX_OKS_RADIUS + 1 && static_cast<int64_t>(p.H) * p.W < (1 << 20) &&
+                  static_cast<int64_t>(p.B) * p.K < (1ll << 31);
+  *out = geo;
+  *smem_bytes = smem;
+  return ok;
+}
+
 template <typename T>
 int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, const void* heatmaps, float* locs,
                            float* vals, int32_t* argmax, double* keypoints, float* conv_out, void* scratch,
@@ -840,7 +872,24 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   const bool vec = (p.W % Elem<T>::kVec == 0) && pp_aligned16(heatmaps);
   const int threads = pick_threads(p.H, p.W);
 
-  // main kernel: TMA-staged plane, convolution pruned to the neighbourhood of {h >= L} when possible
+  // dense kernel (pp_decode_dense.cuh): the whole separable prefilter, specialised per radius; at least two CTAs
+  // per SM must fit, otherwise the pruned kernel below takes over
+  DenseGeom dgeo{};
+  size_t dsmem = 0;
+  if (pp_env_int("PP_DECODE_DENSE", 0) && dense_geometry<T>(p, heatmaps, &dgeo, &dsmem)) {
+    int dper = 1;
+    if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_dense_kernel<T>), kDThreads, dsmem, &dper))
+      return rc;
+    if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) dper = std::min(dper, cap);
+    const int dgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * dper));
+    unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;
+    if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+    decode_expected_dense_kernel<T><<<dgrid, kDThreads, dsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, dgeo, counter);
+    PP_CUDA_OK(cudaGetLastError());
+    return PP_OK;
+  }
+
+  // pruned kernel: TMA-staged plane, convolution pruned to the neighbourhood of {h >= L} when possible
   FastGeom geo{};
   size_t fsmem = 0;
   const bool fast = fast_geometry<T>(p, heatmaps, PP_MAX_OKS_RADIUS, &geo, &fsmem);

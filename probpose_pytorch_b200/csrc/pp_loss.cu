@@ -15,6 +15,7 @@
 
 #include "pp_common.cuh"
 #include "pp_loss_fast.cuh"
+#include "pp_loss_pair.cuh"
 
 namespace {
 
@@ -310,6 +311,20 @@ int launch_fast_tt(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cu
   return PP_OK;
 }
 
+template <bool kFwd, bool kGrad>
+int launch_pair_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
+  int per_sm = 1;
+  auto kern = pp_loss_pair::oks_loss_pair_kernel<kFwd, kGrad>;
+  if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), threads, smem, &per_sm)) return rc;
+  if (const int cap = env_int("PP_LOSS_CTAS", 0); cap > 0) per_sm = std::min(per_sm, cap);
+  const int64_t units = (a.N + a.G - 1) / a.G;
+  const int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  kern<<<grid, threads, smem, st>>>(a);
+  PP_CUDA_OK(cudaGetLastError());
+  *grid_out = grid;
+  return PP_OK;
+}
+
 template <typename T, bool kFwd, bool kGrad>
 int launch_fast_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
   if (a.tgt_off != 0) return launch_fast_tt<T, kFwd, kGrad, true>(a, threads, smem, st, grid_out);
@@ -348,6 +363,31 @@ int launch_fast(const pp_loss_params& p, const void* output, const void* target,
   else { a.a_o = 0.5f; a.a_t = 0.5f; a.d_a = 0.5f; a.d_b = -1.f; }
   a.inv_count = static_cast<float>(1.0 / (static_cast<double>(a.N) * p.H * p.W));
   a.plane_bytes = static_cast<unsigned>(static_cast<int64_t>(p.H) * p.W * e);
+  const bool g = grad != nullptr;
+
+  // float32: two heatmaps per thread with packed FADD2 / FMUL2 / FFMA2 arithmetic (pp_loss_pair.cuh), whenever a
+  // unit of 2 x pairs heatmaps (output + target) fits shared memory
+  if (p.dtype == PP_F32 && a.N >= 2 && per <= 256 && env_int("PP_LOSS_PAIR", 0)) {
+    pp_loss_fast::FastArgs b = a;
+    int pairs = std::max(1, std::min(2, env_int("PP_LOSS_G", (96 + per / 2) / per)));
+    while (pairs > 1 && per * pairs > 256) --pairs;
+    for (;; --pairs) {
+      b.G = 2 * pairs;
+      b.tgt_off = (16 + b.G * b.plane_bytes + 16 + 127) / 128 * 128;
+      b.stage_bytes = (b.tgt_off + b.G * b.plane_bytes + 127) / 128 * 128;
+      if (b.stage_bytes <= static_cast<size_t>(pp_smem_optin()) || pairs == 1) break;
+    }
+    if (b.stage_bytes <= static_cast<size_t>(pp_smem_optin())) {
+      b.stages = env_int("PP_LOSS_STAGES", 2);
+      if (static_cast<size_t>(b.stages) * b.stage_bytes > static_cast<size_t>(pp_smem_optin())) b.stages = 1;
+      const size_t smem = static_cast<size_t>(b.stages) * b.stage_bytes;
+      const int threads = per * pairs;
+      if (fwd && g) return launch_pair_t<true, true>(b, threads, smem, st, grid_out);
+      if (fwd) return launch_pair_t<true, false>(b, threads, smem, st, grid_out);
+      return launch_pair_t<false, true>(b, threads, smem, st, grid_out);
+    }
+  }
+
   for (;; --a.G) {
     a.tgt_off = (16 + a.G * a.plane_bytes + 16 + 127) / 128 * 128;
     a.stage_bytes = (a.tgt_off + a.G * a.plane_bytes + 127) / 128 * 128;
@@ -363,7 +403,6 @@ int launch_fast(const pp_loss_params& p, const void* output, const void* target,
   if (static_cast<size_t>(a.stages) * a.stage_bytes > static_cast<size_t>(pp_smem_optin())) a.stages = 1;
   const size_t smem = static_cast<size_t>(a.stages) * a.stage_bytes;
   const int threads = a.strips * a.segs * a.G;
-  const bool g = grad != nullptr;
   if (p.dtype == PP_F32) {
     if (fwd && g) return launch_fast_t<float, true, true>(a, threads, smem, st, grid_out);
     if (fwd) return launch_fast_t<float, true, false>(a, threads, smem, st, grid_out);

@@ -1035,3 +1035,62 @@ def test_probpose_loss_keypoint_ground_truth_front_end(pp):
     b = mod(gt_kp, (hm, *heads))
     for k in a:
         assert abs(a[k].item() - b[k].item()) <= 1e-6 * abs(a[k].item()) + 1e-9, k
+
+
+# ---- kernel variants that are off by default (kept with their measurements in DESIGN.md / profiles) -----------
+def test_dense_decoder_variant_matches_golden_and_default(pp, golden_dir, monkeypatch):
+    """PP_DECODE_DENSE=1 selects the unpruned, per-radius specialised expected-OKS kernel (pp_decode_dense.cuh):
+    same bit-exact argmax / values and the same coordinates as the reference and as the default kernel."""
+    g = np.load(golden_dir / "decode.npz")
+    wl = synth.WORKLOADS[3]
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    maps = {n: torch.from_numpy(g[n]).cuda() for n in ("blob", "uniform", "clean")}
+    const = torch.zeros(2, 17, 64, 48, device="cuda")
+    const[1] = 0.25
+    plateau = torch.zeros(1, 17, 64, 48, device="cuda")
+    plateau[:, :, 20:40, 10:30] = 0.5                              # thousands of tied candidates -> overflow walk
+    ref = {n: pm.decode_device(m) for n, m in {**maps, "const": const, "plateau": plateau}.items()}
+    monkeypatch.setenv("PP_DECODE_DENSE", "1")
+    for n, m in {**maps, "const": const, "plateau": plateau}.items():
+        out = pm.decode_device(m)
+        assert torch.equal(out["argmax"], ref[n]["argmax"]), n
+        assert torch.equal(out["vals"], ref[n]["vals"]), n
+        assert torch.equal(out["locs"], ref[n]["locs"]), n
+        if n in maps:
+            assert np.array_equal(out["vals"].cpu().numpy(), g[f"{n}_vals"])
+            np.testing.assert_allclose(out["locs"].cpu().numpy(), g[f"{n}_locs"], rtol=RTOL32, atol=1e-5)
+    # fused head tail and bf16 through the same variant
+    x = (maps["blob"] * 0.5)
+    a = pm.decode_device(x, temperature=0.5)
+    monkeypatch.setenv("PP_DECODE_DENSE", "0")
+    b = pm.decode_device(x, temperature=0.5)
+    assert torch.equal(a["argmax"], b["argmax"]) and torch.equal(a["locs"], b["locs"])
+    monkeypatch.setenv("PP_DECODE_DENSE", "1")
+    xb = maps["blob"].bfloat16()
+    a = pm.decode_device(xb)
+    monkeypatch.setenv("PP_DECODE_DENSE", "0")
+    b = pm.decode_device(xb)
+    assert torch.equal(a["argmax"], b["argmax"]) and torch.equal(a["locs"], b["locs"])
+
+
+def test_paired_loss_variant_matches_default(pp, monkeypatch):
+    """PP_LOSS_PAIR=1 selects the two-heatmaps-per-thread FADD2 / FFMA2 loss kernel (pp_loss_pair.cuh); odd and even
+    heatmap counts, with and without the MSE term."""
+    torch.manual_seed(8)
+    for B, K in ((3, 5), (2, 4), (1, 1)):
+        out, tgt = torch.rand(B, K, 64, 48), torch.rand(B, K, 64, 48)
+        tw = (torch.rand(B, K) < 0.7).float()
+        for kw in (dict(smoothing_weight=0.05, oks_type="minus"), dict(smoothing_weight=0.2, gaussian_weight=0.15, oks_type="both")):
+            res = []
+            for flag in ("0", "1"):
+                monkeypatch.setenv("PP_LOSS_PAIR", flag)
+                o = out.cuda().requires_grad_(True)
+                l = pp.OKSHeatmapLoss(use_target_weight=True, **kw).forward_mean(o, tgt.cuda(), tw.cuda())
+                l.backward()
+                res.append((l.item(), o.grad.cpu().numpy()))
+            o_ref = out.clone().requires_grad_(True)
+            l_ref = oc.oks_heatmap_loss(o_ref, tgt, tw, per_pixel=True, **kw).mean()
+            l_ref.backward()
+            for l, gr in res:
+                assert abs(l - l_ref.item()) <= RTOL32 * abs(l_ref.item()) + 1e-9
+                _close(gr, o_ref.grad.numpy(), RTOL32)
