@@ -96,3 +96,22 @@ def test_host_tables_match_oracle():
             ker = np.exp(-(dist ** 2) / (2 * s[k]))
             assert np.array_equal(ker / ker.sum(), ref[k])
     assert np.array_equal(_tables.gaussian_taps(11), oc.gaussian_taps_f32(11))
+
+
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a C program links against the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = Path(__file__).resolve().parents[1]
+    so = root / "probpose_pytorch_b200" / "csrc" / "libprobpose_b200.so"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c",
+                    str(root / "include" / "probpose_b200.h")], check=True)
+    exe = tmp_path / "cabi_smoke"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-I", str(root / "include"), str(root / "tests" / "c" / "cabi_smoke.c"),
+                    "-o", str(exe), str(so), f"-Wl,-rpath,{so.parent}"], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "sizeof encode/decode/loss params: 44 48 72" in res.stdout
