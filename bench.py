@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--sample", type=int, default=0, help="reference arm: images per step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--exchange-every", type=int, default=0,
+                    help="multi-GPU: steps per all-gather bucket (0 = number of buffer sets; 1 = one collective per step)")
     ap.add_argument("--serial", action="store_true", help="run decode after encode on one stream (no fork/join)")
     return ap.parse_args()
 
@@ -298,17 +300,28 @@ def run_product(args):
         else:
             rec, loss, _ = step_device(sets[j])
         if world > 1:
-            # the only exchange on the path: keypoint records + loss partial in ONE all-gather, issued
-            # asynchronously so that it overlaps the next step's kernels (bounded number in flight)
-            pending.append(ppd.exchange_step_results(rec, loss, async_op=True))
-            if len(pending) > 4:
-                pending.popleft().wait()
+            # the only exchange on the path: keypoint records + loss partials.  It is latency bound, so the results
+            # of `--exchange-every` consecutive steps (<= the number of rotating buffer sets, whose outputs are
+            # still intact) travel in ONE all-gather, issued asynchronously so that it overlaps the next steps'
+            # kernels (bounded number in flight).
+            bucket.append((rec, loss))
+            if len(bucket) == exchange_every:
+                pending.append(ppd.exchange_bucket([b[0] for b in bucket], [b[1] for b in bucket], async_op=True))
+                bucket.clear()
+                if len(pending) > 2:
+                    pending.popleft().wait()
         return rec, loss
 
     import collections
     pending = collections.deque()
 
+    bucket = []
+    exchange_every = max(1, min(args.exchange_every or len(sets), len(sets)))
+
     def drain():
+        if bucket:      # a partial bucket at the end of a run still travels
+            pending.append(ppd.exchange_bucket([b[0] for b in bucket], [b[1] for b in bucket], async_op=True))
+            bucket.clear()
         while pending:
             pending.popleft().wait()
 
@@ -526,7 +539,8 @@ def run_product(args):
                        "l2": f"rotating {args.sets} buffer sets x {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
                        "launch": ("CUDA graph replay" if use_graph else "eager")
                                  + (", one stream" if args.serial else ", decode on a second stream beside encode->loss"),
-                       "parallelism": f"dp{world} (batch sharded by image)"},
+                       "parallelism": f"dp{world} (batch sharded by image)"
+                                      + ("" if world == 1 else f"; records + loss of {exchange_every} step(s) per asynchronous all-gather")},
             "roofline": roofline, "kernels": kernels, "e2e": e2e, "cpu_baseline": cpu_baseline,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }

@@ -41,6 +41,13 @@ def _worker(rank, world, port, B, ragged):
             ex = ppd.exchange_step_results(mine.clone(), per_image_loss[lo:hi].mean(), async_op=True)   # overlapped form
             assert torch.equal(ex.wait().records, records)
             assert abs(float(ex.loss) - float(per_image_loss.mean())) < 1e-6
+            # bucketed: three steps in one collective
+            steps = [records * (i + 1) for i in range(3)]
+            bx = ppd.exchange_bucket([ppd.shard_batch(t).clone() for t in steps],
+                                     [per_image_loss[lo:hi].mean() * (i + 1) for i in range(3)], async_op=True)
+            rec3, loss3 = bx
+            assert rec3.shape == (3,) + tuple(records.shape) and torch.equal(rec3, torch.stack(steps))
+            assert torch.allclose(loss3, per_image_loss.mean() * torch.tensor([1.0, 2.0, 3.0]), atol=1e-6)
     finally:
         dist.destroy_process_group()
 
