@@ -78,6 +78,9 @@ int pp_configure_kernel(const void* kernel, int threads, size_t smem, int* ctas_
   PP_REQUIRE(static_cast<int64_t>(smem) <= dyn_max, PP_ERR_UNSUPPORTED_SHAPE,
              "kernel needs %zu bytes of dynamic shared memory, only %lld available", smem, static_cast<long long>(dyn_max));
   PP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn_max)));
+  // ask for the largest shared-memory carve-out: the occupancy computed below assumes it, the driver's default
+  // heuristic may pick a smaller one (capture Q: 4 resident CTAs where 6 fit)
+  PP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
   PP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
   PP_REQUIRE(per_sm >= 1, PP_ERR_UNSUPPORTED_SHAPE, "kernel does not fit on an SM (threads=%d, smem=%zu)", threads, smem);

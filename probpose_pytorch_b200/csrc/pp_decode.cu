@@ -24,6 +24,7 @@
 //   (4) picks the maximum of the exact float32 values with the lowest flat index on ties (NumPy
 //       argmax), and evaluates the four neighbours exactly for the sub-pixel fit.
 #include <algorithm>
+#include <cstdio>
 
 #include "pp_common.cuh"
 
@@ -421,6 +422,7 @@ decode_expected_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict
 
 #include "pp_decode_fast.cuh"
 #include "pp_decode_dense.cuh"
+#include "pp_decode_warp.cuh"
 
 // ---------------------------------------------------------------------------
 // generic exact path: full convolved map (return_heatmap=True, or maps too large for shared memory)
@@ -816,6 +818,27 @@ bool fast_geometry(const pp_decode_params& p, const void* heatmaps, int max_radi
   return ok;
 }
 
+// Shared-memory slot of the warp-per-heatmap decoder (pp_decode_warp.cuh); false when the shape rules it out.
+template <typename T>
+bool warp_geometry(const pp_decode_params& p, const void* heatmaps, WarpGeom* out) {
+  WarpGeom geo{};
+  geo.plane_bytes = static_cast<unsigned>(sizeof(T) * static_cast<size_t>(p.H) * p.W);
+  geo.tmp_off = (geo.plane_bytes + 127) / 128 * 128;
+  geo.taps_off = geo.tmp_off + static_cast<unsigned>(sizeof(wf2)) * kWTmpPairs;
+  geo.cand_off = geo.taps_off + 2u * static_cast<unsigned>(sizeof(wf2)) * kWTaps;
+  geo.exch_off = (geo.cand_off + static_cast<unsigned>(sizeof(int)) * (2 * kWCand + 4) + 15) / 16 * 16;
+  geo.slot_bytes = (geo.exch_off + static_cast<unsigned>(sizeof(TeamExchange)) + 127) / 128 * 128;
+  constexpr int kMinSide = 2 * PP_MAX_OKS_RADIUS + 6;   // single reflections only, with the 4-row task overhang
+  const bool ok = geo.plane_bytes % 16 == 0 && pp_aligned16(heatmaps) && p.W % Elem<T>::kVec == 0 &&
+                  (!p.apply_tail || p.temperature > 0.0f) && p.W >= kMinSide && p.H >= kMinSide &&
+                  2 * (round_up(p.W, 8) + kWTaps + 2) <= kWTmpPairs &&   // a band holds at least two row pairs
+                  static_cast<int64_t>(p.H) * p.W < (1 << 20) && static_cast<int64_t>(p.B) * p.K < (1ll << 31);
+  geo.div_WV = div_magic(static_cast<unsigned>(std::max(1, p.W / Elem<T>::kVec)));
+  geo.div_W = div_magic(static_cast<unsigned>(p.W));
+  *out = geo;
+  return ok;
+}
+
 // Shared-memory layout of the dense decoder; false when the shape / alignment rules it out.
 template <typename T>
 bool dense_geometry(const pp_decode_params& p, const void* heatmaps, DenseGeom* out, size_t* smem_bytes) {
@@ -871,6 +894,40 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   }
   const bool vec = (p.W % Elem<T>::kVec == 0) && pp_aligned16(heatmaps);
   const int threads = pick_threads(p.H, p.W);
+
+  // team-per-heatmap kernel (pp_decode_warp.cuh): G warps own a heatmap from its bulk copy to its outputs.  With
+  // G = 1 (default) it has the best throughput (7.6 ns per heatmap on the mixed C2 inputs against 13.4 ns for the
+  // CTA-per-heatmap kernel below) but the longest single-heatmap latency, so it takes over once every team has at
+  // least two heatmaps to work on; smaller batches stay with the CTA-per-heatmap kernel (measured cross-over between
+  // 2176 and 4352 heatmaps of 64x48, profiles/r01s_summary.md).  PP_DECODE_WARP=0 / 1 forces the choice,
+  // PP_DECODE_TEAM selects G (1 or 2).
+  WarpGeom wgeo{};
+  const int want_warp = pp_env_int("PP_DECODE_WARP", -1);
+  if (want_warp != 0 && !pp_env_int("PP_DECODE_DENSE", 0) && warp_geometry<T>(p, heatmaps, &wgeo)) {
+    constexpr int kTPC = 2;
+    const int G = pp_env_int("PP_DECODE_TEAM", 1);
+    const void* fn = G == 1 ? reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 1, kTPC>)
+                            : reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 2, kTPC>);
+    const int threads = 32 * (G == 1 ? 1 : 2) * kTPC;
+    wgeo.rowoff_off = static_cast<unsigned>(kTPC) * wgeo.slot_bytes;
+    const size_t wsmem = wgeo.rowoff_off + sizeof(int) * static_cast<size_t>(p.H + 2 * kWRowPad);
+    int wper = 0;
+    if (wsmem + 2048 <= static_cast<size_t>(pp_smem_optin()) && pp_configure_kernel(fn, threads, wsmem, &wper) == PP_OK &&
+        wper * kTPC >= 6 && (want_warp == 1 || N >= 2ll * pp_sm_count() * wper * kTPC)) {
+      if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) wper = std::min(wper, cap);
+      const int wgrid = static_cast<int>(std::min<int64_t>((N + kTPC - 1) / kTPC, static_cast<int64_t>(pp_sm_count()) * wper));
+      unsigned* counter = (scratch && scratch_bytes >= 4) ? static_cast<unsigned*>(scratch) : nullptr;
+      if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+      if (pp_env_int("PP_DEBUG", 0))
+        fprintf(stderr, "[pp] decode_expected_warp_kernel G=%d grid=%d threads=%d smem=%zu ctas/sm=%d\n", G, wgrid, threads, wsmem, wper);
+      if (G == 1)
+        decode_expected_warp_kernel<T, 1, kTPC><<<wgrid, threads, wsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, wgeo, counter);
+      else
+        decode_expected_warp_kernel<T, 2, kTPC><<<wgrid, threads, wsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, wgeo, counter);
+      PP_CUDA_OK(cudaGetLastError());
+      return PP_OK;
+    }
+  }
 
   // dense kernel (pp_decode_dense.cuh): the whole separable prefilter, specialised per radius; at least two CTAs
   // per SM must fit, otherwise the pruned kernel below takes over

@@ -29,6 +29,21 @@ def pp():
     return mod
 
 
+
+@pytest.fixture(params=["auto", "team1", "team2", "cta"])
+def expected_kernel(request, monkeypatch):
+    """Which kernel runs the expected-OKS decode: the library's size rule ("auto": small batches such as the ones in
+    these tests take the CTA-per-heatmap kernel), the team-per-heatmap kernel (pp_decode_warp.cuh) with one or two
+    warps per heatmap, or the CTA-per-heatmap kernel (pp_decode_fast.cuh) forced."""
+    mode = request.param
+    if mode == "cta":
+        monkeypatch.setenv("PP_DECODE_WARP", "0")
+    elif mode != "auto":
+        monkeypatch.setenv("PP_DECODE_WARP", "1")
+        monkeypatch.setenv("PP_DECODE_TEAM", mode[-1])
+    return mode
+
+
 def _oracle_encode(kind, wl, kps, vis, sigma=None):
     outs = [oc.encode(kind, wl.input_size, wl.heatmap_size, wl.sigmas, kps[b:b + 1], vis[b:b + 1], sigma=sigma)
             for b in range(kps.shape[0])]
@@ -149,7 +164,7 @@ def test_heatmap_maximum_exact(pp):
 
 # --------------------------------------------------------------------------- expected-OKS decoder
 @pytest.mark.parametrize("name", ["blob", "uniform", "clean"])
-def test_expected_decoder_matches_golden_reference(pp, golden_dir, name):
+def test_expected_decoder_matches_golden_reference(pp, golden_dir, name, expected_kernel):
     g = np.load(golden_dir / "decode.npz")
     wl = synth.WORKLOADS[3]
     arr = g[name]
@@ -177,7 +192,7 @@ def test_expected_decoder_matches_golden_reference(pp, golden_dir, name):
 
 
 @pytest.mark.parametrize("cid,batch", [(2, 6), (4, 3), (5, 1)])
-def test_expected_decoder_argmax_exact_vs_oracle(pp, cid, batch):
+def test_expected_decoder_argmax_exact_vs_oracle(pp, cid, batch, expected_kernel):
     wl = synth.WORKLOADS[cid]
     kps, vis, _ = synth.make_keypoints(wl, batch=batch, seed=200 + cid)
     tgt = _oracle_encode("argmax", wl, synth.jitter_keypoints(wl, kps, 201), vis)["heatmaps"]
@@ -193,7 +208,7 @@ def test_expected_decoder_argmax_exact_vs_oracle(pp, cid, batch):
         assert np.array_equal(dev["vals"][b].cpu().numpy(), vals)
 
 
-def test_expected_decoder_ties_plateaus_and_constants(pp):
+def test_expected_decoder_ties_plateaus_and_constants(pp, expected_kernel):
     """On-grid / half-grid targets (exact ties), saturated plateaus, all-zero and constant maps."""
     wl = synth.WORKLOADS[1]
     K, (W, H) = wl.num_keypoints, wl.heatmap_size
@@ -206,6 +221,8 @@ def test_expected_decoder_ties_plateaus_and_constants(pp):
     maps[2, 0] = 0.0                               # all-zero channel -> (0, 0), no -1 sentinel (B-5)
     maps[2, 1] = 0.25                              # constant channel
     maps[3] = np.round(maps[3] * 4) / 4            # heavy quantisation -> many exact ties
+    maps[0, 2] = 0.0
+    maps[0, 2, 20:40, 10:30] = 0.5               # a plateau wider than the kernel: hundreds of exactly tied maxima
     pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
     dev = pm.decode_device(torch.from_numpy(maps).cuda())
     for b in range(4):
@@ -238,7 +255,7 @@ def test_expected_decoder_reference_test_shape_and_generic_path(pp):
     assert np.array_equal(v, v_ref)
 
 
-def test_decoder_fused_head_tail(pp):
+def test_decoder_fused_head_tail(pp, expected_kernel):
     wl = synth.WORKLOADS[2]
     rng = np.random.default_rng(41)
     logits = rng.normal(0.1, 0.3, size=(4, 17, 64, 48)).astype(np.float32)
@@ -469,7 +486,7 @@ def test_loss_bf16(pp):
     _close(o.grad.float().cpu().numpy(), o_ref.grad.numpy(), RTOL16)
 
 
-def test_decoders_bf16(pp):
+def test_decoders_bf16(pp, expected_kernel):
     wl = synth.WORKLOADS[3]
     kps, vis, _ = synth.make_keypoints(wl, batch=3, seed=55)
     maps = _oracle_encode("argmax", wl, kps, vis)["heatmaps"]
@@ -671,7 +688,7 @@ def _sweep_maps(rng, K, H, W):
 
 
 @pytest.mark.parametrize("H,W", [(12, 12), (16, 20), (24, 20), (33, 28), (40, 36), (64, 48), (80, 64), (96, 72), (128, 96)])
-def test_decoders_shape_sweep(pp, H, W):
+def test_decoders_shape_sweep(pp, H, W, expected_kernel):
     rng = np.random.default_rng(H * 1000 + W)
     K = 14
     sigmas = rng.uniform(0.02, 0.12, size=K)          # radii 2 .. 9

@@ -15,6 +15,8 @@ jit = torch.from_numpy(synth.jitter_keypoints(wl, kps, seed=5000)).to(dev)
 blob = am.encode_batch(jit, torch.from_numpy(vis).to(dev))["heatmaps"]
 amp = torch.from_numpy(synth.blob_params((B, K), seed=6000)).to(dev)
 pred = (blob * amp[:, :, None, None] + torch.rand_like(blob) * 0.02).clamp_(0, 1).contiguous()
+if os.environ.get("PP_PROBE_NOISE"):   # flat / noisy maps only: the dense regime of the decoders
+    pred = (torch.rand_like(blob) * 0.02).contiguous()
 for _ in range(3):
     out = pm.decode_device(pred)
     if os.environ.get("PP_PROBE_DARK"):
