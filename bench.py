@@ -435,15 +435,28 @@ def run_product(args):
     kernels = {k: {"ms": 1e3 * t, "GBps": alg[k] * n_hm * hm_bytes / t / 1e9,
                    "frac": alg[k] * n_hm * hm_bytes / t / 1e9 / peak,
                    "heatmaps_per_s": n_hm / t} for k, t in kt.items()}
-    dom = "loss_fwd_bwd"
+    # the dominant kernel = the one of the three step kernels with the largest share of the step's device time
+    step_kernels = ("encode", "decode_expected", "loss_fwd_bwd")
+    dom = max(step_kernels, key=lambda k: kt[k])
+    decode_kernel = {0: "conv_exact_kernel + argmax_from_conv_kernel", 1: "decode_expected_fast_kernel (one CTA per heatmap)",
+                     2: "decode_expected_warp_kernel (one warp per heatmap)", 3: "decode_expected_dense_kernel",
+                     4: "decode_expected_kernel (generic)"}.get(_lib.lib().pp_decode_expected_last_kernel(), "?")
+    names = {"encode": "encode_kernel (OKS target encode, separable fp64 factors)",
+             "decode_expected": decode_kernel + ": expected-OKS decode, TMA-staged plane, pruned separable prefilter + exact fp64 "
+                                                "re-evaluation; bounded by per-heatmap instruction latency, not by HBM",
+             "loss_fwd_bwd": "oks_loss_fast_kernel (fused OKS loss forward+backward, TMA-staged)"}
     traffic = None
     tfile = ROOT / "profiles" / "traffic.json"
     if tfile.exists():
         traffic = json.loads(tfile.read_text()).get(f"{dom}/C{args.config}/{args.dtype}")
-    roofline = {"bound": "hbm", "kernel": "oks_loss_fast_kernel (fused OKS loss forward+backward, TMA-staged)",
+    serial = sum(kt[k] for k in step_kernels)
+    roofline = {"bound": "hbm", "kernel": names[dom],
                 "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
                 "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": 3 * n_hm * hm_bytes,
+                "algorithmic_bytes_per_launch": alg[dom] * n_hm * hm_bytes,
+                "share_of_step": {k: kt[k] / serial for k in step_kernels},
+                "other_step_kernels": {k: {"kernel": names[k], "achieved": kernels[k]["GBps"], "frac": kernels[k]["frac"]}
+                                       for k in step_kernels if k != dom},
                 "step": {"GBps": 5 * n_hm * hm_bytes * args.steps / (ms * 1e-3) / 1e9,
                          "frac": 5 * n_hm * hm_bytes * args.steps / (ms * 1e-3) / 1e9 / peak,
                          "note": "whole step, 5 x H x W x e bytes per heatmap"}}

@@ -116,6 +116,16 @@ PP_API int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* tab
                        void* scratch, int64_t scratch_bytes,
                        pp_stream_t stream);
 
+/* Which kernel this thread's most recent pp_decode_expected launched (-1 before the first call).  The choice
+ * depends on shape, alignment and batch size (heatmap.py:291-395 has a single code path; this is for benchmarks
+ * and profiles, which must name the kernel they time). */
+#define PP_DECODE_KERNEL_EXACT 0    /* full-map double-precision convolution (return_heatmap / maps beyond shared memory) */
+#define PP_DECODE_KERNEL_CTA 1      /* one CTA per heatmap, pruned prefilter (pp_decode_fast.cuh) */
+#define PP_DECODE_KERNEL_TEAM 2     /* one warp (team) per heatmap, band-wise prefilter (pp_decode_warp.cuh) */
+#define PP_DECODE_KERNEL_DENSE 3    /* unpruned per-radius variant, PP_DECODE_DENSE=1 (pp_decode_dense.cuh) */
+#define PP_DECODE_KERNEL_GENERIC 4  /* unaligned / odd shapes */
+PP_API int pp_decode_expected_last_kernel(void);
+
 /* Number of floats of `conv_out` work space pp_decode_expected needs for this shape even when the
  * caller does not want the convolved maps (maps too large for the shared-memory kernel); 0 otherwise. */
 PP_API int64_t pp_decode_expected_workspace_floats(const pp_decode_params* p);

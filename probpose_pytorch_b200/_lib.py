@@ -23,7 +23,7 @@ PP_UPSTREAM_SCALAR, PP_UPSTREAM_FULL = 0, 1
 #: every symbol include/probpose_b200.h declares
 EXPORTS = (
     "pp_version", "pp_last_error_string", "pp_device_info", "pp_encode", "pp_decode_expected",
-    "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes",
+    "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes", "pp_decode_expected_last_kernel",
     "pp_heatmap_maximum", "pp_decode_argmax_dark", "pp_heatmap_tail", "pp_heatmap_tail_backward",
     "pp_sparsemax_tail", "pp_sparsemax_tail_backward",
     "pp_oks_loss_scratch_bytes",
@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
     L.pp_device_info.argtypes = [vp, vp, vp, vp]
     L.pp_encode.argtypes = [C.POINTER(EncodeParams), vp, vp, vp, vp, vp, vp, vp, vp]
     L.pp_decode_expected.argtypes = [C.POINTER(DecodeParams), C.POINTER(OksTable), vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.pp_decode_expected_last_kernel.argtypes = []
+    L.pp_decode_expected_last_kernel.restype = C.c_int
     L.pp_decode_expected_scratch_bytes.argtypes = []
     L.pp_decode_expected_scratch_bytes.restype = i64
     L.pp_decode_expected_workspace_floats.argtypes = [C.POINTER(DecodeParams)]

@@ -870,6 +870,8 @@ bool dense_geometry(const pp_decode_params& p, const void* heatmaps, DenseGeom* 
   return ok;
 }
 
+thread_local int g_last_expected_kernel = -1;   // PP_DECODE_KERNEL_* of this thread's most recent pp_decode_expected
+
 template <typename T>
 int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, const void* heatmaps, float* locs,
                            float* vals, int32_t* argmax, double* keypoints, float* conv_out, void* scratch,
@@ -880,6 +882,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   const size_t smem = sizeof(float) * (static_cast<size_t>(g.raw_floats) + g.tmp_floats + g.out_floats);
   const bool fits = smem <= static_cast<size_t>(pp_smem_optin());
   if (conv_out != nullptr || !fits) {
+    g_last_expected_kernel = PP_DECODE_KERNEL_EXACT;
     // exact full-map path; needs a convolved-map buffer
     PP_REQUIRE(conv_out != nullptr, PP_ERR_SCRATCH,
                "pp_decode_expected: %dx%d maps do not fit in shared memory; pass conv_out as work space", p.H, p.W);
@@ -910,6 +913,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
                             : reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 2, kTPC>);
     const int threads = 32 * (G == 1 ? 1 : 2) * kTPC;
     wgeo.rowoff_off = static_cast<unsigned>(kTPC) * wgeo.slot_bytes;
+    wgeo.full_taps = pp_env_int("PP_DECODE_FULLTAPS", 0) ? 1u : 0u;
     const size_t wsmem = wgeo.rowoff_off + sizeof(int) * static_cast<size_t>(p.H + 2 * kWRowPad);
     int wper = 0;
     if (wsmem + 2048 <= static_cast<size_t>(pp_smem_optin()) && pp_configure_kernel(fn, threads, wsmem, &wper) == PP_OK &&
@@ -920,6 +924,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
       if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
       if (pp_env_int("PP_DEBUG", 0))
         fprintf(stderr, "[pp] decode_expected_warp_kernel G=%d grid=%d threads=%d smem=%zu ctas/sm=%d\n", G, wgrid, threads, wsmem, wper);
+      g_last_expected_kernel = PP_DECODE_KERNEL_TEAM;
       if (G == 1)
         decode_expected_warp_kernel<T, 1, kTPC><<<wgrid, threads, wsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, wgeo, counter);
       else
@@ -941,6 +946,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
     const int dgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * dper));
     unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;
     if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+    g_last_expected_kernel = PP_DECODE_KERNEL_DENSE;
     decode_expected_dense_kernel<T><<<dgrid, kDThreads, dsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, dgeo, counter);
     PP_CUDA_OK(cudaGetLastError());
     return PP_OK;
@@ -959,6 +965,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
     const int fgrid = static_cast<int>(fgrid64);
     unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;
     if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+    g_last_expected_kernel = PP_DECODE_KERNEL_CTA;
     decode_expected_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, geo, counter);
     PP_CUDA_OK(cudaGetLastError());
     return PP_OK;
@@ -966,6 +973,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   int per_sm = 1;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_kernel<T>), threads, smem, &per_sm)) return rc;
   const int grid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  g_last_expected_kernel = PP_DECODE_KERNEL_GENERIC;
   decode_expected_kernel<T><<<grid, threads, smem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, vec, false);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
@@ -1054,6 +1062,8 @@ int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* table, con
     return launch_decode_expected<float>(*p, *table, heatmaps, locs, vals, argmax, keypoints, conv_out, scratch, scratch_bytes, st);
   return launch_decode_expected<__nv_bfloat16>(*p, *table, heatmaps, locs, vals, argmax, keypoints, conv_out, scratch, scratch_bytes, st);
 }
+
+int pp_decode_expected_last_kernel(void) { return g_last_expected_kernel; }
 
 int64_t pp_decode_expected_workspace_floats(const pp_decode_params* p) {
   if (!p || p->H < 1 || p->W < 1) return 0;

@@ -35,6 +35,7 @@ struct WarpGeom {
   unsigned exch_off;      // TeamExchange
   unsigned slot_bytes;    // per-team slot (multiple of 128)
   unsigned rowoff_off;    // CTA-wide table of reflected row offsets, after the last slot
+  unsigned full_taps;     // 1: prefilter with every tap (PP_DECODE_FULLTAPS=1, for A/B measurements and tests)
   unsigned div_WV, div_W;
 };
 
@@ -262,6 +263,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   const int N = p.B * p.K;   // the launcher guarantees N < 2^31
   const bool tail = p.apply_tail != 0;
   const float temp = p.temperature;
+  const bool pp_no_truncation = geo.full_taps != 0;
   const int step_y = fast_div(S, geo.div_WV), step_x = S - step_y * WV;
   const int first_y = fast_div(tl, geo.div_WV), first_x = tl - first_y * WV;
 
@@ -299,18 +301,19 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   int cur_item = ex->i[6][0], cur_hm = ex->i[7][0];
   team_sync<G>(team);
 
-  int k_loaded = -1, r = 1, d = 3, nch4 = 1;
+  int k_loaded = -1, r = 1, d = 3, rf = 1, df = 3, nch4 = 1;
+  float tail2d = 0.0f;
   const double* w2dk = tab.kernel2d;
 
   for (int it = 0; cur_item < N; ++it) {
     const int hm = cur_hm;
     // claim the item after this one now, look at the answer later (publish_next, after the first phases): the
     // atomic's round trip then overlaps the scans instead of stalling the warp (capture R: 7 % of the samples)
-    int pulled = N;
-    if (tl == 0) pulled = dynamic ? static_cast<int>(min(atomicAdd(work_counter, 1u), static_cast<unsigned>(N)))
-                                  : min(cur_item + nteams, N);
+    unsigned pulled_raw = 0u;   // not looked at (not even clamped) before publish_next
+    if (tl == 0) pulled_raw = dynamic ? atomicAdd(work_counter, 1u) : static_cast<unsigned>(cur_item) + nteams;
     auto publish_next = [&]() {   // thread 0: next item -> exchange slots (read at the end of the iteration) + L2 prefetch
       if (tl == 0) {
+        const int pulled = static_cast<int>(min(pulled_raw, static_cast<unsigned>(N)));
         const int h = pulled < N ? item_to_hm(pulled) : N;
         ex->i[6][0] = pulled;
         ex->i[7][0] = h;
@@ -325,12 +328,27 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
     if (k != k_loaded) {   // uniform across the team; the previous heatmap ended with a team barrier
       r = tab.radius[k];
       d = 2 * r + 1;
-      nch4 = (d + 3) >> 2;
+      // The prefilter keeps the central 2 rf + 1 taps only.  For the wide kernels (radius = ceil(3 s) >= 6) the taps
+      // beyond rf = 5 / 6 carry less than 5e-4 of the 2-D mass; dropping them saves a chunk of multiply-adds in
+      // each pass.  What they would have added lies in [tail2d * min h, tail2d * max h] at every pixel, so it
+      // changes the difference between two pixels by at most tail2d * (max h - min h): the candidate band is
+      // widened by exactly that (tail2d is measured from the taps, with 1 % + 1e-6 of slack).  The lower bound L
+      // and the exact evaluation always use the full d x d table.
+      rf = r >= 8 ? 6 : r >= 6 ? 5 : r;
+      if (pp_no_truncation) rf = r;
+      df = 2 * rf + 1;
+      nch4 = (df + 3) >> 2;
       w2dk = tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
+      const float* t1 = tab.taps_f32 + k * PP_OKS_TAPS + (r - rf);
+      {
+        // mass of the kept taps (every warp for itself, fixed order -> identical in all of them)
+        double s1 = (lane < df) ? static_cast<double>(t1[lane]) : 0.0;
+        s1 = warp_sum(s1);
+        tail2d = rf == r ? 0.0f : static_cast<float>(fmax(1.0 - s1 * s1, 0.0) * 1.01 + 1e-6);
+      }
       if (tl < kWTaps) {
-        const float* t1 = tab.taps_f32 + k * PP_OKS_TAPS;
-        const float g0 = tl < d ? t1[tl] : 0.0f;
-        const float g1 = (tl >= 1 && tl <= d) ? t1[tl - 1] : 0.0f;
+        const float g0 = tl < df ? t1[tl] : 0.0f;
+        const float g1 = (tl >= 1 && tl <= df) ? t1[tl - 1] : 0.0f;
         taps[tl] = wf2_make(g0, g0);
         taps[kWTaps + tl] = wf2_make(g1, g1);
       }
@@ -368,6 +386,8 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
     } else {
       __syncwarp();
     }
+
+    publish_next();   // the scan above has covered the atomic's round trip
 
     int best = 0;
     float best_val = 0.0f, score = vmax;
@@ -436,7 +456,6 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       }
       bx0 = __reduce_min_sync(0xffffffffu, bx0); bx1 = __reduce_max_sync(0xffffffffu, bx1);
       by0 = __reduce_min_sync(0xffffffffu, by0); by1 = __reduce_max_sync(0xffffffffu, by1);
-      publish_next();
       if (G > 1) {
         if (lane == 0) { ex->i[1][tw] = bx0; ex->i[2][tw] = bx1; ex->i[3][tw] = by0; ex->i[4][tw] = by1; }
         if (tl == 0) cand[kWCand] = 0;
@@ -458,25 +477,25 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       // (reflected columns included); cbase is even so that a column task stores its 2 x 2 values with one 128-bit
       // store, which shifts the row-pass taps by s = 0 / 1 column (second tap table).  Output block t of a row pair
       // reads tmp[q][8 t .. 8 t + 8 nch8 + 7].
-      const int sh = (r - ox0) & 1;
-      const int cbase = r - ox0 + sh;                       // tmp column of source column x: x + cbase
-      const int nch8 = (d + sh + 7) >> 3;
+      const int sh = (rf - ox0) & 1;
+      const int cbase = rf - ox0 + sh;                      // tmp column of source column x: x + cbase
+      const int nch8 = (df + sh + 7) >> 3;
       const wf2* rtaps = taps + sh * kWTaps;
       const int nxb = (OW + 7) >> 3;
       int TS = 8 * nxb + 8 * nch8;                          // row-pair stride in pairs: 2 * odd -> conflict-free
       if (((TS >> 1) & 1) == 0) TS += 2;
       const int BQ = min((OH + 3) >> 2 << 1, (kWTmpPairs / TS) & ~1);   // row pairs per band (even)
       const int BR = 2 * BQ;
-      const int xs0 = max(ox0 - r, 0) & ~1;                 // first source pair (even column)
-      const int xs1 = min(ox1 + r, W - 1);
+      const int xs0 = max(ox0 - rf, 0) & ~1;                // first source pair (even column)
+      const int xs1 = min(ox1 + rf, W - 1);
       const int npair = ((xs1 - xs0) >> 1) + 1;
       const unsigned mpair = div_magic(npair);
-      const int cmax = OW + 2 * r - 1 + sh;                 // last tmp column that meets a non-zero tap
+      const int cmax = OW + 2 * rf - 1 + sh;                // last tmp column that meets a non-zero tap
       const int overhang = 4 * nch4 + 3;                    // rows touched below y0 - r by the padded chunks
 
       const float amax = fmaxf(fabsf(vmax), fabsf(vmin));
-      const float gamma = static_cast<float>(2 * d + 8) * 1.1920929e-7f;   // (2d + 8) * 2^-23
-      const float band = (2.0f * gamma + 4.0f * 5.9604645e-8f) * amax;
+      const float gamma = static_cast<float>(2 * df + 8) * 1.1920929e-7f;   // (2 df + 8) * 2^-23
+      const float band = (2.0f * gamma + 4.0f * 5.9604645e-8f) * amax + tail2d * (vmax - vmin);
 
       // Candidates.  Only a pixel whose prefilter value lies within `band` of the prefilter maximum can be the exact
       // maximum, and the final maximum is at least the warp's running one (gm, refreshed with one shuffle reduction
@@ -498,8 +517,8 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
             const int yb = fast_div(t, mpair), x = xs0 + 2 * (t - yb * npair);
             const int y0 = ya + 4 * yb;
             wf2 acc[4];
-            if (y0 - r >= 0 && y0 - r + overhang < H) warp_col_task<T, true>(plane, taps, nch4, x, y0, r, W, rowoff, acc);
-            else warp_col_task<T, false>(plane, taps, nch4, x, y0, r, W, rowoff, acc);
+            if (y0 - rf >= 0 && y0 - rf + overhang < H) warp_col_task<T, true>(plane, taps, nch4, x, y0, rf, W, rowoff, acc);
+            else warp_col_task<T, false>(plane, taps, nch4, x, y0, rf, W, rowoff, acc);
             float a0[4], a1[4];
 #pragma unroll
             for (int o = 0; o < 4; ++o) wf2_split(acc[o], a0[o], a1[o]);
@@ -627,8 +646,6 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
         nb[0] = ev[1]; nb[1] = ev[2]; nb[2] = ev[3]; nb[3] = ev[4];
       }
       score = plane_value<T>(plane, best);
-    } else {
-      publish_next();
     }
 
     // ---- H: outputs.  The x and y halves of the sub-pixel fit (heatmap.py:136-165, float32, the reference's

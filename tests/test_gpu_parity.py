@@ -30,7 +30,7 @@ def pp():
 
 
 
-@pytest.fixture(params=["auto", "team1", "team2", "cta"])
+@pytest.fixture(params=["auto", "team1", "team2", "team1-fulltaps", "cta"])
 def expected_kernel(request, monkeypatch):
     """Which kernel runs the expected-OKS decode: the library's size rule ("auto": small batches such as the ones in
     these tests take the CTA-per-heatmap kernel), the team-per-heatmap kernel (pp_decode_warp.cuh) with one or two
@@ -40,7 +40,9 @@ def expected_kernel(request, monkeypatch):
         monkeypatch.setenv("PP_DECODE_WARP", "0")
     elif mode != "auto":
         monkeypatch.setenv("PP_DECODE_WARP", "1")
-        monkeypatch.setenv("PP_DECODE_TEAM", mode[-1])
+        monkeypatch.setenv("PP_DECODE_TEAM", mode[4])
+        if mode.endswith("fulltaps"):   # prefilter with every tap instead of the truncated wide kernels
+            monkeypatch.setenv("PP_DECODE_FULLTAPS", "1")
     return mode
 
 

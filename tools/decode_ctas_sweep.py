@@ -26,7 +26,7 @@ def main():
     pred = (blob * amp[:, :, None, None] + torch.rand_like(blob) * 0.02).clamp_(0, 1).contiguous()
     noise = (torch.rand_like(blob) * 0.02).contiguous()
     clean = (blob * amp[:, :, None, None]).contiguous()
-    for mode in (1, 2, 4, 0):
+    for mode in (1, 0):
         os.environ["PP_DECODE_WARP"] = "1" if mode else "0"
         os.environ["PP_DECODE_TEAM"] = str(max(mode, 1))
         for cap in (2, 0):
