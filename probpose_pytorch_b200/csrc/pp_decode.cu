@@ -908,13 +908,20 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   const int want_warp = pp_env_int("PP_DECODE_WARP", -1);
   if (want_warp != 0 && !pp_env_int("PP_DECODE_DENSE", 0) && warp_geometry<T>(p, heatmaps, &wgeo)) {
     constexpr int kTPC = 2;
-    const int G = pp_env_int("PP_DECODE_TEAM", 1);
-    const void* fn = G == 1 ? reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 1, kTPC>)
-                            : reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 2, kTPC>);
-    const int threads = 32 * (G == 1 ? 1 : 2) * kTPC;
     wgeo.rowoff_off = static_cast<unsigned>(kTPC) * wgeo.slot_bytes;
     wgeo.full_taps = pp_env_int("PP_DECODE_FULLTAPS", 0) ? 1u : 0u;
     const size_t wsmem = wgeo.rowoff_off + sizeof(int) * static_cast<size_t>(p.H + 2 * kWRowPad);
+    // warps per heatmap: one while a dozen heatmaps fit on an SM (64x48 float32: 12); larger planes leave room for
+    // fewer heatmaps, and two warps each then keep the SM's schedulers fed (96x72 float32, 6 heatmaps per SM:
+    // 202 us with two warps, 237 us with one, 232 us for the CTA-per-heatmap kernel; profiles/r01s_summary.md)
+    int G = pp_env_int("PP_DECODE_TEAM", 0);
+    if (G != 1 && G != 2) {
+      const int64_t slots = (static_cast<int64_t>(pp_smem_optin()) + 1024) / static_cast<int64_t>(wsmem + 1024) * kTPC;
+      G = slots >= 10 ? 1 : 2;
+    }
+    const void* fn = G == 1 ? reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 1, kTPC>)
+                            : reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 2, kTPC>);
+    const int threads = 32 * G * kTPC;
     int wper = 0;
     if (wsmem + 2048 <= static_cast<size_t>(pp_smem_optin()) && pp_configure_kernel(fn, threads, wsmem, &wper) == PP_OK &&
         wper * kTPC >= 6 && (want_warp == 1 || N >= 2ll * pp_sm_count() * wper * kTPC)) {

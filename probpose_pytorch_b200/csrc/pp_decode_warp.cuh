@@ -73,25 +73,25 @@ __device__ __forceinline__ wf2 load_pair<__nv_bfloat16>(const __nv_bfloat16* p) 
 
 // column pass of one task: two adjacent columns (x even), four consecutive rows, taps in chunks of four
 //   acc[o] = (sum_j tap[j] h[reflect(y0 + o - r + j)][x], same for x + 1)
-// kInside: every row the chunks touch (including the zero-tap overhang) lies inside the map.
-// Otherwise the row offsets come from the CTA's table rowoff[i] = reflect(i - kWRowPad) * W, which also covers the
-// overhang (those rows meet zero taps).
-template <typename T, bool kInside>
+// Row offsets come from the CTA's table rowoff[i] = reflect(i - kWRowPad) * W, which also covers the overhang of the
+// zero-padded chunks (those rows meet zero taps).  A second, table-free body for tasks whose rows all lie inside the
+// map was measured and dropped: it saves one shared load per row but the larger kernel runs slower (160 us against
+// 154 us at B = 1024) -- code size matters more than instruction count here.
+template <typename T>
 __device__ __forceinline__ void warp_col_task(const T* __restrict__ plane, const wf2* __restrict__ g2, int nch4, int x,
-                                              int y0, int r, int W, const int* __restrict__ rowoff, wf2 (&acc)[4]) {
+                                              int y0, int r, const int* __restrict__ rowoff, wf2 (&acc)[4]) {
   wf2 w[8];
-  const T* base = plane + x + (kInside ? (y0 - r) * W : 0);
+  const T* base = plane + x;
   const int* ro = rowoff + (y0 - r + kWRowPad);
-  auto fetch = [&](int j) -> wf2 {
-    if (kInside) return load_pair<T>(base + j * W);
-    return load_pair<T>(base + ro[j]);
-  };
+  auto fetch = [&](int j) -> wf2 { return load_pair<T>(base + ro[j]); };
 #pragma unroll
   for (int j = 0; j < 4; ++j) w[j] = fetch(j);
 #pragma unroll
   for (int o = 0; o < 4; ++o) acc[o] = 0ull;
-  // (requesting the next chunk's rows ahead of the multiply-adds was measured: 68 us against 64.5 us -- the extra
-  // register moves cost more than the shared-memory latency they hide)
+  // Measured and rejected: requesting the next chunk's rows ahead of the multiply-adds (68 us against 64.5 us -- the
+  // extra register moves cost more than the shared-memory latency they hide), and full unrolling per chunk count
+  // through a switch (no window shifting, no loop: 67.7 us against 59.6 us on the mixed C2 inputs -- the five + three
+  // unrolled bodies no longer fit the instruction cache once warps with different radii share an SM).
 #pragma unroll 1
   for (int c = 0; c < nch4; ++c) {
 #pragma unroll
@@ -491,7 +491,6 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       const int npair = ((xs1 - xs0) >> 1) + 1;
       const unsigned mpair = div_magic(npair);
       const int cmax = OW + 2 * rf - 1 + sh;                // last tmp column that meets a non-zero tap
-      const int overhang = 4 * nch4 + 3;                    // rows touched below y0 - r by the padded chunks
 
       const float amax = fmaxf(fabsf(vmax), fabsf(vmin));
       const float gamma = static_cast<float>(2 * df + 8) * 1.1920929e-7f;   // (2 df + 8) * 2^-23
@@ -517,8 +516,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
             const int yb = fast_div(t, mpair), x = xs0 + 2 * (t - yb * npair);
             const int y0 = ya + 4 * yb;
             wf2 acc[4];
-            if (y0 - rf >= 0 && y0 - rf + overhang < H) warp_col_task<T, true>(plane, taps, nch4, x, y0, rf, W, rowoff, acc);
-            else warp_col_task<T, false>(plane, taps, nch4, x, y0, rf, W, rowoff, acc);
+            warp_col_task<T>(plane, taps, nch4, x, y0, rf, rowoff, acc);
             float a0[4], a1[4];
 #pragma unroll
             for (int o = 0; o < 4; ++o) wf2_split(acc[o], a0[o], a1[o]);

@@ -1,5 +1,5 @@
 """Expected-OKS decoder variants at B = 256 and B = 1024 (C2 shapes): separates the per-heatmap cost from the
-launch / tail overhead.  Usage: python tools/decode_scale_probe.py"""
+launch / tail overhead.  Usage: python tools/decode_scale_probe.py [config_id]"""
 import os
 import sys
 from pathlib import Path
@@ -22,10 +22,11 @@ def make(B, wl, dev):
 
 
 def main():
-    wl = synth.WORKLOADS[2]
+    cid = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    wl = synth.WORKLOADS[cid]
     dev = torch.device("cuda")
     pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
-    preds = {B: make(B, wl, dev) for B in (128, 256, 1024)}
+    preds = {B: make(B, wl, dev) for B in ((128, 256, 1024) if cid == 2 else (wl.batch // 4, wl.batch))}
     for mode in (1, 2, 0):
         os.environ["PP_DECODE_WARP"] = "1" if mode else "0"
         os.environ["PP_DECODE_TEAM"] = str(max(mode, 1))
