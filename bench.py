@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--exchange-every", type=int, default=0,
                     help="multi-GPU: steps per all-gather bucket (0 = number of buffer sets; 1 = one collective per step)")
     ap.add_argument("--serial", action="store_true", help="run decode after encode on one stream (no fork/join)")
+    ap.add_argument("--exchange", choices=["mailbox", "nccl"], default="mailbox",
+                    help="multi-GPU record + loss exchange: stores into every rank's mailbox over NVLink peer memory from the "
+                         "record-packing kernel (default), or bucketed NCCL all-gathers")
     return ap.parse_args()
 
 
@@ -259,36 +262,57 @@ def run_product(args):
 
     side = torch.cuda.Stream(device=dev)
 
-    def step_device(s):
+    # ---- multi-GPU exchange of the step's results (keypoint records + loss): a mailbox per rank in NVLink peer
+    # memory, written by the record-packing kernel itself; one slot per rotating buffer set
+    mailbox, exchange_note = None, ""
+    if world > 1 and args.exchange == "mailbox":
+        try:
+            mailbox = ppd.PeerMailbox(B, K, len(sets), dev)
+            exchange_note = f"records + loss stored into every rank's mailbox over NVLink by pp_pack_records ({len(sets)} slots)"
+        except Exception as e:   # symmetric memory unavailable on this box: the NCCL path still measures the step
+            exchange_note = f"NCCL (symmetric memory unavailable: {type(e).__name__}: {str(e)[:80]})"
+            mailbox = None
+
+    def step_device(s, slot=0):
         """The hot path on device-resident inputs.  The decode only depends on the prediction, so it runs on
-        a second stream next to encode -> loss (fork / join; inside the captured graph these are two branches)."""
+        a second stream next to encode -> loss (fork / join; inside the captured graph these are two branches);
+        the records are packed (and, on several GPUs, published together with the loss) after the join."""
         cur = torch.cuda.current_stream(dev)
+        pred5 = (s["pred"], *s["heads"])
+        rec = None
         if not args.serial:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                rec = codec.decode_device((s["pred"], *s["heads"]))
+                dec = pm.decode_device(s["pred"])
+                # the records are packed right behind the decode and, on several GPUs, stored into every rank's
+                # mailbox by the same kernel; the loss joins them after the join (commit)
+                rec = codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
         enc = am.encode_batch(s["kps"], s["vis"], dtype=tdtype)
         if args.serial:
-            rec = codec.decode_device((s["pred"], *s["heads"]))
+            dec = pm.decode_device(s["pred"])
         out = s["pred"].detach().requires_grad_(True)
         loss = loss_fn.forward_mean(out, enc["heatmaps"], enc["keypoint_weights"])
         loss.backward()
         if not args.serial:
             cur.wait_stream(side)
+        if rec is None:
+            rec = codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
+        if mailbox is not None:
+            mailbox.commit(slot, loss.detach())
         return rec, loss.detach(), out.grad
 
     # ---- CUDA graphs of the step, one per buffer set
     graphs, results = [], []
     use_graph = not args.no_graph
-    for s in sets:
+    for j, s in enumerate(sets):
         for _ in range(2):
-            step_device(s)
+            step_device(s, j)
     torch.cuda.synchronize()
     if use_graph:
-        for s in sets:
+        for j, s in enumerate(sets):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                results.append(step_device(s))
+                results.append(step_device(s, j))
             graphs.append(g)
         torch.cuda.synchronize()
 
@@ -297,9 +321,11 @@ def run_product(args):
         if use_graph:
             graphs[j].replay()
             rec, loss, _ = results[j]
+            if mailbox is not None:
+                mailbox.published(j)      # the replayed graph published slot j again
         else:
-            rec, loss, _ = step_device(sets[j])
-        if world > 1:
+            rec, loss, _ = step_device(sets[j], j)
+        if world > 1 and mailbox is None:
             # the only exchange on the path: keypoint records + loss partials.  It is latency bound, so the results
             # of `--exchange-every` consecutive steps (<= the number of rotating buffer sets, whose outputs are
             # still intact) travel in ONE all-gather, issued asynchronously so that it overlaps the next steps'
@@ -349,6 +375,17 @@ def run_product(args):
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    exchange_checked = None
+    if mailbox is not None:
+        # what arrived in this rank's mailbox for the last step must be what an all-gather of the ranks' results gives
+        j = (args.steps - 1) % len(sets)
+        got_rec, got_loss = mailbox.read(j)
+        rec_l, loss_l = (results[j][0], results[j][1]) if use_graph else step_device(sets[j], j)[:2]
+        want = ppd.exchange_step_results(rec_l, loss_l.to(torch.float64))
+        exchange_checked = bool(torch.equal(got_rec.view(want.records.shape), want.records)
+                                and torch.allclose(got_loss.mean(), want.loss.double(), rtol=1e-6, atol=0))
+        if not exchange_checked:
+            raise RuntimeError("mailbox exchange does not match the all-gather of the ranks' results")
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -539,7 +576,7 @@ def run_product(args):
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
     if rank == 0:
-        launches_per_step = 5   # encode, decode, loss, loss finalize, grad-scale check
+        launches_per_step = 6 + (1 if mailbox is not None else 0)   # encode, decode, loss, loss finalize, grad-scale check, record packing (+ mailbox commit)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -553,7 +590,10 @@ def run_product(args):
                        "launch": ("CUDA graph replay" if use_graph else "eager")
                                  + (", one stream" if args.serial else ", decode on a second stream beside encode->loss"),
                        "parallelism": f"dp{world} (batch sharded by image)"
-                                      + ("" if world == 1 else f"; records + loss of {exchange_every} step(s) per asynchronous all-gather")},
+                                      + ("" if world == 1 else
+                                         f"; {exchange_note}, checked against an all-gather: {exchange_checked}" if mailbox is not None else
+                                         f"; records + loss of {exchange_every} step(s) per asynchronous all-gather"
+                                         + (f" [{exchange_note}]" if exchange_note else ""))},
             "roofline": roofline, "kernels": kernels, "e2e": e2e, "cpu_baseline": cpu_baseline,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }

@@ -252,6 +252,41 @@ PP_API int pp_pck_accuracy(const float* pred, const float* gt, const uint8_t* ma
                            int32_t norm_dtype, int32_t N, int32_t K, double thr, double* acc, double* avg_acc,
                            int32_t* cnt, float* distances /* or NULL */, pp_stream_t stream);
 
+/* ---- decoded-keypoint records and their exchange between GPUs ("final keypoint gather" + loss) ----
+ * Tail of Codec.decode (codec.py:249-263): one (x, y, score, probability, visibility, oks, error / diagonal) float64
+ * record per keypoint.  With a mailbox the same kernel also stores the records and the step's local loss into every
+ * rank's mailbox over NVLink peer memory; pp_mailbox_commit adds the loss and raises a per-source flag: the
+ * all-gather of a multi-GPU loop without a collective call.  The mailbox is a symmetric allocation (same size on every rank, mapped
+ * into every rank's address space, e.g. torch.distributed._symmetric_memory) of slots * world blocks of
+ * pp_mailbox_block_bytes(N) bytes: [N * 7 doubles | pad to 16 | loss (double) | flag (uint32) | pad]; the loss sits
+ * 16 bytes before the end of the block. */
+typedef struct pp_mailbox {
+  void* const* peer_bufs;   /* device array of `world` pointers: base of every rank's mailbox (own rank included) */
+  uint32_t* state;          /* local device memory, slots + 1 words, zero before the first call: sequence number of
+                               each slot (the last word is reserved) */
+  int32_t world, rank;
+  int32_t slots, slot;      /* the block (slot, rank) of every mailbox is written */
+  int64_t block_bytes;      /* pp_mailbox_block_bytes(N) */
+} pp_mailbox;
+
+PP_API int64_t pp_mailbox_block_bytes(int64_t n_records);
+PP_API int pp_pack_records(int64_t N,
+                           const double* keypoints,      /* (N, 2) input-space coordinates (pp_decode_expected) */
+                           const float* scores,          /* (N) */
+                           const float* probabilities, const float* visibilities, const float* oks,
+                           const float* errors,          /* (N) each: the four scalar heads */
+                           float inv_diagonal,           /* 1 / sqrt(H^2 + W^2) in float32 (codec.py:261) */
+                           double* records,              /* out (N, 7) local, or NULL when only the mailbox is wanted */
+                           const pp_mailbox* mailbox,    /* or NULL: local records only */
+                           pp_stream_t stream);
+/* Completes the publication of `mailbox->slot`: stores the step's local loss (device scalar, or NULL for 0) into the
+ * block and raises its flag on every rank.  Must be ordered after the pp_pack_records of the same slot. */
+PP_API int pp_mailbox_commit(const pp_mailbox* mailbox, int64_t n_records, const float* loss, pp_stream_t stream);
+/* Wait until all `world` sources have published sequence number >= expected_seq into `slot` of this rank's mailbox.
+ * *status (device int, zero before the call) becomes 1 + source rank if a source did not arrive within timeout_us. */
+PP_API int pp_mailbox_wait(const void* local_mailbox, int32_t world, int32_t slot, int64_t n_records, uint32_t expected_seq,
+                           int64_t timeout_us, int32_t* status, pp_stream_t stream);
+
 /* ProbPoseLoss.get_binary_accuracy, force_balanced=False (loss.py:653-697): best accuracy over the given
  * thresholds among the mask-selected entries.  out = (best_acc, best_threshold); counts (n_thresholds + 1, the
  * last entry is the number of selected samples) may be NULL. */

@@ -29,6 +29,7 @@ EXPORTS = (
     "pp_oks_loss_scratch_bytes",
     "pp_oks_loss_forward", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
     "pp_pck_accuracy", "pp_binary_accuracy", "pp_masked_mae",
+    "pp_mailbox_block_bytes", "pp_pack_records", "pp_mailbox_commit", "pp_mailbox_wait",
 )
 
 
@@ -54,6 +55,11 @@ class LossParams(C.Structure):
                 ("skip_empty_channel", C.c_int32),
                 ("smoothing_weight", C.c_double), ("gaussian_weight", C.c_double), ("loss_weight", C.c_double),
                 ("mask_stride_b", C.c_int64), ("mask_stride_k", C.c_int64)]
+
+
+class Mailbox(C.Structure):
+    _fields_ = [("peer_bufs", C.c_void_p), ("state", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32),
+                ("slots", C.c_int32), ("slot", C.c_int32), ("block_bytes", C.c_int64)]
 
 
 _lib = None
@@ -100,10 +106,16 @@ def lib() -> C.CDLL:
     L.pp_oks_loss_backward.argtypes = [C.POINTER(LossParams), vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp]
     L.pp_scale_inplace.argtypes = [vp, i32, i64, vp, vp]
     L.pp_pose_targets.argtypes = [vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, vp]
+    L.pp_mailbox_block_bytes.argtypes = [i64]
+    L.pp_mailbox_block_bytes.restype = i64
+    L.pp_pack_records.argtypes = [i64, vp, vp, vp, vp, vp, vp, f32, vp, C.POINTER(Mailbox), vp]
+    L.pp_mailbox_commit.argtypes = [C.POINTER(Mailbox), i64, vp, vp]
+    L.pp_mailbox_wait.argtypes = [vp, i32, i32, i64, C.c_uint32, i64, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("pp_version", "pp_last_error_string", "pp_oks_loss_scratch_bytes",
-                        "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes"):
+                        "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes",
+                        "pp_mailbox_block_bytes"):
             fn.restype = C.c_int
     if L.pp_version() != 1:
         raise RuntimeError(f"{LIB_PATH}: ABI version {L.pp_version()} != 1; rebuild the extension")

@@ -15,7 +15,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libprobpose_b200.so"
-SOURCES = ["pp_api.cu", "pp_encode.cu", "pp_decode.cu", "pp_loss.cu", "pp_targets.cu", "pp_sparsemax.cu", "pp_metrics.cu"]
+SOURCES = ["pp_api.cu", "pp_encode.cu", "pp_decode.cu", "pp_loss.cu", "pp_targets.cu", "pp_sparsemax.cu", "pp_metrics.cu", "pp_records.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

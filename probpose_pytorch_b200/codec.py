@@ -306,21 +306,44 @@ class Codec:
         errors = errors / np.sqrt(H ** 2 + W ** 2)
         return preds, probabilities, visibilities, oks, errors
 
-    def decode_device(self, pred, *, temperature: float | None = None) -> Tensor:
+    def decode_device(self, pred, *, temperature: float | None = None, mailbox=None, slot: int = 0,
+                      loss: Tensor | None = None) -> Tensor:
         """Fully device-resident decode: returns one packed (B, K, 7) float64 tensor of records
         ``(x, y, score, probability, visibility, oks, error / diagonal)`` -- the unit that is
-        all-gathered across GPUs."""
+        gathered across GPUs.  The records are packed by one kernel (``pp_pack_records``); with a
+        :class:`~probpose_pytorch_b200.distributed.PeerMailbox` the same kernel also stores them into ``slot`` of every
+        rank's mailbox over NVLink; ``loss`` (a device scalar) then completes the publication (``mailbox.commit``) --
+        without it the caller commits later, once the step's loss exists."""
         heatmaps, probabilities, visibilities, oks, errors = pred
-        B, C, H, W = heatmaps.shape
         out = self.probmap.decode_device(heatmaps if heatmaps.ndim == 4 else heatmaps.unsqueeze(0),
                                          temperature=temperature)
-        rec = torch.empty((B, C, 7), dtype=torch.float64, device=heatmaps.device)
-        rec[..., 0:2] = out["keypoints"]
-        rec[..., 2] = out["scores"]
-        rec[..., 3] = probabilities.reshape(B, C)
-        rec[..., 4] = visibilities.reshape(B, C)
-        rec[..., 5] = oks.reshape(B, C)
-        rec[..., 6] = errors.reshape(B, C) / float(np.sqrt(H ** 2 + W ** 2))
+        return self.pack_records(out, pred, mailbox=mailbox, slot=slot, loss=loss)
+
+    def pack_records(self, decoded: dict, pred, *, mailbox=None, slot: int = 0, loss: Tensor | None = None) -> Tensor:
+        """The record-packing half of :meth:`decode_device` on an already decoded batch (``probmap.decode_device``
+        output); lets a caller publish the records together with a loss that is computed later in the step."""
+        heatmaps, probabilities, visibilities, oks, errors = pred
+        B, C, H, W = heatmaps.shape if heatmaps.ndim == 4 else (1,) + tuple(heatmaps.shape)
+        dev = heatmaps.device
+        n = B * C
+        heads = [h.reshape(-1).to(torch.float32).contiguous() for h in (probabilities, visibilities, oks, errors)]
+        for h in heads:
+            assert h.numel() == n, "scalar heads must hold one value per keypoint"
+        kp = decoded["keypoints"].reshape(n, 2)
+        sc = decoded["scores"].reshape(n)
+        assert kp.dtype == torch.float64 and sc.dtype == torch.float32 and kp.is_contiguous() and sc.is_contiguous()
+        rec = torch.empty((B, C, 7), dtype=torch.float64, device=dev)
+        inv_diag = float(np.float32(1.0) / np.float32(np.sqrt(H ** 2 + W ** 2)))   # what torch's f32 / scalar multiplies by
+        mb = None
+        if mailbox is not None:
+            assert mailbox.n_records == n, f"mailbox built for {mailbox.n_records} records, got {n}"
+            mb = mailbox.descriptor(slot)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().pp_pack_records(n, _lib.ptr(kp), _lib.ptr(sc), *[_lib.ptr(h) for h in heads], inv_diag,
+                                            _lib.ptr(rec), mb, _lib.stream_ptr(dev))
+        _lib.check(rc, "pp_pack_records")
+        if mailbox is not None and loss is not None:
+            mailbox.commit(slot, loss)
         return rec
 
     def decode_heatmap(self, heatmaps):

@@ -164,3 +164,91 @@ def exchange_bucket(records: Sequence[Tensor], losses: Sequence[Tensor], async_o
     out = flat.new_empty(ws * flat.numel())
     work = dist.all_gather_into_tensor(out, flat, async_op=async_op)
     return BucketExchange(out.view(ws, flat.numel()), S, tuple(records[0].shape), losses[0].dtype, work if async_op else None)
+
+
+class PeerMailbox:
+    """Record / loss exchange over NVLink peer memory, without a collective call.
+
+    Every rank owns a mailbox of ``slots x world`` blocks (a symmetric allocation: the same buffer exists on every
+    rank and all of them are mapped into every rank's address space).  ``Codec.decode_device(..., mailbox=mb,
+    slot=s, loss=l)`` packs a step's keypoint records and, in the same kernel, stores them and the local loss into
+    block ``(s, rank)`` of EVERY rank's mailbox (``pp_pack_records``); ``commit(s, loss)`` adds the loss and raises the
+    block's flag (``pp_mailbox_commit``; ``decode_device`` does it itself when it is given the loss).  ``read(s)``
+    waits for the flags of all sources and returns ``(records (B_global, K, 7), losses (world,))`` -- what one
+    all-gather of records + loss would have delivered.  A slot is rewritten when it is published again; a consumer
+    that wants every step reads a slot before ``slots`` further steps have been published (loss logging and
+    evaluation do).  CUDA-graph capturable: the sequence numbers live in device memory.
+
+    Plumbing: ``torch.distributed._symmetric_memory`` allocates and maps the buffers (world > 1); with one process an
+    ordinary tensor plays every peer.
+    """
+
+    def __init__(self, batch_local: int, num_keypoints: int, slots: int, device: torch.device, group=None):
+        from . import _lib
+        self.world, self.rank = world()
+        self.slots, self.device = int(slots), torch.device(device)
+        self.shape = (int(batch_local), int(num_keypoints), 7)
+        self.n_records = int(batch_local) * int(num_keypoints)
+        self.block_bytes = int(_lib.lib().pp_mailbox_block_bytes(self.n_records))
+        nbytes = self.slots * self.world * self.block_bytes
+        self._handle = None
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.buf.zero_()
+            self._handle = symm_mem.rendezvous(self.buf, grp)
+            ptrs = [int(p) for p in self._handle.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            dist.barrier()                      # every mailbox is zeroed before anybody publishes
+        else:
+            self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            ptrs = [self.buf.data_ptr()]
+        self._peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        self._state = torch.zeros(self.slots + 1, dtype=torch.int32, device=self.device)
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._published = [0] * self.slots       # host copy of the sequence numbers (launch order)
+        self._lib = _lib
+
+    def descriptor(self, slot: int):
+        assert 0 <= slot < self.slots
+        return self._lib.Mailbox(self._peer_ptrs.data_ptr(), self._state.data_ptr(), self.world, self.rank, self.slots,
+                                 int(slot), self.block_bytes)
+
+    def commit(self, slot: int, loss: Tensor | None = None) -> None:
+        """Complete the publication of ``slot``: the local loss joins the records (stored by ``pp_pack_records`` into the
+        same slot, earlier on this stream or on a stream this one has waited for) and the flags go up on every rank."""
+        if loss is not None:
+            loss = loss.detach().reshape(()).to(torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self._lib.lib().pp_mailbox_commit(self.descriptor(slot), self.n_records, self._lib.ptr(loss),
+                                                   self._lib.stream_ptr(self.device))
+        self._lib.check(rc, "pp_mailbox_commit")
+        if not torch.cuda.is_current_stream_capturing():
+            self.published(slot)      # a captured commit publishes when (and as often as) its graph is replayed
+
+    def published(self, slot: int, times: int = 1) -> None:
+        """Book-keeping: ``slot`` was published ``times`` more times (a replayed CUDA graph publishes without
+        passing through Python -- call this after each replay)."""
+        self._published[slot] += times
+
+    def read(self, slot: int, timeout_us: int = 2_000_000):
+        """(records (world * B_local, K, 7) float64 in rank order, losses (world,) float64) of the latest publication
+        of ``slot`` by every rank.  Every rank must have published the slot equally often."""
+        expected = self._published[slot]
+        assert expected > 0, "nothing published into this slot yet"
+        with torch.cuda.device(self.device):
+            self._status.zero_()
+            rc = self._lib.lib().pp_mailbox_wait(self._lib.ptr(self.buf), self.world, int(slot), self.n_records,
+                                                 expected & 0xFFFFFFFF, int(timeout_us), self._lib.ptr(self._status),
+                                                 self._lib.stream_ptr(self.device))
+        self._lib.check(rc, "pp_mailbox_wait")
+        late = int(self._status.item())
+        if late:
+            raise RuntimeError(f"PeerMailbox.read: rank {late - 1} did not publish slot {slot} (sequence {expected}) in time")
+        blocks = self.buf[slot * self.world * self.block_bytes:(slot + 1) * self.world * self.block_bytes]
+        blocks = blocks.view(self.world, self.block_bytes)
+        rec = blocks[:, :self.n_records * 56].contiguous().view(torch.float64)
+        rec = rec.view((self.world * self.shape[0],) + self.shape[1:])
+        loss = blocks[:, self.block_bytes - 16:self.block_bytes - 8].contiguous().view(torch.float64).reshape(self.world)
+        return rec, loss

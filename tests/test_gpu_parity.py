@@ -1113,3 +1113,52 @@ def test_paired_loss_variant_matches_default(pp, monkeypatch):
             for l, gr in res:
                 assert abs(l - l_ref.item()) <= RTOL32 * abs(l_ref.item()) + 1e-9
                 _close(gr, o_ref.grad.numpy(), RTOL32)
+
+
+# --------------------------------------------------------------------------- records + peer mailbox
+def test_pack_records_and_single_process_mailbox(pp):
+    """pp_pack_records = the record tail of Codec.decode (codec.py:249-263); with a mailbox the same kernel publishes
+    records + loss (one process plays every peer here; bench.py checks the multi-GPU exchange against an all-gather)."""
+    from probpose_pytorch_b200.distributed import PeerMailbox
+    wl = synth.WORKLOADS[2]
+    B, K = 5, wl.num_keypoints
+    W, H = wl.heatmap_size
+    rng = np.random.default_rng(91)
+    kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=92)
+    maps = _oracle_encode("argmax", wl, kps, vis)["heatmaps"]
+    pred = torch.from_numpy(synth.blob_predictions_numpy(maps, synth.blob_params(maps.shape[:2], 93), 94)).cuda()
+    heads = [torch.from_numpy(rng.random((B, K, 1, 1), dtype=np.float32)).cuda() for _ in range(4)]
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    codec = pp.Codec(pm)
+    rec = codec.decode_device((pred, *heads))
+    dec = pm.decode_device(pred)
+    assert rec.shape == (B, K, 7) and rec.dtype == torch.float64
+    assert torch.equal(rec[..., 0:2], dec["keypoints"]) and torch.equal(rec[..., 2], dec["scores"].double())
+    for c, h in zip((3, 4, 5), heads):
+        assert torch.equal(rec[..., c], h.reshape(B, K).double())
+    want_err = (heads[3].reshape(B, K) / float(np.sqrt(H ** 2 + W ** 2))).double()       # torch's float32 / scalar
+    assert torch.equal(rec[..., 6], want_err)
+    # mailbox: two slots, published twice each; the reader sees the latest publication
+    mb = PeerMailbox(B, K, 2, pred.device)
+    for rnd in range(2):
+        for slot in range(2):
+            scale = 1.0 + slot + 10 * rnd
+            hs = [h * scale for h in heads]
+            loss = torch.tensor(0.25 * scale, device="cuda")
+            r = codec.decode_device((pred, *hs), mailbox=mb, slot=slot, loss=loss)
+            got, got_loss = mb.read(slot)
+            assert torch.equal(got.view(r.shape), r)
+            assert got_loss.shape == (1,) and abs(got_loss.item() - 0.25 * scale) < 1e-6
+    # captured in a CUDA graph: the sequence numbers advance on the device, the host is told after each replay
+    g = torch.cuda.CUDAGraph()
+    static_heads = [h.clone() for h in heads]
+    loss = torch.tensor(3.0, device="cuda")
+    codec.decode_device((pred, *static_heads), mailbox=mb, slot=1, loss=loss)           # warm-up outside the graph
+    with torch.cuda.graph(g):
+        r = codec.decode_device((pred, *static_heads), mailbox=mb, slot=1, loss=loss)
+    for k in range(3):
+        static_heads[0].fill_(0.5 + k)
+        g.replay()
+        mb.published(1)
+        got, got_loss = mb.read(1)
+        assert torch.equal(got.view(r.shape), r) and float(got[0, 0, 3]) == 0.5 + k and got_loss.item() == 3.0
