@@ -22,6 +22,20 @@
 // 2^-50 of scipy's sum, far inside a float32 rounding cell).
 #pragma once
 
+// developer-only phase timing (see pp_decode_fast.cuh): lane 0 of every team accumulates cycles between marks
+#ifdef PP_PHASE_TIMING
+#define PP_WMARK(slot)                                                        \
+  do {                                                                        \
+    if (tl == 0) {                                                            \
+      const long long now_ = clock64();                                       \
+      atomicAdd(&g_phase_cycles[slot], static_cast<unsigned long long>(now_ - mark_)); \
+      mark_ = now_;                                                           \
+    }                                                                         \
+  } while (0)
+#else
+#define PP_WMARK(slot) do { } while (0)
+#endif
+
 constexpr int kWTmpPairs = 592;     // band buffer per team, in float2 (row pair) elements: 4.6 KB (8 full-width row pairs of a 64x48 map)
 constexpr int kWCand = 64;          // candidate list per warp
 constexpr int kWTaps = 24;          // 1-D taps zero-padded to 3 chunks of 8
@@ -305,6 +319,9 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   float tail2d = 0.0f;
   const double* w2dk = tab.kernel2d;
 
+#ifdef PP_PHASE_TIMING
+  long long mark_ = clock64();
+#endif
   for (int it = 0; cur_item < N; ++it) {
     const int hm = cur_hm;
     // claim the item after this one now, look at the answer later (publish_next, after the first phases): the
@@ -354,7 +371,9 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       }
       k_loaded = k;
     }
+    PP_WMARK(0);
     mbar_wait(bar, it & 1);
+    PP_WMARK(1);
 
     // ---- A: head tail in place (optional), then max / min
     if (tail) {
@@ -369,12 +388,16 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       team_sync<G>(team);
     }
     float xmax = -INFINITY, xmin = INFINITY;
+    int ivec = 0;   // first 128-bit vector of this thread that holds its maximum: phase B looks at that one only
 #pragma unroll 4
     for (int i = tl; i < NV; i += S) {
       float f[V];
       unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+      float m = f[0], mn = f[0];
 #pragma unroll
-      for (int j = 0; j < V; ++j) { xmax = fmaxf(xmax, f[j]); xmin = fminf(xmin, f[j]); }
+      for (int j = 1; j < V; ++j) { m = fmaxf(m, f[j]); mn = fminf(mn, f[j]); }
+      if (m > xmax) { xmax = m; ivec = i; }
+      xmin = fminf(xmin, mn);
     }
     const float tmax = xmax;
     float vmax = warp_max(xmax), vmin = -warp_max(-xmin);
@@ -388,6 +411,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
     }
 
     publish_next();   // the scan above has covered the atomic's round trip
+    PP_WMARK(2);
 
     int best = 0;
     float best_val = 0.0f, score = vmax;
@@ -398,12 +422,10 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       // ---- B: the raw maximum p0 (lowest index) and a lower bound L of the convolved maximum
       int idx = 0x7fffffff;
       if (tmax == vmax) {
-        for (int i = tl; i < NV && idx == 0x7fffffff; i += S) {
-          float f[V];
-          unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+        float f[V];
+        unpack(*reinterpret_cast<const uint4*>(plane + ivec * V), f, T());
 #pragma unroll
-          for (int j = V - 1; j >= 0; --j) idx = (f[j] == vmax) ? i * V + j : idx;
-        }
+        for (int j = V - 1; j >= 0; --j) idx = (f[j] == vmax) ? ivec * V + j : idx;
       }
       int imax = __reduce_min_sync(0xffffffffu, idx);
       if (G > 1) {
@@ -430,6 +452,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
         L = e - fabsf(e) * 1e-6f - 1e-37f;
       }
 
+      PP_WMARK(3);
       // ---- C: bounding box of S = {h >= L}; p0 is in S, so the box is never empty
       int bx0 = W, bx1 = -1, by0 = H, by1 = -1;
       {
@@ -472,6 +495,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       const int ox1 = min(bx1 + r, W - 1), oy1 = min(by1 + r, H - 1);
       const int OW = ox1 - ox0 + 1, OH = oy1 - oy0 + 1;
 
+      PP_WMARK(4);
       // ---- D/E: separable float32 prefilter over the region, in bands of row pairs.
       // Band buffer: tmp[q][c] = column-pass values of rows (ya + 2q, ya + 2q + 1) at source column x = c - cbase
       // (reflected columns included); cbase is even so that a column task stores its 2 x 2 values with one 128-bit
@@ -537,6 +561,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
             }
           }
           team_sync<G>(team);
+          PP_WMARK(5);   // column passes (+ the row passes of all bands but the last)
           const int nq = (rows + 1) >> 1, ntask = nq * nxb;
           const unsigned mq = div_magic(nq);
           for (int t0 = 0; t0 < ntask; t0 += S) {   // whole warps: every lane joins the reduction of the round
@@ -580,6 +605,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
             }
           }
         }
+        PP_WMARK(6);
         if (collect) break;
         // prefilter maximum -> threshold; keep the listed pixels that are still inside the band
         float pm = gm;
@@ -617,6 +643,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       team_sync<G>(team);
       count = cand[kWCand];
 
+      PP_WMARK(7);
       // ---- G: exact values of the candidates and of the winner's four neighbours
       TeamExact<T> te;
       te.plane = plane; te.w2d = w2dk; te.ex = ex; te.H = H; te.W = W; te.r = r; te.d = d;
@@ -644,6 +671,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
         nb[0] = ev[1]; nb[1] = ev[2]; nb[2] = ev[3]; nb[3] = ev[4];
       }
       score = plane_value<T>(plane, best);
+      PP_WMARK(8);
     }
 
     // ---- H: outputs.  The x and y halves of the sub-pixel fit (heatmap.py:136-165, float32, the reference's
@@ -669,6 +697,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       }
     }
 
+    PP_WMARK(10);
     // ---- next heatmap: everybody is done with the plane, thread 0 starts the copy (an L2 hit by now)
     team_sync<G>(team);
     cur_item = ex->i[6][0];
@@ -679,5 +708,6 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
       tma_load_1d(slot, heatmaps + static_cast<size_t>(cur_hm) * HW, geo.plane_bytes, bar);
     }
     team_sync<G>(team);   // ex->i[6..7] are rewritten at the top of the next iteration
+    PP_WMARK(11);
   }
 }

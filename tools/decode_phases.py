@@ -15,7 +15,8 @@ DBG = Path("/tmp/libprobpose_b200_timing.so")
 
 
 def build():
-    srcs = [str(CSRC / f) for f in ("pp_api.cu", "pp_encode.cu", "pp_decode.cu", "pp_loss.cu")]
+    from probpose_pytorch_b200.build import SOURCES
+    srcs = [str(CSRC / f) for f in SOURCES]
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DPP_PHASE_TIMING",
            "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-shared", "-cudart", "static",
            "-o", str(DBG), *srcs]
@@ -39,8 +40,15 @@ def main():
     dev = torch.device("cuda")
     clean = am.encode_batch(kin, torch.ones((B, 17), device=dev))["heatmaps"]
     noise = torch.rand_like(clean) * 0.02
-    names = ["top/tables", "TMA wait", "scan A", "B: p0+L", "C: bbox", "D: gather/col", "E/F: prefilter", "candidates",
-             "G: exact cands", "neighbours", "H: outputs", "final barrier"]
+    import os
+    forced = os.environ.get("PP_DECODE_WARP", "1")
+    os.environ["PP_DECODE_WARP"] = forced           # the team kernel unless PP_DECODE_WARP=0 asks for the CTA kernel
+    if forced != "0":
+        names = ["top/tables", "TMA wait", "scan A (+publish)", "B: p0+L", "C: bbox", "column pass", "row pass", "candidates",
+                 "exact values", "-", "outputs", "end sync + TMA issue"]
+    else:
+        names = ["top/tables", "TMA wait", "scan A", "B: p0+L", "C: bbox", "D: gather/col", "E/F: prefilter", "candidates",
+                 "G: exact cands", "neighbours", "H: outputs", "final barrier"]
     buf = (C.c_ulonglong * 16)()
     for label, t in (("clean blobs (tile path)", clean), ("noise only (full path)", noise), ("zeros", torch.zeros_like(clean))):
         pm.decode_device(t)
@@ -50,7 +58,7 @@ def main():
         L.pp_debug_phase_cycles(buf, 1)
         n = 5 * B * 17
         tot = sum(buf[i] for i in range(12))
-        print(f"== {label}: {tot / n:9.0f} cycles per heatmap per CTA")
+        print(f"== {label}: {tot / n:9.0f} cycles per heatmap per CTA / team")
         for i, nm in enumerate(names):
             print(f"   {nm:16s} {buf[i] / n:9.0f}  {100 * buf[i] / max(tot, 1):5.1f}%")
 
