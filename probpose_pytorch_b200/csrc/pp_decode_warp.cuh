@@ -317,6 +317,11 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
 
   int k_loaded = -1, r = 1, d = 3, rf = 1, df = 3, nch4 = 1;
   float tail2d = 0.0f;
+  // Measured and rejected (tools/decode_phases.py shows 2.6 k cycles at the top of every heatmap for the dependent
+  // radius -> taps loads of a new channel, and 4.1 k in the exact evaluation's dependent table loads): prefetching
+  // the next channel's taps into registers a heatmap ahead and staging the d x d table in the idle band buffer
+  // shorten those phases but not the kernel (59.7 us / 158.6 us at B = 256 / 1024 against 58.2 / 151.3) -- with twelve
+  // warps per SM the waits are already covered by other warps, and the extra code costs issue slots.
   const double* w2dk = tab.kernel2d;
 
 #ifdef PP_PHASE_TIMING
