@@ -25,7 +25,7 @@ for f in sorted(glob.glob("gpurun_out/${L}_bench_*.json")):
           {k: (round(v["ms"] * 1e3, 1), round(v["frac"], 3)) for k, v in j["kernels"].items()},
           "e2e", round(j["e2e"]["value"] / 1e6, 2), "cpu", (j.get("cpu_baseline") or {}).get("value"))
 PY
-K='regex:encode_kernel|decode_expected|oks_loss_fast|finalize_kernel'
+K='regex:encode_kernel|decode_expected|oks_loss_fast|finalize_kernel|pack_records|mailbox'
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/${L}_launches_bench.csv \
     python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-graph --serial > gpurun_out/${L}_ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k "$K" -s 30 -c 4 -o gpurun_out/${L}_full -f \
