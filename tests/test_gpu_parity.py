@@ -1162,3 +1162,34 @@ def test_pack_records_and_single_process_mailbox(pp):
         mb.published(1)
         got, got_loss = mb.read(1)
         assert torch.equal(got.view(r.shape), r) and float(got[0, 0, 3]) == 0.5 + k and got_loss.item() == 3.0
+
+
+def test_expected_decoder_kernel_selection(pp, monkeypatch):
+    """pp_decode_expected_last_kernel reports the kernel the size rule picked: small batches take the CTA-per-heatmap
+    kernel, batches with at least two heatmaps per resident warp the warp-per-heatmap kernel, odd shapes the generic
+    one; both fast kernels agree bit for bit."""
+    from probpose_pytorch_b200 import _lib
+    wl = synth.WORKLOADS[2]
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    last = _lib.lib().pp_decode_expected_last_kernel
+    small = torch.rand(4, 17, 64, 48, device="cuda")
+    a = pm.decode_device(small)
+    assert last() == 1
+    monkeypatch.setenv("PP_DECODE_WARP", "1")
+    b = pm.decode_device(small)
+    assert last() == 2
+    monkeypatch.delenv("PP_DECODE_WARP")
+    for key in ("locs", "vals", "argmax", "keypoints"):
+        assert torch.equal(a[key], b[key]), key
+    big = torch.rand(256, 17, 64, 48, device="cuda") * 0.02
+    big[:, :, 30, 20] = 1.0
+    c = pm.decode_device(big)
+    assert last() == 2
+    monkeypatch.setenv("PP_DECODE_WARP", "0")
+    d = pm.decode_device(big)
+    assert last() == 1
+    for key in ("locs", "vals", "argmax", "keypoints"):
+        assert torch.equal(c[key], d[key]), key
+    monkeypatch.delenv("PP_DECODE_WARP")
+    l, v = pp.get_heatmap_expected_value(np.random.default_rng(3).random((5, 19, 27), dtype=np.float32), np.full(5, 0.07))
+    assert last() == 4
