@@ -1,4 +1,5 @@
-// Expected-OKS decoder, one WARP per heatmap (included into pp_decode.cu after pp_decode_fast.cuh, same namespace).
+// Expected-OKS decoder, one WARP (generally: a team of G warps) per heatmap.  Included into pp_decode.cu after
+// pp_decode_fast.cuh, same namespace.
 //
 // Why.  The CTA-per-heatmap kernel (pp_decode_fast.cuh) spends most of its time waiting: ncu capture J shows
 // 2.8 barrier-stall cycles per issued instruction, 1.5 no-instruction cycles (a 5.7 k-instruction kernel whose six
@@ -7,19 +8,24 @@
 // of the same does not help.  Here a heatmap belongs to ONE warp from its bulk copy to its outputs:
 //   * no __syncthreads anywhere after the prologue, no cross-warp reduction, no single-thread section that idles
 //     three other warps; warp-wide reductions are shuffles / redux;
-//   * a heatmap costs its plane + a 5 KB band buffer of shared memory (17.4 KB for 64x48 float32), so twelve
+//   * a heatmap costs its plane + a 4.6 KB band buffer of shared memory (17.9 KB for 64x48 float32), so twelve
 //     heatmaps are in flight per SM instead of six;
 //   * one code path for every map: the pruned region of the convolution (the neighbourhood of S = {h >= L}, see
-//     pp_decode_fast.cuh for the bound) is processed in row bands -- column pass from the plane into the band buffer
-//     (reflect in y by row index, reflected columns written by the producing lane), row pass from the band buffer
-//     with 128-bit windows.  Blob-shaped maps need one small band, flat / noisy maps four full-width ones;
-//   * the per-lane top three prefilter values are tracked in registers (the update runs only when a task's maximum
-//     beats the lane's third best), so nothing but the band buffer is ever stored;
+//     pp_decode_fast.cuh for the bound) is processed in bands of row pairs -- column pass from the plane into the band
+//     buffer (reflect in y through a CTA-wide row-offset table, reflected columns written by the producing lane), row
+//     pass from the band buffer with 128-bit windows, both on two-wide FFMA2.  Blob-shaped maps need one small band,
+//     flat / noisy maps four full-width ones; the wide kernels are prefiltered with their central taps only;
+//   * candidates come from a warp-wide running maximum (one shuffle reduction per round of row tasks): a task
+//     reports pixels only when it comes within the error band of it, into a 64-entry list that is filtered with the
+//     final threshold; nothing but the band buffer and that list is ever stored;
 //   * exact double-precision re-evaluation with the reference's d x d table, read through the read-only cache: the
 //     winner and its four neighbours share every tap load (5 DFMA per tap per lane).
 // The arithmetic of the prefilter (fmaf chains over zero-padded taps), the error band and the exact evaluation are
 // those of pp_decode_fast.cuh; only the order in which partial double sums meet differs (any order is within
 // 2^-50 of scipy's sum, far inside a float32 rounding cell).
+// G = 2 (two warps share a heatmap through a named barrier) is used for planes so large that fewer than ten fit on an
+// SM; at 64x48 it is slower than G = 1.  What was measured on the way, including everything that did not help, is in
+// profiles/r01s_summary.md.
 #pragma once
 
 // developer-only phase timing (see pp_decode_fast.cuh): lane 0 of every team accumulates cycles between marks
