@@ -21,6 +21,18 @@ int main(void) {
   if (rc == PP_OK) return 3;
   rc = pp_sparsemax_tail(NULL, NULL, NULL, PP_F32, 1, 0, 0.5f, 1.0f, NULL);
   if (rc == PP_OK) return 4;
+  {
+    pp_mailbox mb;
+    memset(&mb, 0, sizeof mb);
+    if (pp_mailbox_block_bytes(85) != 85 * 56 + 8 + 16) return 5;      /* records, pad to 16, loss + flag + pad */
+    if (pp_mailbox_block_bytes(4352) % 16 != 0) return 6;
+    rc = pp_pack_records(4, NULL, NULL, NULL, NULL, NULL, NULL, 1.0f, NULL, NULL, NULL);
+    if (rc == PP_OK) return 7;
+    rc = pp_mailbox_commit(&mb, 4, NULL, NULL);                          /* inconsistent (all-zero) mailbox */
+    if (rc == PP_OK) return 8;
+    if (pp_decode_expected_last_kernel() != -1) return 9;                /* nothing decoded on this thread yet */
+    printf("sizeof mailbox: %zu\n", sizeof mb);
+  }
   printf("sizeof encode/decode/loss params: %zu %zu %zu; version %d; last error: %s\n", sizeof ep, sizeof dp, sizeof lp,
          pp_version(), pp_last_error_string());
   return 0;

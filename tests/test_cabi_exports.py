@@ -115,3 +115,6 @@ def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "sizeof encode/decode/loss params: 44 48 72" in res.stdout
+    from probpose_pytorch_b200 import _lib
+    import ctypes
+    assert f"sizeof mailbox: {ctypes.sizeof(_lib.Mailbox)}" in res.stdout      # the ctypes mirror has the C layout
