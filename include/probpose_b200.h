@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 1
+#define PP_ABI_VERSION 2
 #define PP_MAX_OKS_RADIUS 9   /* ceil(3 * 3.0): s is clipped to [0.55, 3.0] (heatmap.py:178-179) */
 #define PP_OKS_TAPS (2 * PP_MAX_OKS_RADIUS + 1)
 #define PP_MAX_BLUR_KSIZE 31
@@ -54,6 +54,8 @@ typedef enum pp_dtype { PP_F32 = 0, PP_BF16 = 1, PP_F64 = 2 } pp_dtype;
 
 /* ---- library ---------------------------------------------------------- */
 PP_API int pp_version(void);
+/* hash of the CUDA sources this library was compiled from (the build passes it in); lets a binding detect a stale build */
+PP_API const char* pp_source_hash(void);
 PP_API const char* pp_last_error_string(void);
 /* number of SMs and opt-in shared memory per block of the current device */
 PP_API int pp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin_bytes);
@@ -90,7 +92,21 @@ typedef struct pp_oks_table {
                                packed row-major with row stride d = 2r+1 */
   const int32_t* order;     /* (K) channels sorted by decreasing radius (longest jobs first in the kernel's
                                work queue), or NULL for 0..K-1 */
+  /* Optional (both NULL = not available): the 1-D taps of every distinct channel folded with the 'reflect' boundary
+   * into banded Toeplitz matrices, float16, in the register-fragment order of mma.sync.m16n8k16 -- the operand tables
+   * of the tensor-core prefilter (csrc/pp_decode_mma.cuh).  Built on the device by pp_oks_mma_table_build for one
+   * (H, W); channels with identical taps share a table through mma_index. */
+  const void* mma_tables;   /* pp_oks_mma_table_bytes(U, H, W) bytes, 16-byte aligned */
+  const int32_t* mma_index; /* (K) table of channel k, in [0, U) */
+  int32_t mma_H, mma_W;     /* the heatmap shape the tables were built for (they are ignored for any other shape) */
 } pp_oks_table;
+
+/* Bytes of the tensor-core prefilter tables for U distinct channels of an H x W heatmap; 0 when the shape has no
+ * tensor-core kernel (then leave pp_oks_table.mma_tables NULL). */
+PP_API int64_t pp_oks_mma_table_bytes(int32_t U, int32_t H, int32_t W);
+/* Fill `out` (device) from the U distinct channels' taps_f32 rows (U, PP_OKS_TAPS) and radii (U), device pointers. */
+PP_API int pp_oks_mma_table_build(const float* taps_f32, const int32_t* radius, int32_t U, int32_t H, int32_t W,
+                                  void* out, pp_stream_t stream);
 
 typedef struct pp_decode_params {
   int32_t B, K, H, W;
@@ -106,6 +122,10 @@ typedef struct pp_decode_params {
  * kernel's work-queue counter; NULL is allowed (the heatmaps are then split statically, ~25 % slower on
  * mixed inputs). */
 PP_API int64_t pp_decode_expected_scratch_bytes(void);
+/* Scratch that additionally lets pp_decode_expected use the tensor-core prefilter kernel: 16 bytes + one int32 per
+ * heatmap (the list of heatmaps -- exact plateaus, maps without float32 dynamic range -- that it hands on to the
+ * general kernel).  With less scratch than this the general kernels run. */
+PP_API int64_t pp_decode_expected_scratch_bytes_for(const pp_decode_params* p);
 PP_API int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* table,
                        const void* heatmaps,
                        float* locs,        /* out (N, 2) sub-pixel argmax, heatmap px */
@@ -124,6 +144,7 @@ PP_API int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* tab
 #define PP_DECODE_KERNEL_TEAM 2     /* one warp (team) per heatmap, band-wise prefilter (pp_decode_warp.cuh) */
 #define PP_DECODE_KERNEL_DENSE 3    /* unpruned per-radius variant, PP_DECODE_DENSE=1 (pp_decode_dense.cuh) */
 #define PP_DECODE_KERNEL_GENERIC 4  /* unaligned / odd shapes */
+#define PP_DECODE_KERNEL_MMA 5      /* one warp per heatmap, tensor-core (mma.sync) Toeplitz prefilter (pp_decode_mma.cuh) */
 PP_API int pp_decode_expected_last_kernel(void);
 
 /* Number of floats of `conv_out` work space pp_decode_expected needs for this shape even when the

@@ -57,3 +57,4 @@ from .loss_oracle import oks_heatmap_loss, oks_heatmap_loss_grad_closed_form  # 
 from . import metrics_oracle  # noqa: F401
 from .sparsemax_oracle import head_tail_sparsemax, sparsemax, sparsemax_f64  # noqa: F401
 from .targets_oracle import error_from_heatmaps, oks_from_heatmaps  # noqa: F401
+from .probpose_loss_oracle import ProbPoseLossLayout, training_losses  # noqa: F401

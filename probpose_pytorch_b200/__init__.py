@@ -3,7 +3,8 @@
 Drop-in, same call signatures as zir-vision/ProbPose_pytorch for:
   * ``codec``   : ``generate_probmaps``, ``ProbMap``, ``ArgMaxProbMap``, ``Codec``
   * ``heatmap`` : ``get_heatmap_maximum``, ``get_heatmap_expected_value``
-  * ``loss``    : ``OKSHeatmapLoss``; ``probpose_loss``: ``ProbPoseLoss`` (+ ``BCELoss``, ``MSELoss``, ``L1LogLoss``)
+  * ``loss``    : ``OKSHeatmapLoss``; ``probpose_loss``: ``patch_probpose_loss`` (device-side members for the
+    reference's own ``ProbPoseLoss`` instance), ``ground_truth_from_keypoints``
   * ``metrics`` : ``pose_pck_accuracy``, ``keypoint_pck_accuracy``
   * ``head``    : ``heatmap_tail`` (tail of ``ProbMapHead.forward_heatmap``), ``Sparsemax``
 
@@ -16,9 +17,9 @@ from .codec import ArgMaxProbMap, Codec, ProbMap, generate_probmaps  # noqa: F40
 from .head import HeatmapTail, Sparsemax, heatmap_tail, patch_probmap_head  # noqa: F401
 from .heatmap import get_heatmap_expected_value, get_heatmap_maximum  # noqa: F401
 from .loss import OKSHeatmapLoss  # noqa: F401
-from .probpose_loss import BCELoss, L1LogLoss, MSELoss, ProbPoseLoss  # noqa: F401
+from .probpose_loss import FusedOKSHeatmapLoss, ground_truth_from_keypoints, patch_probpose_loss  # noqa: F401
 
 __all__ = ["ArgMaxProbMap", "Codec", "ProbMap", "generate_probmaps", "heatmap_tail", "HeatmapTail",
            "patch_probmap_head", "Sparsemax",
            "get_heatmap_expected_value", "get_heatmap_maximum", "OKSHeatmapLoss",
-           "ProbPoseLoss", "BCELoss", "MSELoss", "L1LogLoss"]
+           "FusedOKSHeatmapLoss", "patch_probpose_loss", "ground_truth_from_keypoints"]

@@ -13,6 +13,7 @@ import torch
 
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libprobpose_b200.so"
 
+PP_ABI_VERSION = 2
 PP_F32, PP_BF16, PP_F64 = 0, 1, 2
 PP_MAX_OKS_RADIUS = 9
 PP_OKS_TAPS = 2 * PP_MAX_OKS_RADIUS + 1
@@ -22,7 +23,8 @@ PP_UPSTREAM_SCALAR, PP_UPSTREAM_FULL = 0, 1
 
 #: every symbol include/probpose_b200.h declares
 EXPORTS = (
-    "pp_version", "pp_last_error_string", "pp_device_info", "pp_encode", "pp_decode_expected",
+    "pp_version", "pp_source_hash", "pp_last_error_string", "pp_device_info", "pp_encode", "pp_decode_expected",
+    "pp_oks_mma_table_bytes", "pp_oks_mma_table_build", "pp_decode_expected_scratch_bytes_for",
     "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes", "pp_decode_expected_last_kernel",
     "pp_heatmap_maximum", "pp_decode_argmax_dark", "pp_heatmap_tail", "pp_heatmap_tail_backward",
     "pp_sparsemax_tail", "pp_sparsemax_tail_backward",
@@ -40,7 +42,8 @@ class EncodeParams(C.Structure):
 
 
 class OksTable(C.Structure):
-    _fields_ = [("radius", C.c_void_p), ("taps_f32", C.c_void_p), ("kernel2d", C.c_void_p), ("order", C.c_void_p)]
+    _fields_ = [("radius", C.c_void_p), ("taps_f32", C.c_void_p), ("kernel2d", C.c_void_p), ("order", C.c_void_p),
+                ("mma_tables", C.c_void_p), ("mma_index", C.c_void_p), ("mma_H", C.c_int32), ("mma_W", C.c_int32)]
 
 
 class DecodeParams(C.Structure):
@@ -70,18 +73,28 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        try:  # a fresh checkout on a box with nvcc: build once, in-tree
-            from .build import build
+    # The library embeds a hash of the sources it was compiled from.  A missing or stale binary is rebuilt in-tree
+    # (nvcc is on every box this runs on; concurrent ranks are serialised by a file lock inside build()); if that is
+    # impossible the import fails -- an edited kernel never runs against an old binary, and there is no CPU fallback.
+    from .build import build, built_hash, source_hash
+    have = built_hash()
+    if have is None or have not in (source_hash(False), source_hash(True)):
+        try:
             build()
         except Exception as e:
             raise RuntimeError(
-                f"{LIB_PATH} is missing and could not be built ({e}): run `python -m probpose_pytorch_b200.build`.  "
-                "There is no CPU fallback.") from e
+                f"{LIB_PATH} is {'missing' if have is None else 'stale (built from other sources)'} and could not be "
+                f"built ({e}): run `python -m probpose_pytorch_b200.build`.  There is no CPU fallback.") from e
     L = C.CDLL(str(LIB_PATH))
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     L.pp_version.restype = C.c_int
     L.pp_last_error_string.restype = C.c_char_p
+    L.pp_source_hash.restype = C.c_char_p
+    L.pp_oks_mma_table_bytes.argtypes = [i32, i32, i32]
+    L.pp_oks_mma_table_bytes.restype = i64
+    L.pp_oks_mma_table_build.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.pp_decode_expected_scratch_bytes_for.argtypes = [C.POINTER(DecodeParams)]
+    L.pp_decode_expected_scratch_bytes_for.restype = i64
     L.pp_device_info.argtypes = [vp, vp, vp, vp]
     L.pp_encode.argtypes = [C.POINTER(EncodeParams), vp, vp, vp, vp, vp, vp, vp, vp]
     L.pp_decode_expected.argtypes = [C.POINTER(DecodeParams), C.POINTER(OksTable), vp, vp, vp, vp, vp, vp, vp, i64, vp]
@@ -113,12 +126,13 @@ def lib() -> C.CDLL:
     L.pp_mailbox_wait.argtypes = [vp, i32, i32, i64, C.c_uint32, i64, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("pp_version", "pp_last_error_string", "pp_oks_loss_scratch_bytes",
+        if name not in ("pp_version", "pp_source_hash", "pp_last_error_string", "pp_oks_loss_scratch_bytes",
+                        "pp_oks_mma_table_bytes", "pp_decode_expected_scratch_bytes_for",
                         "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes",
                         "pp_mailbox_block_bytes"):
             fn.restype = C.c_int
-    if L.pp_version() != 1:
-        raise RuntimeError(f"{LIB_PATH}: ABI version {L.pp_version()} != 1; rebuild the extension")
+    if L.pp_version() != PP_ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH}: ABI version {L.pp_version()} != {PP_ABI_VERSION}; rebuild the extension")
     _lib = L
     return L
 

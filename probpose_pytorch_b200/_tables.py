@@ -63,6 +63,33 @@ class OksKernelTable:
         self.max_radius = int(radius.max())
         # work-queue order of the decoder: widest kernels (most expensive heatmaps) first
         self.order = torch.from_numpy(np.argsort(-radius, kind="stable").astype(np.int32)).to(device)
+        # operand tables of the tensor-core prefilter (csrc/pp_decode_mma.cuh): one per distinct (radius, taps) row,
+        # built on the device by the library for the shapes it has such a kernel for
+        self.mma_tables = self.mma_index = None
+        self.shape = (H, W)
+        uniq, index = np.unique(np.concatenate([radius[:, None].astype(np.float32), taps], axis=1), axis=0,
+                                return_inverse=True)
+        U = int(uniq.shape[0])
+        from . import _lib
+        nbytes = int(_lib.lib().pp_oks_mma_table_bytes(U, H, W)) if device.type == "cuda" else 0
+        if nbytes > 0:
+            u_taps = torch.from_numpy(np.ascontiguousarray(uniq[:, 1:])).to(device)
+            u_radius = torch.from_numpy(uniq[:, 0].astype(np.int32)).to(device)
+            tables = torch.empty(nbytes // 2, dtype=torch.float16, device=device)
+            with torch.cuda.device(device):
+                rc = _lib.lib().pp_oks_mma_table_build(_lib.ptr(u_taps), _lib.ptr(u_radius), U, H, W, _lib.ptr(tables),
+                                                       _lib.stream_ptr(device))
+            _lib.check(rc, "pp_oks_mma_table_build")
+            self.mma_tables = tables
+            self.mma_index = torch.from_numpy(index.reshape(-1).astype(np.int32)).to(device)
+
+    def descriptor(self):
+        """The ``pp_oks_table`` struct for this table."""
+        from . import _lib
+        H, W = self.shape
+        return _lib.OksTable(self.radius.data_ptr(), self.taps.data_ptr(), self.kernel2d.data_ptr(), self.order.data_ptr(),
+                             self.mma_tables.data_ptr() if self.mma_tables is not None else None,
+                             self.mma_index.data_ptr() if self.mma_index is not None else None, H, W)
 
 
 def gaussian_taps(ksize: int) -> np.ndarray:

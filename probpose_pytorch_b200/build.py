@@ -3,10 +3,17 @@
 nvcc cross-compiles for sm_100a without a GPU.  The resulting
 ``csrc/libprobpose_b200.so`` has no dependency on torch or Python (cudart is
 linked statically) and is git-ignored but travels to the GPU box with the tree.
+
+The library carries a hash of the sources it was compiled from
+(``pp_source_hash()``); ``_lib.lib()`` compares it with the tree on every import,
+so an edited ``.cu`` / ``.cuh`` can never run against a stale binary.  Builds are
+serialised with a file lock (several ranks of a ``torchrun`` may import at once).
 """
 
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -14,6 +21,7 @@ import sys
 from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
+ROOT = CSRC.parents[1]
 LIB = CSRC / "libprobpose_b200.so"
 SOURCES = ["pp_api.cu", "pp_encode.cu", "pp_decode.cu", "pp_loss.cu", "pp_targets.cu", "pp_sparsemax.cu", "pp_metrics.cu", "pp_records.cu"]
 NVCC_FLAGS = [
@@ -31,46 +39,77 @@ def _nvcc() -> str:
     return cand
 
 
-def _stale() -> bool:
+def _deps(experiments: bool = False) -> list[Path]:
+    deps = [CSRC / s for s in SOURCES] + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "probpose_b200.h"]
+    if experiments:
+        deps += sorted((ROOT / "tools" / "experiments").glob("*.cuh"))
+    return deps
+
+
+def source_hash(experiments: bool = False) -> str:
+    """sha256 over the CUDA sources, the header and the compiler flags (16 hex digits)."""
+    h = hashlib.sha256()
+    for d in _deps(experiments):
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16] + ("+x" if experiments else "")
+
+
+def built_hash() -> str | None:
+    """The source hash embedded in the existing library, or None (no library / unreadable)."""
     if not LIB.exists():
-        return True
-    t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + [CSRC.parents[1] / "include" / "probpose_b200.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+        return None
+    import ctypes
+    try:
+        L = ctypes.CDLL(str(LIB))
+        L.pp_source_hash.restype = ctypes.c_char_p
+        return L.pp_source_hash().decode()
+    except (OSError, AttributeError):
+        return None
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a and link ``libprobpose_b200.so``."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a and link ``libprobpose_b200.so`` (no-op when the
+    existing library was built from the current sources)."""
+    want = source_hash(experiments)
+    if not force and built_hash() == want:
         return LIB
     nvcc = _nvcc()
     objdir = CSRC / "build"
     objdir.mkdir(exist_ok=True)
-    procs = []
-    for src in SOURCES:
-        obj = objdir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    objs = []
-    for src, obj, pr in procs:
-        out, _ = pr.communicate()
-        if verbose or pr.returncode:
-            sys.stderr.write(out)
-        if pr.returncode:
-            raise RuntimeError(f"nvcc failed on {src}")
-        objs.append(str(obj))
-    tmp = LIB.with_suffix(".so.tmp")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-            "-Xcompiler", "-fPIC", "-o", str(tmp), *objs]
-    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode:
-        sys.stderr.write(res.stdout)
-        raise RuntimeError("link of libprobpose_b200.so failed")
-    os.replace(tmp, LIB)
+    with open(objdir / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and built_hash() == want:   # another process built it while we waited
+            return LIB
+        flags = list(NVCC_FLAGS) + (["-DPP_EXPERIMENTS"] if experiments else [])
+        procs = []
+        for src in SOURCES:
+            obj = objdir / (Path(src).stem + ".o")
+            cmd = [nvcc, *flags, "-c", str(CSRC / src), "-o", str(obj)]
+            if src == "pp_api.cu":
+                cmd.insert(1, f'-DPP_SOURCE_HASH="{want}"')
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs = []
+        for src, obj, pr in procs:
+            out, _ = pr.communicate()
+            if verbose or pr.returncode:
+                sys.stderr.write(out)
+            if pr.returncode:
+                raise RuntimeError(f"nvcc failed on {src}")
+            objs.append(str(obj))
+        tmp = LIB.with_suffix(".so.tmp")
+        link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+                "-Xcompiler", "-fPIC", "-o", str(tmp), *objs]
+        res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode:
+            sys.stderr.write(res.stdout)
+            raise RuntimeError("link of libprobpose_b200.so failed")
+        os.replace(tmp, LIB)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))

@@ -93,6 +93,11 @@ extern "C" {
 
 int pp_version(void) { return PP_ABI_VERSION; }
 
+#ifndef PP_SOURCE_HASH
+#define PP_SOURCE_HASH "unknown"
+#endif
+const char* pp_source_hash(void) { return PP_SOURCE_HASH; }
+
 const char* pp_last_error_string(void) { return g_error; }
 
 int pp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin_bytes) {

@@ -421,8 +421,11 @@ decode_expected_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict
 }
 
 #include "pp_decode_fast.cuh"
-#include "pp_decode_dense.cuh"
+#ifdef PP_EXPERIMENTS   // measured-and-rejected variants live in tools/experiments, outside the default build
+#include "../../tools/experiments/pp_decode_dense.cuh"
+#endif
 #include "pp_decode_warp.cuh"
+#include "pp_decode_mma.cuh"
 
 // ---------------------------------------------------------------------------
 // generic exact path: full convolved map (return_heatmap=True, or maps too large for shared memory)
@@ -839,6 +842,7 @@ bool warp_geometry(const pp_decode_params& p, const void* heatmaps, WarpGeom* ou
   return ok;
 }
 
+#ifdef PP_EXPERIMENTS
 // Shared-memory layout of the dense decoder; false when the shape / alignment rules it out.
 template <typename T>
 bool dense_geometry(const pp_decode_params& p, const void* heatmaps, DenseGeom* out, size_t* smem_bytes) {
@@ -868,6 +872,41 @@ bool dense_geometry(const pp_decode_params& p, const void* heatmaps, DenseGeom* 
   *out = geo;
   *smem_bytes = smem;
   return ok;
+}
+#endif
+
+// Launch of the tensor-core kernel for the shapes it is instantiated for; PP_ERR_UNSUPPORTED_SHAPE otherwise.
+template <typename T, int H, int W, int WPC, int MINB>
+int mma_launch_shape(const pp_decode_params& p, const pp_oks_table& tab, const T* hm, float* locs, float* vals,
+                     int32_t* argmax, double* keypoints, unsigned* scratch, float* dbg, cudaStream_t st) {
+  const int64_t N = static_cast<int64_t>(p.B) * p.K;
+  MmaGeom geo{};
+  geo.plane_bytes = static_cast<unsigned>(sizeof(T) * H * W);
+  geo.cand_off = (geo.plane_bytes + 15) / 16 * 16;
+  geo.slot_bytes = (geo.cand_off + static_cast<unsigned>(sizeof(int)) * (2 * kWCand + 4) + 127) / 128 * 128;
+  geo.div_W = div_magic(static_cast<unsigned>(W));
+  const size_t smem = static_cast<size_t>(WPC) * geo.slot_bytes;
+  auto kern = decode_expected_mma_kernel<T, H, W, WPC, MINB>;
+  int per = 0;
+  if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), 32 * WPC, smem, &per)) return rc;
+  if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) per = std::min(per, cap);
+  int grid = static_cast<int>(std::min<int64_t>((N + WPC - 1) / WPC, static_cast<int64_t>(pp_sm_count()) * per));
+  if (const int cap = pp_env_int("PP_DECODE_GRID", 0); cap > 0) grid = std::min(grid, cap);   // test hook: many heatmaps per warp
+  PP_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(unsigned) * kMmaScratchHead, st));
+  if (pp_env_int("PP_DEBUG", 0))
+    fprintf(stderr, "[pp] decode_expected_mma_kernel %dx%d grid=%d threads=%d smem=%zu ctas/sm=%d\n", H, W, grid, 32 * WPC, smem, per);
+  kern<<<grid, 32 * WPC, smem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, geo, scratch, dbg);
+  PP_CUDA_OK(cudaGetLastError());
+  return PP_OK;
+}
+
+template <typename T>
+int mma_launch(const pp_decode_params& p, const pp_oks_table& tab, const T* hm, float* locs, float* vals, int32_t* argmax,
+               double* keypoints, unsigned* scratch, float* dbg, cudaStream_t st) {
+  if (!pp_aligned16(hm) || (p.apply_tail && !(p.temperature > 0.0f))) return PP_ERR_UNSUPPORTED_SHAPE;
+  if (p.H == 64 && p.W == 48) return mma_launch_shape<T, 64, 48, 4, 4>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
+  if (p.H == 96 && p.W == 72) return mma_launch_shape<T, 96, 72, 4, 2>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
+  return PP_ERR_UNSUPPORTED_SHAPE;
 }
 
 thread_local int g_last_expected_kernel = -1;   // PP_DECODE_KERNEL_* of this thread's most recent pp_decode_expected
@@ -899,48 +938,78 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   const int threads = pick_threads(p.H, p.W);
 
   // team-per-heatmap kernel (pp_decode_warp.cuh): G warps own a heatmap from its bulk copy to its outputs.  With
-  // G = 1 (default) it has the best throughput (7.6 ns per heatmap on the mixed C2 inputs against 13.4 ns for the
-  // CTA-per-heatmap kernel below) but the longest single-heatmap latency, so it takes over once every team has at
-  // least two heatmaps to work on; smaller batches stay with the CTA-per-heatmap kernel (measured cross-over between
+  // G = 1 it has a better throughput than the CTA-per-heatmap kernel below but the longest single-heatmap latency, so
+  // among the two it takes over once every team has at least two heatmaps to work on (measured cross-over between
   // 2176 and 4352 heatmaps of 64x48, profiles/r01s_summary.md).  PP_DECODE_WARP=0 / 1 forces the choice,
-  // PP_DECODE_TEAM selects G (1 or 2).
+  // PP_DECODE_TEAM selects G (1 or 2).  It is also the kernel that decodes the heatmaps the tensor-core kernel hands
+  // on (`list`).
   WarpGeom wgeo{};
-  const int want_warp = pp_env_int("PP_DECODE_WARP", -1);
-  if (want_warp != 0 && !pp_env_int("PP_DECODE_DENSE", 0) && warp_geometry<T>(p, heatmaps, &wgeo)) {
-    constexpr int kTPC = 2;
+  const bool warp_ok = warp_geometry<T>(p, heatmaps, &wgeo);
+  constexpr int kTPC = 2;
+  int wG = 1, wper = 0;
+  size_t wsmem = 0;
+  const void* wfn = nullptr;
+  if (warp_ok) {
     wgeo.rowoff_off = static_cast<unsigned>(kTPC) * wgeo.slot_bytes;
     wgeo.full_taps = pp_env_int("PP_DECODE_FULLTAPS", 0) ? 1u : 0u;
-    const size_t wsmem = wgeo.rowoff_off + sizeof(int) * static_cast<size_t>(p.H + 2 * kWRowPad);
+    wsmem = wgeo.rowoff_off + sizeof(int) * static_cast<size_t>(p.H + 2 * kWRowPad);
     // warps per heatmap: one while a dozen heatmaps fit on an SM (64x48 float32: 12); larger planes leave room for
     // fewer heatmaps, and two warps each then keep the SM's schedulers fed (96x72 float32, 6 heatmaps per SM:
     // 202 us with two warps, 237 us with one, 232 us for the CTA-per-heatmap kernel; profiles/r01s_summary.md)
-    int G = pp_env_int("PP_DECODE_TEAM", 0);
-    if (G != 1 && G != 2) {
+    wG = pp_env_int("PP_DECODE_TEAM", 0);
+    if (wG != 1 && wG != 2) {
       const int64_t slots = (static_cast<int64_t>(pp_smem_optin()) + 1024) / static_cast<int64_t>(wsmem + 1024) * kTPC;
-      G = slots >= 10 ? 1 : 2;
+      wG = slots >= 10 ? 1 : 2;
     }
-    const void* fn = G == 1 ? reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 1, kTPC>)
-                            : reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 2, kTPC>);
-    const int threads = 32 * G * kTPC;
-    int wper = 0;
-    if (wsmem + 2048 <= static_cast<size_t>(pp_smem_optin()) && pp_configure_kernel(fn, threads, wsmem, &wper) == PP_OK &&
-        wper * kTPC >= 6 && (want_warp == 1 || N >= 2ll * pp_sm_count() * wper * kTPC)) {
-      if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) wper = std::min(wper, cap);
-      const int wgrid = static_cast<int>(std::min<int64_t>((N + kTPC - 1) / kTPC, static_cast<int64_t>(pp_sm_count()) * wper));
-      unsigned* counter = (scratch && scratch_bytes >= 4) ? static_cast<unsigned*>(scratch) : nullptr;
-      if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
-      if (pp_env_int("PP_DEBUG", 0))
-        fprintf(stderr, "[pp] decode_expected_warp_kernel G=%d grid=%d threads=%d smem=%zu ctas/sm=%d\n", G, wgrid, threads, wsmem, wper);
-      g_last_expected_kernel = PP_DECODE_KERNEL_TEAM;
-      if (G == 1)
-        decode_expected_warp_kernel<T, 1, kTPC><<<wgrid, threads, wsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, wgeo, counter);
-      else
-        decode_expected_warp_kernel<T, 2, kTPC><<<wgrid, threads, wsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, wgeo, counter);
-      PP_CUDA_OK(cudaGetLastError());
-      return PP_OK;
+    wfn = wG == 1 ? reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 1, kTPC>)
+                  : reinterpret_cast<const void*>(decode_expected_warp_kernel<T, 2, kTPC>);
+  }
+  const bool warp_fits = warp_ok && wsmem + 2048 <= static_cast<size_t>(pp_smem_optin()) &&
+                         pp_configure_kernel(wfn, 32 * wG * kTPC, wsmem, &wper) == PP_OK && wper * kTPC >= 6;
+  auto launch_warp = [&](int grid, unsigned* counter, const int* list, const unsigned* list_count) -> int {
+    if (pp_env_int("PP_DEBUG", 0))
+      fprintf(stderr, "[pp] decode_expected_warp_kernel G=%d grid=%d threads=%d smem=%zu ctas/sm=%d list=%d\n", wG, grid,
+              32 * wG * kTPC, wsmem, wper, list != nullptr);
+    if (wG == 1)
+      decode_expected_warp_kernel<T, 1, kTPC><<<grid, 32 * wG * kTPC, wsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, wgeo, counter, list, list_count);
+    else
+      decode_expected_warp_kernel<T, 2, kTPC><<<grid, 32 * wG * kTPC, wsmem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, wgeo, counter, list, list_count);
+    PP_CUDA_OK(cudaGetLastError());
+    return PP_OK;
+  };
+
+  // tensor-core kernel (pp_decode_mma.cuh): one warp per heatmap, the whole separable prefilter as two banded
+  // Toeplitz GEMMs on mma.sync; needs the per-channel operand tables (pp_oks_mma_table_build) for exactly this
+  // shape, scratch for the hand-over list and the team kernel above for the heatmaps on that list.
+  // PP_DECODE_MMA=0 disables it; PP_DECODE_WARP=0 / 1 (a forced choice among the general kernels) does too.
+  const int want_warp = pp_env_int("PP_DECODE_WARP", -1);
+  if (warp_fits && want_warp < 0 && pp_env_int("PP_DECODE_MMA", 1) && tab.mma_tables && tab.mma_index &&
+      tab.mma_H == p.H && tab.mma_W == p.W && pp_aligned16(tab.mma_tables) && scratch &&
+      scratch_bytes >= static_cast<int64_t>(sizeof(unsigned)) * (kMmaScratchHead + N) && N < (1ll << 31)) {
+    int rc = mma_launch<T>(p, tab, hm, locs, vals, argmax, keypoints, static_cast<unsigned*>(scratch), nullptr, st);
+    if (rc == PP_OK) {
+      // second, usually empty, launch: the heatmaps the tensor-core kernel could not rank (plateaus, no dynamic range)
+      unsigned* words = static_cast<unsigned*>(scratch);
+      const int cap = pp_env_int("PP_DECODE_RETRY_GRID", 0);
+      const int rgrid = static_cast<int>(std::min<int64_t>((N + kTPC - 1) / kTPC, cap > 0 ? cap : pp_sm_count()));
+      g_last_expected_kernel = PP_DECODE_KERNEL_MMA;
+      return launch_warp(rgrid, words + 1, reinterpret_cast<const int*>(words + kMmaScratchHead), words + 2);
     }
+    if (rc != PP_ERR_UNSUPPORTED_SHAPE) return rc;
   }
 
+  if (want_warp != 0 && warp_fits && (want_warp == 1 || N >= 2ll * pp_sm_count() * wper * kTPC)) {
+    int per = wper;
+    if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) per = std::min(per, cap);
+    int wgrid = static_cast<int>(std::min<int64_t>((N + kTPC - 1) / kTPC, static_cast<int64_t>(pp_sm_count()) * per));
+    if (const int cap = pp_env_int("PP_DECODE_GRID", 0); cap > 0) wgrid = std::min(wgrid, cap);   // test hook: many heatmaps per team
+    unsigned* counter = (scratch && scratch_bytes >= 4) ? static_cast<unsigned*>(scratch) : nullptr;
+    if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+    g_last_expected_kernel = PP_DECODE_KERNEL_TEAM;
+    return launch_warp(wgrid, counter, nullptr, nullptr);
+  }
+
+#ifdef PP_EXPERIMENTS
   // dense kernel (pp_decode_dense.cuh): the whole separable prefilter, specialised per radius; at least two CTAs
   // per SM must fit, otherwise the pruned kernel below takes over
   DenseGeom dgeo{};
@@ -958,6 +1027,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
     PP_CUDA_OK(cudaGetLastError());
     return PP_OK;
   }
+#endif
 
   // pruned kernel: TMA-staged plane, convolution pruned to the neighbourhood of {h >= L} when possible
   FastGeom geo{};
@@ -968,8 +1038,8 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
     if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_expected_fast_kernel<T>), kFThreads, fsmem, &fper))
       return rc;
     if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) fper = std::min(fper, cap);
-    int64_t fgrid64 = std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper);
-    const int fgrid = static_cast<int>(fgrid64);
+    int fgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper));
+    if (const int cap = pp_env_int("PP_DECODE_GRID", 0); cap > 0) fgrid = std::min(fgrid, cap);   // test hook: many heatmaps per CTA
     unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;
     if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
     g_last_expected_kernel = PP_DECODE_KERNEL_CTA;
@@ -999,7 +1069,8 @@ int launch_decode_dark(const pp_decode_params& p, const float* taps, int ksize, 
       int fper = 1;
       if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_dark_fast_kernel<T>), kFThreads, fsmem, &fper))
         return rc;
-      const int fgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper));
+      int fgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper));
+      if (const int cap = pp_env_int("PP_DARK_GRID", 0); cap > 0) fgrid = std::min(fgrid, cap);   // test hook: many heatmaps per CTA
       unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;
       if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
       decode_dark_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, taps, ksize, static_cast<const T*>(heatmaps), peaks,
@@ -1057,6 +1128,31 @@ extern "C" {
 
 int64_t pp_decode_expected_scratch_bytes(void) { return 16; }
 
+int64_t pp_decode_expected_scratch_bytes_for(const pp_decode_params* p) {
+  if (!p || p->B < 0 || p->K < 0) return 16;
+  return static_cast<int64_t>(sizeof(unsigned)) * (kMmaScratchHead + static_cast<int64_t>(p->B) * p->K);
+}
+
+int64_t pp_oks_mma_table_bytes(int32_t U, int32_t H, int32_t W) {
+  if (U <= 0) return 0;
+  if (H == 64 && W == 48) return static_cast<int64_t>(U) * (MmaShape<64, 48>::kT1 + MmaShape<64, 48>::kT2) * 16;
+  if (H == 96 && W == 72) return static_cast<int64_t>(U) * (MmaShape<96, 72>::kT1 + MmaShape<96, 72>::kT2) * 16;
+  return 0;
+}
+
+int pp_oks_mma_table_build(const float* taps_f32, const int32_t* radius, int32_t U, int32_t H, int32_t W, void* out,
+                           pp_stream_t stream) {
+  PP_REQUIRE(taps_f32 && radius && out && U > 0, PP_ERR_INVALID_ARG, "pp_oks_mma_table_build: null argument");
+  PP_REQUIRE(pp_oks_mma_table_bytes(U, H, W) > 0, PP_ERR_UNSUPPORTED_SHAPE,
+             "pp_oks_mma_table_build: no tensor-core decoder for %dx%d maps", H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = std::min(U * 8, 1024);
+  if (H == 64) build_mma_tables_kernel<64, 48><<<grid, 256, 0, st>>>(taps_f32, radius, U, static_cast<__half*>(out));
+  else build_mma_tables_kernel<96, 72><<<grid, 256, 0, st>>>(taps_f32, radius, U, static_cast<__half*>(out));
+  PP_CUDA_OK(cudaGetLastError());
+  return PP_OK;
+}
+
 int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* table, const void* heatmaps, float* locs,
                        float* vals, int32_t* argmax, double* keypoints, float* conv_out, void* scratch,
                        int64_t scratch_bytes, pp_stream_t stream) {
@@ -1071,6 +1167,26 @@ int pp_decode_expected(const pp_decode_params* p, const pp_oks_table* table, con
 }
 
 int pp_decode_expected_last_kernel(void) { return g_last_expected_kernel; }
+
+// Test hook (not part of the ABI header): runs the tensor-core kernel and additionally writes its float16 / float32
+// proposal values, mapped back to the heatmap's units, into `prefilter` (N, H, W) -- tests/test_gpu_parity.py checks
+// the rigorous error bound kMmaErr against the oracle's exact convolution with it.  Heatmaps that the kernel hands on
+// keep their `prefilter` plane untouched and their outputs unwritten.
+__attribute__((visibility("default"))) int pp_debug_decode_mma_prefilter(const pp_decode_params* p, const pp_oks_table* table,
+                                                                         const void* heatmaps, float* locs, float* vals,
+                                                                         int32_t* argmax, float* prefilter, void* scratch,
+                                                                         int64_t scratch_bytes, pp_stream_t stream) {
+  if (int rc = check_decode_params("pp_debug_decode_mma_prefilter", p)) return rc;
+  PP_REQUIRE(table && table->mma_tables && table->mma_index && heatmaps && locs && vals && prefilter && scratch &&
+                 scratch_bytes >= pp_decode_expected_scratch_bytes_for(p),
+             PP_ERR_INVALID_ARG, "pp_debug_decode_mma_prefilter: null argument / scratch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->heatmap_dtype == PP_F32)
+    return mma_launch<float>(*p, *table, static_cast<const float*>(heatmaps), locs, vals, argmax, nullptr,
+                             static_cast<unsigned*>(scratch), prefilter, st);
+  return mma_launch<__nv_bfloat16>(*p, *table, static_cast<const __nv_bfloat16*>(heatmaps), locs, vals, argmax, nullptr,
+                                   static_cast<unsigned*>(scratch), prefilter, st);
+}
 
 int64_t pp_decode_expected_workspace_floats(const pp_decode_params* p) {
   if (!p || p->H < 1 || p->W < 1) return 0;

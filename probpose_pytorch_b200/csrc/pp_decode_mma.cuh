@@ -1,0 +1,450 @@
+// Expected-OKS decoder with a tensor-core prefilter: one warp per heatmap, the separable OKS convolution of the WHOLE
+// map evaluated as two small banded-Toeplitz GEMMs on mma.sync.m16n8k16 (f16 x f16 -> f32, SASS HMMA.16816.F32).
+// Included into pp_decode.cu after pp_decode_warp.cuh, same namespace.
+//
+// Why.  The pruned float32 prefilter of pp_decode_warp.cuh costs 4.4 k warp instructions per 64x48 heatmap on blob-shaped
+// maps and about twice that on flat / noise-only maps (bounding box of {h >= L}, region set-up, banded column and row
+// passes, candidate tracking), runs at 41 % issue utilisation with twelve warps per SM and has a long tail at small
+// batches (profiles/r01s_summary.md).  The convolution with reflect boundaries is a product with two constant banded
+// matrices per channel,
+//        R = Ty . H . Tx^T,      Tx[x'][x] = sum of the 1-D taps j with reflect(x' + j - r) == x   (same for Ty),
+// i.e. 0.3 MFLOP per 64x48 map: 116 HMMA instructions of one warp instead of ~1800 two-wide FFMAs plus their shared
+// memory traffic -- and the same 116 for every map, so there is no bounding box, no region logic and no tail.  The
+// tensor cores only PROPOSE candidates; every decision is made on exact values:
+//   * h is shifted and scaled into [0, 1) (h~ = (h - min h) * 2^k: the convolution commutes with both, the taps sum to
+//     one in every folded row) and rounded to float16, as are the folded taps and the intermediate; accumulation is
+//     float32.  With u = 2^-11: |Z(p) - R(p) 2^k - const| <= E = (4 u + slack) for every pixel, rigorous, see kMmaErr;
+//   * a pixel can only be the exact argmax if Z(p) >= max Z - 2 E - (float32 rounding of R): those pixels -- one to
+//     three on blob-shaped maps, a handful on noise -- are re-evaluated in float64 with the reference's own d x d table
+//     (NumPy tie-break), as are the winner's four neighbours for the float32 sub-pixel fit in the reference's operation
+//     order.  That part is pp_decode_warp.cuh's;
+//   * maps that defeat the proposal step (more than kWCand near-maximal pixels: exact plateaus wider than the kernel,
+//     heavily quantised maps; or no float32 dynamic range at all) are appended to a list in global memory and decoded
+//     by decode_expected_warp_kernel in a second, usually empty, launch.
+// Data flow of one heatmap (64x48 float32): TMA bulk copy of the plane into the warp's 12 KB slot -> one 128-bit scan
+// (min / max) -> 48 64-bit loads, scale + convert into the 48 B-fragment registers of H^T (the warp now holds the whole
+// map in float16) -> per block of 16 output columns: GEMM 1 (Y^T = Tx . H^T, <= 3 x 8 HMMA, A-fragments of Tx from a
+// per-channel table in L1 / L2), accumulators repacked in registers into the A-fragments of GEMM 2 (the C layout of two
+// adjacent n-blocks IS the A layout of one k-block), GEMM 2 (Z^T = Y^T . Ty^T, B-fragments of Ty from the table),
+// running maximum + candidate list.  No shared-memory writes besides the candidate list.
+#pragma once
+
+#include <cuda_fp16.h>
+
+// Rigorous bound of |Z - (exact scaled value) - constant|, in units of the scaled range (h~ in [0, 1)):
+//   h~ -> f16: u h~ + eta;  folded taps -> f16: u t + eta;  GEMM 1 in f32: gamma;  Y -> f16: u Y + eta;  GEMM 2: gamma
+//   => (4 u + 2 gamma) + (W + H + 4) eta + |g (x) g - k2d| (1.3e-7),  u = 2^-11 = 4.88e-4, eta = 2^-25 (f16 subnormal
+//   half-spacing), gamma <= 64 * 2^-22 (truncating float32 accumulation of at most 96 products).  4 u = 1.953e-3.
+constexpr float kMmaErr = 2.2e-3f;
+
+template <int HH, int WW>
+struct MmaShape {
+  static constexpr int H = HH, W = WW;
+  static constexpr int MB = (W + 15) / 16;   // blocks of 16 output columns x' (M of both GEMMs)
+  static constexpr int KB = MB;              // blocks of 16 input columns x (K of GEMM 1)
+  static constexpr int NB = H / 8;           // blocks of 8 rows (N of both GEMMs)
+  static constexpr int NBP = NB / 2;
+  static constexpr int KB2 = H / 16;         // blocks of 16 input rows y (K of GEMM 2)
+  static constexpr int kT1 = MB * KB * 32;   // uint4 (8 halves) per channel: A-fragments of Tx, [mb][kb][lane]
+  static constexpr int kT2 = KB2 * NBP * 32; // uint4 per channel: B-fragments of Ty for n-block pairs, [kb2][nbp][lane]
+  static_assert(H % 16 == 0 && W % 8 == 0, "shape not tiled by the fragments");
+};
+
+// ---- operand tables (built once per codec and shape by pp_oks_mma_table_build) ----
+__device__ __forceinline__ float folded_tap(const float* __restrict__ g, int r, int n, int o, int i) {
+  float s = 0.0f;   // entry [o][i] of the reflect-folded Toeplitz matrix of taps g (radius r) on an axis of length n
+  for (int j = 0; j <= 2 * r; ++j)
+    if (reflect1(o + j - r, n) == i) s += g[j];
+  return s;
+}
+
+template <int H, int W>
+__global__ void __launch_bounds__(256)
+build_mma_tables_kernel(const float* __restrict__ taps, const int* __restrict__ radius, int U, __half* __restrict__ out) {
+  using S = MmaShape<H, W>;
+  constexpr int per = (S::kT1 + S::kT2) * 8;   // halves per channel
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < static_cast<long long>(U) * per;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(idx / per);
+    int e = static_cast<int>(idx - static_cast<long long>(u) * per);
+    const float* g = taps + u * PP_OKS_TAPS;
+    const int r = radius[u];
+    float v = 0.0f;
+    if (e < S::kT1 * 8) {
+      // A fragment of Tx, tile (mb, kb): reg q -> rows g / g+8 (q & 1), k-columns 2t.. / 2t+8.. (q >> 1)
+      const int hh = e & 1, q = (e >> 1) & 3, lane = (e >> 3) & 31, tile = e >> 8;
+      const int mb = tile / S::KB, kb = tile - mb * S::KB;
+      const int gg = lane >> 2, t = lane & 3;
+      const int xo = 16 * mb + gg + 8 * (q & 1), xi = 16 * kb + 2 * t + hh + 8 * (q >> 1);
+      if (xo < W && xi < W) v = folded_tap(g, r, W, xo, xi);
+    } else {
+      // B fragments of Ty^T for the n-blocks (2 nbp, 2 nbp + 1), tile (kb2, nbp): reg q -> n-block (q >> 1),
+      // k-rows 2t.. / 2t+8.. (q & 1); element [k = y][n = y'] = Ty[y'][y]
+      e -= S::kT1 * 8;
+      const int hh = e & 1, q = (e >> 1) & 3, lane = (e >> 3) & 31, tile = e >> 8;
+      const int kb2 = tile / S::NBP, nbp = tile - kb2 * S::NBP;
+      const int gg = lane >> 2, t = lane & 3;
+      const int yi = 16 * kb2 + 2 * t + hh + 8 * (q & 1), yo = 8 * (2 * nbp + (q >> 1)) + gg;
+      v = folded_tap(g, r, H, yo, yi);
+    }
+    out[idx] = __float2half_rn(v);
+  }
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// (p[0], p[1]) of the staged plane as floats; p is 2-element aligned
+template <typename T>
+__device__ __forceinline__ float2 plane_pair(const T* p);
+template <>
+__device__ __forceinline__ float2 plane_pair<float>(const float* p) {
+  return *reinterpret_cast<const float2*>(p);
+}
+template <>
+__device__ __forceinline__ float2 plane_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+
+struct MmaGeom {
+  unsigned plane_bytes;   // H * W * sizeof(T)
+  unsigned cand_off;      // byte offset of the candidate list inside a warp's slot
+  unsigned slot_bytes;    // per-warp slot (multiple of 128)
+  unsigned div_W;
+};
+
+// scratch layout (unsigned words): [0] work counter of this kernel, [1] work counter of the hand-over launch,
+// [2] number of handed-over heatmaps, [3] unused, [4 ..] their indices
+constexpr int kMmaScratchHead = 4;
+
+// exact values of an interior pixel whose five windows lie inside the map (no reflection): same sums as team_exact5
+template <typename T>
+__device__ __noinline__ void mma_exact5_inside(const T* __restrict__ plane, const double* __restrict__ w2d, int W, int r,
+                                               int y, int x, int lane, float (&out)[5]) {
+  const int d = 2 * r + 1, n = d * d;
+  const int qs = 32 / d, rs = 32 - qs * d;
+  int ti = lane / d, tj = lane - ti * d;
+  const T* base = plane + (y - r) * W + (x - r);
+  double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int i = lane; i < n; i += 32) {
+    const T* q = base + ti * W + tj;
+    const double w = __ldg(w2d + i);
+    a[0] = fma(w, static_cast<double>(Elem<T>::to_f32(q[0])), a[0]);
+    a[1] = fma(w, static_cast<double>(Elem<T>::to_f32(q[-1])), a[1]);
+    a[2] = fma(w, static_cast<double>(Elem<T>::to_f32(q[1])), a[2]);
+    a[3] = fma(w, static_cast<double>(Elem<T>::to_f32(q[-W])), a[3]);
+    a[4] = fma(w, static_cast<double>(Elem<T>::to_f32(q[W])), a[4]);
+    tj += rs; ti += qs;
+    if (tj >= d) { tj -= d; ++ti; }
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) out[q] = static_cast<float>(warp_sum(a[q]));
+}
+
+template <typename T, int H, int W, int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB)
+decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict__ heatmaps,
+                           float* __restrict__ locs, float* __restrict__ vals, int32_t* __restrict__ argmax,
+                           double* __restrict__ keypoints, MmaGeom geo, unsigned* __restrict__ scratch,
+                           float* __restrict__ dbg_prefilter) {
+  using S = MmaShape<H, W>;
+  extern __shared__ __align__(128) unsigned char msm[];
+  __shared__ __align__(8) uint64_t bars[WPC];
+
+  constexpr int V = Elem<T>::kVec;
+  constexpr int HW = H * W, NV = HW / V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gg = lane >> 2, t4 = lane & 3;
+  unsigned char* slot = msm + static_cast<size_t>(warp) * geo.slot_bytes;
+  const T* plane = reinterpret_cast<const T*>(slot);
+  T* plane_rw = reinterpret_cast<T*>(slot);
+  int* cand = reinterpret_cast<int*>(slot + geo.cand_off);          // cand[0 .. kWCand) pixels, cand[kWCand] count
+  float* cand_val = reinterpret_cast<float*>(cand + kWCand + 4);    // their prefilter values
+  uint64_t* bar = &bars[warp];
+
+  const int N = p.B * p.K;   // the launcher guarantees N < 2^31
+  const bool tail = p.apply_tail != 0;
+  const float temp = p.temperature;
+  unsigned* work_counter = scratch;
+  unsigned* retry_count = scratch + 2;
+  int* retry_list = reinterpret_cast<int*>(scratch + kMmaScratchHead);
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  // work queue: items are pulled one at a time from a global counter, channel-major (item j -> channel order[j / B],
+  // image j % B) so that the warps of an SM mostly share one channel's operand tables in L1
+  auto item_to_hm = [&](int j) -> int {
+    const int slot_k = j / p.B, b = j - slot_k * p.B;
+    const int kk = tab.order ? tab.order[slot_k] : slot_k;
+    return b * p.K + kk;
+  };
+  int cur_item = 0, cur_hm = 0;
+  if (lane == 0) {
+    cur_item = static_cast<int>(min(atomicAdd(work_counter, 1u), static_cast<unsigned>(N)));
+    cur_hm = cur_item < N ? item_to_hm(cur_item) : N;
+    if (cur_item < N) {
+      mbar_expect_tx(bar, geo.plane_bytes);
+      tma_load_1d(slot, heatmaps + static_cast<size_t>(cur_hm) * HW, geo.plane_bytes, bar);
+    }
+  }
+  cur_item = __shfl_sync(0xffffffffu, cur_item, 0);
+  cur_hm = __shfl_sync(0xffffffffu, cur_hm, 0);
+
+  for (int it = 0; cur_item < N; ++it) {
+    const int hm = cur_hm;
+    // claim the next item now, look at the answer after the scan (the atomic's round trip is covered by it)
+    unsigned pulled_raw = 0u;
+    if (lane == 0) pulled_raw = atomicAdd(work_counter, 1u);
+
+    const int k = hm % p.K;
+    const int r = tab.radius[k];
+    const uint4* t1 = reinterpret_cast<const uint4*>(tab.mma_tables) + static_cast<size_t>(tab.mma_index[k]) * (S::kT1 + S::kT2);
+    const uint4* t2 = t1 + S::kT1;
+    const double* w2dk = tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
+
+    mbar_wait(bar, it & 1);
+
+    // ---- A: head tail in place (optional), then min / max
+    if (tail) {
+      for (int i = lane; i < NV; i += 32) {
+        float f[V];
+        uint4* vec = reinterpret_cast<uint4*>(plane_rw + i * V);
+        unpack(*vec, f, T());
+#pragma unroll
+        for (int j = 0; j < V; ++j) f[j] = tail_value<T>(f[j], temp);
+        *vec = pack(f, T());
+      }
+      __syncwarp();
+    }
+    float vmax = -INFINITY, vmin = INFINITY;
+#pragma unroll 4
+    for (int i = lane; i < NV; i += 32) {
+      float f[V];
+      unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+#pragma unroll
+      for (int j = 0; j < V; j += 2) {
+        vmax = fmaxf(vmax, fmaxf(f[j], f[j + 1]));
+        vmin = fminf(vmin, fminf(f[j], f[j + 1]));
+      }
+    }
+    vmax = warp_max(vmax);
+    vmin = -warp_max(-vmin);
+
+    int next_item = 0, next_hm = 0;
+    if (lane == 0) {
+      next_item = static_cast<int>(min(pulled_raw, static_cast<unsigned>(N)));
+      next_hm = next_item < N ? item_to_hm(next_item) : N;
+      if (next_item < N)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(heatmaps + static_cast<size_t>(next_hm) * HW),
+                     "r"(geo.plane_bytes)
+                     : "memory");
+    }
+
+    int best = 0;
+    float best_val = 0.0f, score = vmax;
+    float nb[4] = {0.f, 0.f, 0.f, 0.f};
+    bool interior = false, handed_over = false;
+
+    if (vmax != vmin) {   // constant maps (e.g. all zero after the clamp): first index wins, border pixel
+      // ---- B: scale.  range 2^k in [0.5, 1); maps without float32 dynamic range go to the general kernel
+      const float range = vmax - vmin;
+      const int ebits = static_cast<int>((__float_as_uint(range) >> 23) & 0xffu);
+      const float amax = fmaxf(fabsf(vmax), fabsf(vmin));
+      const float sc = __uint_as_float(static_cast<unsigned>(253 - ebits) << 23);
+      // candidate band in scaled units: twice the proposal error + the float32 rounding of the two exact values
+      const float band = 2.0f * kMmaErr + 4.0f * 5.9604645e-8f * amax * sc;
+      handed_over = ebits < 30 || ebits > 250 || !(band < 0.25f);
+      if (!handed_over) {
+        const float off = -vmin * sc;
+        // ---- C: the whole map as float16 B-fragments of H^T: hf[kb][nb] = rows 8 nb + g, columns 16 kb + 2 t (+ 8)
+        uint32_t hf[S::KB][S::NB][2];
+#pragma unroll
+        for (int kb = 0; kb < S::KB; ++kb)
+#pragma unroll
+          for (int nbk = 0; nbk < S::NB; ++nbk)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int x = 16 * kb + 8 * q;              // + 2 t4
+              if (x + 8 <= W || x + 2 * t4 < W) {         // columns beyond W (W = 8 mod 16) meet zero taps; keep them finite
+                const float2 v = plane_pair<T>(plane + (8 * nbk + gg) * W + x + 2 * t4);
+                hf[kb][nbk][q] = pack_h2(fmaf(v.x, sc, off), fmaf(v.y, sc, off));
+              } else {
+                hf[kb][nbk][q] = 0u;
+              }
+            }
+
+        if (lane == 0) cand[kWCand] = 0;
+        __syncwarp();
+        float gm = -INFINITY;
+#pragma unroll
+        for (int mb = 0; mb < S::MB; ++mb) {
+          // GEMM 1: Y^T[16 mb + ..][y] = sum_x Tx[x'][x] h~[y][x]; only |mb - kb| <= 1 tiles are non-zero (radius <= 9)
+          float acc1[S::NB][4];
+#pragma unroll
+          for (int nbk = 0; nbk < S::NB; ++nbk)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc1[nbk][c] = 0.0f;
+#pragma unroll
+          for (int kb = 0; kb < S::KB; ++kb) {
+            if (kb < mb - 1 || kb > mb + 1) continue;
+            const uint4 a4 = __ldg(t1 + (mb * S::KB + kb) * 32 + lane);
+            const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int nbk = 0; nbk < S::NB; ++nbk) mma16816(acc1[nbk], a, hf[kb][nbk][0], hf[kb][nbk][1]);
+          }
+          // the accumulators of n-blocks (2 j, 2 j + 1) are the A fragment of k-block j of GEMM 2
+          uint32_t ya[S::KB2][4];
+#pragma unroll
+          for (int j = 0; j < S::KB2; ++j) {
+            ya[j][0] = pack_h2(acc1[2 * j][0], acc1[2 * j][1]);
+            ya[j][1] = pack_h2(acc1[2 * j][2], acc1[2 * j][3]);
+            ya[j][2] = pack_h2(acc1[2 * j + 1][0], acc1[2 * j + 1][1]);
+            ya[j][3] = pack_h2(acc1[2 * j + 1][2], acc1[2 * j + 1][3]);
+          }
+          // GEMM 2: Z^T[x'][y'] = sum_y Y^T[x'][y] Ty[y'][y]; tiles with |kb2 - nbp| <= 1 only
+          float z[S::NB][4];
+#pragma unroll
+          for (int nbk = 0; nbk < S::NB; ++nbk)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) z[nbk][c] = 0.0f;
+#pragma unroll
+          for (int nbp = 0; nbp < S::NBP; ++nbp)
+#pragma unroll
+            for (int kb2 = 0; kb2 < S::KB2; ++kb2) {
+              if (kb2 < nbp - 1 || kb2 > nbp + 1) continue;
+              const uint4 b4 = __ldg(t2 + (kb2 * S::NBP + nbp) * 32 + lane);
+              mma16816(z[2 * nbp], ya[kb2], b4.x, b4.y);
+              mma16816(z[2 * nbp + 1], ya[kb2], b4.z, b4.w);
+            }
+          // z[nb][c]: column x' = 16 mb + g + 8 (c >> 1), row y' = 8 nb + 2 t + (c & 1)
+          const bool hi_ok = 16 * mb + 8 + 8 <= W;   // the rows g + 8 of the last block lie beyond W when W = 8 mod 16
+          float m = -INFINITY;
+#pragma unroll
+          for (int nbk = 0; nbk < S::NB; ++nbk) {
+            m = fmaxf(m, fmaxf(z[nbk][0], z[nbk][1]));
+            if (hi_ok) m = fmaxf(m, fmaxf(z[nbk][2], z[nbk][3]));
+          }
+          if (dbg_prefilter) {
+            const float inv = 1.0f / sc;
+#pragma unroll
+            for (int nbk = 0; nbk < S::NB; ++nbk)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c < 2 || hi_ok)
+                  dbg_prefilter[static_cast<size_t>(hm) * HW + (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1)] =
+                      z[nbk][c] * inv + vmin;
+          }
+          gm = fmaxf(gm, warp_max(m));
+          const float lo = gm - band;
+          if (m >= lo) {   // rare: new running maxima and near ties
+#pragma unroll
+            for (int nbk = 0; nbk < S::NB; ++nbk)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if ((c < 2 || hi_ok) && z[nbk][c] >= lo) {
+                  const int s = atomicAdd(&cand[kWCand], 1);
+                  if (s < kWCand) {
+                    cand[s] = (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1);
+                    cand_val[s] = z[nbk][c];
+                  }
+                }
+          }
+        }
+        __syncwarp();
+        const float thr = gm - band;
+        const int raw = cand[kWCand];
+        handed_over = raw > kWCand;
+        if (!handed_over) {
+          // keep the listed pixels that are inside the band of the final maximum
+          int keep_id[kWCand / 32];
+          bool keep[kWCand / 32];
+#pragma unroll
+          for (int u = 0; u < kWCand / 32; ++u) {
+            const int e = lane + u * 32;
+            keep[u] = e < raw && cand_val[min(e, kWCand - 1)] >= thr;
+            keep_id[u] = cand[min(e, kWCand - 1)];
+          }
+          __syncwarp();
+          if (lane == 0) cand[kWCand] = 0;
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < kWCand / 32; ++u)
+            if (keep[u]) cand[atomicAdd(&cand[kWCand], 1)] = keep_id[u];
+          __syncwarp();
+          const int count = cand[kWCand];
+
+          // ---- G: exact values of the candidates and of the winner's four neighbours
+          TeamExact<T> te;
+          te.plane = plane; te.w2d = w2dk; te.ex = nullptr; te.H = H; te.W = W; te.r = r; te.d = 2 * r + 1;
+          te.tl = lane; te.tw = 0; te.team = 0; te.calls = 0;
+          if (count == 1) {
+            best = cand[0];
+          } else {
+            best_val = -INFINITY; best = 0x7fffffff;
+            for (int q = 0; q < count; ++q) {
+              const int ci = cand[q], cy = fast_div(ci, geo.div_W);
+              argmax_combine(best_val, best, team_exact1<T, 1>(te, cy, ci - cy * W), ci);
+            }
+          }
+          const int by = fast_div(best, geo.div_W), bx = best - by * W;
+          interior = bx > 0 && bx < W - 1 && by > 0 && by < H - 1;
+          if (interior) {
+            float ev[5];
+            if (bx - r >= 1 && bx + r < W - 1 && by - r >= 1 && by + r < H - 1) mma_exact5_inside<T>(plane, w2dk, W, r, by, bx, lane, ev);
+            else team_exact5<T, 1>(te, by, bx, ev);
+            best_val = ev[0];
+            nb[0] = ev[1]; nb[1] = ev[2]; nb[2] = ev[3]; nb[3] = ev[4];
+          }
+          score = plane_value<T>(plane, best);
+        }
+      }
+    }
+
+    // ---- H: outputs (thread 0: x, thread 1: y; heatmap.py:136-165 in float32, the reference's operation order) or
+    // hand-over to the general kernel
+    if (handed_over) {
+      if (lane == 0) retry_list[atomicAdd(retry_count, 1u)] = hm;
+    } else if (lane < 2) {
+      const int by = fast_div(best, geo.div_W), bx = best - by * W;
+      const bool is_y = lane == 1;
+      float f = static_cast<float>(is_y ? by : bx);
+      if (interior) {
+        const float lo = is_y ? nb[2] : nb[0], hi = is_y ? nb[3] : nb[1], c = best_val;   // left/up, right/down
+        const float g = __fdiv_rn(__fsub_rn(hi, lo), 2.0f);
+        float h = __fsub_rn(__fadd_rn(hi, lo), __fmul_rn(2.0f, c));
+        if (h == 0.0f) h = 1e-6f;
+        f = __fadd_rn(f, __fdiv_rn(-g, h));
+      }
+      locs[static_cast<size_t>(hm) * 2 + (is_y ? 1 : 0)] = f;
+      if (keypoints)   // float32 / int -> float64, then * input_size (codec.py:237)
+        keypoints[static_cast<size_t>(hm) * 2 + (is_y ? 1 : 0)] =
+            static_cast<double>(f) / static_cast<double>(is_y ? H - 1 : W - 1) * (is_y ? p.input_h : p.input_w);
+      if (is_y) {
+        vals[hm] = score;
+        if (argmax) argmax[hm] = best;
+      }
+    }
+
+    // ---- next heatmap: the warp is done with the plane, lane 0 starts the copy (an L2 hit by now)
+    __syncwarp();
+    if (lane == 0 && next_item < N) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, geo.plane_bytes);
+      tma_load_1d(slot, heatmaps + static_cast<size_t>(next_hm) * HW, geo.plane_bytes, bar);
+    }
+    cur_item = __shfl_sync(0xffffffffu, next_item, 0);
+    cur_hm = __shfl_sync(0xffffffffu, next_hm, 0);
+  }
+}

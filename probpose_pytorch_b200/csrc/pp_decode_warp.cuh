@@ -261,7 +261,8 @@ template <typename T, int G, int TPC>
 __global__ void __launch_bounds__(32 * G * TPC, 6)
 decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict__ heatmaps,
                             float* __restrict__ locs, float* __restrict__ vals, int32_t* __restrict__ argmax,
-                            double* __restrict__ keypoints, WarpGeom geo, unsigned* __restrict__ work_counter) {
+                            double* __restrict__ keypoints, WarpGeom geo, unsigned* __restrict__ work_counter,
+                            const int* __restrict__ list, const unsigned* __restrict__ list_count) {
   extern __shared__ __align__(128) unsigned char wsm[];
   __shared__ __align__(8) uint64_t bars[TPC];
 
@@ -280,7 +281,9 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   uint64_t* bar = &bars[team];
 
   const int H = p.H, W = p.W, HW = H * W, WV = W / V, NV = HW / V;
-  const int N = p.B * p.K;   // the launcher guarantees N < 2^31
+  // `list` (with its device-side length): decode only the listed heatmaps -- the ones the tensor-core kernel
+  // (pp_decode_mma.cuh) handed on; the launcher guarantees B * K < 2^31
+  const int N = list ? static_cast<int>(*list_count) : p.B * p.K;
   const bool tail = p.apply_tail != 0;
   const float temp = p.temperature;
   const bool pp_no_truncation = geo.full_taps != 0;
@@ -302,6 +305,7 @@ decode_expected_warp_kernel(pp_decode_params p, pp_oks_table tab, const T* __res
   const bool dynamic = work_counter != nullptr;
   const int gteam = blockIdx.x * TPC + team, nteams = gridDim.x * TPC;
   auto item_to_hm = [&](int j) -> int {
+    if (list) return list[j];
     if (!dynamic) return j;
     const int slot_k = j / p.B, b = j - slot_k * p.B;
     const int kk = tab.order ? tab.order[slot_k] : slot_k;

@@ -15,7 +15,9 @@
 
 #include "pp_common.cuh"
 #include "pp_loss_fast.cuh"
-#include "pp_loss_pair.cuh"
+#ifdef PP_EXPERIMENTS   // measured-and-rejected variant, outside the default build
+#include "../../tools/experiments/pp_loss_pair.cuh"
+#endif
 
 namespace {
 
@@ -304,13 +306,15 @@ int launch_fast_tt(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cu
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), threads, smem, &per_sm)) return rc;
   if (const int cap = env_int("PP_LOSS_CTAS", 0); cap > 0) per_sm = std::min(per_sm, cap);
   const int64_t units = (a.N + a.G - 1) / a.G;
-  const int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  if (const int cap = env_int("PP_LOSS_GRID", 0); cap > 0) grid = std::min(grid, cap);   // test hook: many units per CTA
   kern<<<grid, threads, smem, st>>>(a);
   PP_CUDA_OK(cudaGetLastError());
   *grid_out = grid;
   return PP_OK;
 }
 
+#ifdef PP_EXPERIMENTS
 template <bool kFwd, bool kGrad>
 int launch_pair_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
   int per_sm = 1;
@@ -318,12 +322,14 @@ int launch_pair_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cud
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), threads, smem, &per_sm)) return rc;
   if (const int cap = env_int("PP_LOSS_CTAS", 0); cap > 0) per_sm = std::min(per_sm, cap);
   const int64_t units = (a.N + a.G - 1) / a.G;
-  const int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(pp_sm_count()) * per_sm));
+  if (const int cap = env_int("PP_LOSS_GRID", 0); cap > 0) grid = std::min(grid, cap);   // test hook: many units per CTA
   kern<<<grid, threads, smem, st>>>(a);
   PP_CUDA_OK(cudaGetLastError());
   *grid_out = grid;
   return PP_OK;
 }
+#endif
 
 template <typename T, bool kFwd, bool kGrad>
 int launch_fast_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
@@ -365,6 +371,7 @@ int launch_fast(const pp_loss_params& p, const void* output, const void* target,
   a.plane_bytes = static_cast<unsigned>(static_cast<int64_t>(p.H) * p.W * e);
   const bool g = grad != nullptr;
 
+#ifdef PP_EXPERIMENTS
   // float32: two heatmaps per thread with packed FADD2 / FMUL2 / FFMA2 arithmetic (pp_loss_pair.cuh), whenever a
   // unit of 2 x pairs heatmaps (output + target) fits shared memory
   if (p.dtype == PP_F32 && a.N >= 2 && per <= 256 && env_int("PP_LOSS_PAIR", 0)) {
@@ -387,6 +394,7 @@ int launch_fast(const pp_loss_params& p, const void* output, const void* target,
       return launch_pair_t<false, true>(b, threads, smem, st, grid_out);
     }
   }
+#endif
 
   for (;; --a.G) {
     a.tgt_off = (16 + a.G * a.plane_bytes + 16 + 127) / 128 * 128;

@@ -124,8 +124,9 @@ def expected_value_device(heatmaps: torch.Tensor, sigmas, *, input_size=None, re
         conv = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
         if return_heatmap:
             out["conv"] = conv
-    t = _lib.OksTable(tab.radius.data_ptr(), tab.taps.data_ptr(), tab.kernel2d.data_ptr(), tab.order.data_ptr())
-    scratch = torch.empty(4, dtype=torch.int32, device=dev)   # work-queue counter of the kernel
+    t = tab.descriptor()
+    # work-queue counters + the hand-over list of the tensor-core kernel (one int32 per heatmap)
+    scratch = torch.empty((int(_lib.lib().pp_decode_expected_scratch_bytes_for(p)) + 3) // 4, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.lib().pp_decode_expected(p, t, _lib.ptr(hm), _lib.ptr(out["locs"]), _lib.ptr(out["vals"]),
                                            _lib.ptr(out["argmax"]), _lib.ptr(kp), _lib.ptr(conv), _lib.ptr(scratch),

@@ -1,227 +1,175 @@
-"""``ProbPoseLoss`` -- the training-step caller of the hot path (loss.py:342-510) -- on the device.
+"""Device-side parts for the reference's own ``ProbPoseLoss`` (loss.py:342-712).
 
-Same constructor, ``forward`` arguments, returned dictionaries and loss modules as the reference.  What
-changes is where the work happens:
+``ProbPoseLoss`` is the training-step *caller* of the hot path, not part of it, so this package does not
+re-implement it.  :func:`patch_probpose_loss` takes an instance of the reference's class and swaps the
+pieces that sit on the hot path for their CUDA versions; the reference's ``forward`` and its four
+scalar-head losses keep running unchanged:
 
-* heatmap loss: ``OKSHeatmapLoss(per_pixel=True).mean()`` is one fused forward+backward kernel
-  (``OKSHeatmapLoss.forward_mean``) instead of ~20 elementwise / convolution launches and a (B, K, H, W)
-  temporary per launch;
-* OKS / error targets (``_oks_from_heatmaps`` / ``_error_from_heatmaps``, loss.py:512-640): two DARK
-  decodes + a (B, K) kernel on the device instead of a device->host copy of both heatmap stacks and
-  2 B per-sample NumPy / OpenCV decodes per step (``pose_targets``);
-* accuracy read-outs (``compute_acc=True``, loss.py:463-508): ``metrics`` kernels;
-* the ground-truth dict (dataset.py:130-135) may carry ``keypoints`` (B, K, 2) instead of ``heatmaps``: the
-  targets are then encoded on the device (``encode_batch``), so the DataLoader workers no longer encode and the
-  per-step host->device copy of the (B, K, H, W) target stack (loss.py:376) disappears.
+=====================================  ================================================================
+reference member (loss.py)             replaced by
+=====================================  ================================================================
+``keypoint_loss_module`` (:348-352)    :class:`FusedOKSHeatmapLoss`: ``module(out, tgt, w, per_pixel=True).mean()``
+                                       (:428-431) becomes ONE fused forward+backward kernel
+``_oks_from_heatmaps`` (:550-640)      two DARK decodes + ``pp_pose_targets`` on the device, no host copy
+``_error_from_heatmaps`` (:512-548)    same; the (B, K) result is returned as a NumPy array because the
+                                       caller wraps it with ``torch.from_numpy`` (:383-384)
+``get_pose_accuracy`` (:642-651),      ``metrics`` kernels
+``get_binary_accuracy`` (:653-697),
+``get_mae`` (:699-712)
+=====================================  ================================================================
 
-The four scalar heads' losses (BCE / MSE / smooth-L1-of-logs on (B, K) values, loss.py:194-339) are a few
-torch element-wise calls on 4 K numbers: plumbing, kept in torch on the device.
+:func:`ground_truth_from_keypoints` builds the ground-truth dictionary the reference's ``forward`` reads
+(dataset.py:130-135) from (B, K, 2) keypoints on the device, so a loader can ship keypoints instead of
+(B, K, H, W) target planes.
 """
 
 from __future__ import annotations
 
-from functools import partial
-from typing import Sequence
-
 import numpy as np
 import torch
-import torch.nn.functional as F
-from torch import Tensor, nn
+from torch import Tensor
 
 from . import metrics
+from .codec import ArgMaxProbMap, Codec
 from .loss import OKSHeatmapLoss
 from .pose_targets import error_from_heatmaps, oks_from_heatmaps
 
-
-class BCELoss(nn.Module):
-    """Binary cross entropy on probabilities (``use_sigmoid=True``) or logits; loss.py:194-260."""
-
-    def __init__(self, use_target_weight=False, loss_weight=1.0, reduction="mean", use_sigmoid=False):
-        super().__init__()
-        assert reduction in ("mean", "sum", "none"), (
-            f"the argument `reduction` should be either 'mean', 'sum' or 'none', but got {reduction}")
-        self.reduction = reduction
-        self.use_sigmoid = use_sigmoid
-        self.criterion = partial(F.binary_cross_entropy if use_sigmoid else F.binary_cross_entropy_with_logits,
-                                 reduction="none")
-        self.use_target_weight = use_target_weight
-        self.loss_weight = loss_weight
-
-    def forward(self, output, target, target_weight=None):
-        loss = self.criterion(output, target)
-        if self.use_target_weight:
-            assert target_weight is not None
-            if target_weight.dim() == 1:
-                target_weight = target_weight[:, None]
-            loss = loss * target_weight
-        if self.reduction == "sum":
-            loss = loss.sum()
-        elif self.reduction == "mean":
-            loss = loss.mean()
-        return loss * self.loss_weight
+__all__ = ["FusedOKSHeatmapLoss", "LazyPerPixelLoss", "patch_probpose_loss", "ground_truth_from_keypoints"]
 
 
-class MSELoss(nn.Module):
-    """``mse_loss(output * w, target * w)``; loss.py:263-292."""
+class LazyPerPixelLoss:
+    """The un-reduced per-pixel loss of ``OKSHeatmapLoss(..., per_pixel=True)``, not materialised yet.
 
-    def __init__(self, use_target_weight=False, loss_weight=1.0):
-        super().__init__()
-        self.criterion = F.mse_loss
-        self.use_target_weight = use_target_weight
-        self.loss_weight = loss_weight
+    ``.mean()`` -- the only thing ``ProbPoseLoss.forward`` does with it (loss.py:431) -- runs the fused
+    forward+backward kernel and never writes the (B, K, H, W) map.  Anything else (indexing, arithmetic,
+    ``.sum()``, passing it to torch functions) first materialises the real tensor with the per-pixel kernel.
+    """
 
-    def forward(self, output, target, target_weight=None):
-        if self.use_target_weight:
-            assert target_weight is not None
-            loss = self.criterion(output * target_weight, target * target_weight)
-        else:
-            loss = self.criterion(output, target)
-        return loss * self.loss_weight
+    def __init__(self, module: OKSHeatmapLoss, output, target, target_weights, mask):
+        self._module, self._args = module, (output, target, target_weights, mask)
+        self._tensor = None
+
+    def mean(self, *args, **kwargs):
+        if args or kwargs or self._tensor is not None:
+            return self.materialize().mean(*args, **kwargs)
+        return self._module.forward_mean(*self._args)
+
+    def materialize(self) -> Tensor:
+        if self._tensor is None:
+            self._tensor = OKSHeatmapLoss.forward(self._module, *self._args, per_pixel=True)
+        return self._tensor
+
+    @property
+    def shape(self):
+        return self._args[0].shape
+
+    def __getattr__(self, name):
+        return getattr(self.materialize(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        unwrap = lambda a: a.materialize() if isinstance(a, LazyPerPixelLoss) else a
+        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in (kwargs or {}).items()})
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __len__(self):
+        return self.shape[0]
 
 
-class L1LogLoss(nn.Module):
-    """Smooth-L1 between ``log(1 + output)`` and ``log(1 + target)``; loss.py:295-339."""
-
-    def __init__(self, use_target_weight=False, loss_weight=1.0):
-        super().__init__()
-        self.criterion = F.smooth_l1_loss
-        self.use_target_weight = use_target_weight
-        self.loss_weight = loss_weight
-
-    def forward(self, output, target, target_weight=None):
-        output = torch.log(1 + output)
-        target = torch.log(1 + target)
-        if self.use_target_weight:
-            assert target_weight is not None
-            assert output.ndim >= target_weight.ndim
-            for _ in range(output.ndim - target_weight.ndim):
-                target_weight = target_weight.unsqueeze(-1)
-            loss = self.criterion(output * target_weight, target * target_weight)
-        else:
-            loss = self.criterion(output, target)
-        return loss * self.loss_weight
+for _op in ("add", "radd", "sub", "rsub", "mul", "rmul", "truediv", "rtruediv", "neg", "pow"):
+    def _delegate(self, *a, _name=f"__{_op}__"):
+        return getattr(self.materialize(), _name)(*a)
+    setattr(LazyPerPixelLoss, f"__{_op}__", _delegate)
 
 
-class ProbPoseLoss(nn.Module):
-    """Drop-in for the reference's ``ProbPoseLoss`` (loss.py:342-510).  ``codec`` is a
-    ``Codec(ArgMaxProbMap(...))`` of this package; predictions must live on a CUDA device."""
+class FusedOKSHeatmapLoss(OKSHeatmapLoss):
+    """``OKSHeatmapLoss`` whose ``per_pixel=True`` result is lazy (see :class:`LazyPerPixelLoss`)."""
 
-    def __init__(self, codec, freeze_error: bool = True):
-        super().__init__()
-        self.codec = codec
-        self.keypoint_loss_module = OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus")
-        self.probability_loss_module = BCELoss(use_target_weight=False, use_sigmoid=True)
-        self.visibility_loss_module = BCELoss(use_target_weight=False, use_sigmoid=True)
-        self.oks_loss_module = MSELoss(use_target_weight=True)
-        self.error_loss_module = L1LogLoss(use_target_weight=True)
-        self.freeze_error = freeze_error
-        self.freeze_oks = False
+    def forward(self, output, target, target_weights=None, mask=None, per_pixel=False, per_keypoint=False):
+        if per_pixel:
+            return LazyPerPixelLoss(self, output, target, target_weights, mask)
+        return super().forward(output, target, target_weights, mask, per_pixel, per_keypoint)
 
-    def forward(self, gt, pred, keypoint_weights: Tensor | None = None, learn_heatmaps_from_zeros: bool = False,
-                compute_acc: bool = False):
-        dt_heatmaps, dt_probs, dt_vis, dt_oks, dt_errs = pred
-        device = dt_heatmaps.device
-        B, C, H, W = dt_heatmaps.shape
-        if keypoint_weights is None:
-            keypoint_weights = torch.ones((B, C), device=device, dtype=dt_heatmaps.dtype)
 
-        def dev(x, dtype):
-            return torch.as_tensor(x).to(device, dtype=dtype)
+def _device_codec(codec) -> Codec:
+    """This package's ``Codec(ArgMaxProbMap)`` with the parameters of the reference codec object."""
+    pm = getattr(codec, "probmap", codec)
+    if isinstance(pm, ArgMaxProbMap):
+        return codec if isinstance(codec, Codec) else Codec(pm)
+    return Codec(ArgMaxProbMap(pm.input_size, pm.heatmap_size, pm.sigmas, sigma=getattr(pm, "sigma", -1),
+                               blur_kernel_size=getattr(pm, "blur_kernel_size", 11)))
 
-        if "heatmaps" not in gt:
-            # keypoint front end: the loader ships (B, K, 2) input-space keypoints and the
-            # target planes are encoded here, on the device -- B*K*3 numbers cross PCIe instead of B*K*H*W
-            enc = self.codec.probmap.encode_batch(torch.as_tensor(gt["keypoints"]).reshape(B, C, -1),
-                                                  torch.as_tensor(gt["keypoints_visible"]).reshape(B, C).to(torch.float32),
-                                                  dtype=dt_heatmaps.dtype, device=device)
-            gt = dict(gt, heatmaps=enc["heatmaps"], in_image=gt.get("in_image", enc["in_image"]))
-        gt_heatmaps = dev(gt["heatmaps"], dt_heatmaps.dtype).view((B, C, H, W))
-        gt_probs = dev(gt["in_image"], torch.int64).view((B, C))
-        gt_annotated = dev(gt["keypoints_visible"], torch.int64).view((B, C))
-        gt_vis = dev(gt["keypoints_visibility"], torch.int64).view((B, C))
-        dt_heatmaps = dt_heatmaps.view((B, C, H, W))
 
-        # targets of the error / OKS heads, from the two stacks of heatmaps, without leaving the device
-        if self.freeze_error:
-            gt_errs = torch.zeros((B, C), device=device, dtype=dt_errs.dtype)
-        else:
-            gt_errs = self._error_from_heatmaps(gt_heatmaps, dt_heatmaps).to(dt_errs.dtype)
-        if self.freeze_oks:
-            gt_oks = torch.zeros((B, C), device=device, dtype=dt_oks.dtype)
-        else:
-            gt_oks, _ = self._oks_from_heatmaps(gt_heatmaps, dt_heatmaps, gt_probs & gt_annotated, heatmap_size=(W, H))
-            gt_oks = gt_oks.to(dt_oks.dtype).view((B, C))
+def _balanced_subset(gt, mask) -> np.ndarray | None:
+    """The random balanced subsample of loss.py:666-682, drawn like the reference does (NumPy's global generator,
+    positives shuffled first) on the (B, K) booleans; returns the selection as a flat boolean array over all entries."""
+    m = np.asarray(torch.as_tensor(mask).detach().cpu().numpy(), dtype=bool).reshape(-1)
+    g = torch.as_tensor(gt).detach().cpu().numpy().reshape(-1)[m].astype(bool)
+    n_pos = int(g.sum())
+    num = min(n_pos, int(g.size) - n_pos)
+    if num == 0:
+        return None
+    pos, neg = np.flatnonzero(g), np.flatnonzero(~g)
+    np.random.shuffle(pos)
+    np.random.shuffle(neg)
+    chosen = np.zeros(g.size, dtype=bool)
+    chosen[pos[:num]] = True
+    chosen[neg[:num]] = True
+    sel = np.zeros(m.size, dtype=bool)
+    sel[np.flatnonzero(m)[chosen]] = True
+    return sel
 
-        dt_probs, dt_vis = dt_probs.view((B, C)), dt_vis.view((B, C))
-        dt_oks, dt_errs = dt_oks.view((B, C)), dt_errs.view((B, C))
-        keypoint_weights = keypoint_weights.view((B, C))
-        annotated_in = gt_annotated & (gt_probs > 0.5)
 
-        heatmap_weights = gt_annotated if learn_heatmaps_from_zeros else keypoint_weights
-        # == keypoint_loss_module(dt, gt, w, per_pixel=True).mean(), fused forward + backward
-        heatmap_loss = self.keypoint_loss_module.forward_mean(dt_heatmaps, gt_heatmaps, heatmap_weights.to(torch.float32))
-        probability_loss = self.probability_loss_module(dt_probs, gt_probs.float())
+def patch_probpose_loss(loss_module):
+    """Swap the hot-path members of a reference ``ProbPoseLoss`` instance for their CUDA versions, in place.
 
-        # loss.py:438-452: weights that balance visible / invisible keypoints.  The visibility module is built
-        # with use_target_weight=False, so they do not enter the loss; they are still formed, because an
-        # annotated-free batch fails here in the reference (min() of an empty tensor) and must fail here too.
-        invisible_in = (gt_vis == 0) & (gt_annotated > 0.5)
-        visible_in = (gt_vis > 0) & (gt_annotated > 0.5)
-        weighted = annotated_in.clone().to(torch.float64)
-        weighted[invisible_in] = (1 / (invisible_in.sum() + 1e-10)).to(weighted.dtype)
-        weighted[visible_in] = (1 / (visible_in.sum() + 1e-10)).to(weighted.dtype)
-        weighted = (weighted / weighted[weighted > 0].min()).to(dt_vis.dtype)
+    ``loss_module`` is the reference's object (anything with its member names works); its ``codec`` may be the
+    reference's ``Codec(ArgMaxProbMap(...))`` -- an equivalent device codec is built from its parameters.
+    Returns ``loss_module``.
+    """
+    old = loss_module.keypoint_loss_module
+    loss_module.keypoint_loss_module = FusedOKSHeatmapLoss(
+        use_target_weight=getattr(old, "use_target_weight", True), skip_empty_channel=getattr(old, "skip_empty_channel", False),
+        smoothing_weight=getattr(old, "smoothing_weight", 0.05), gaussian_weight=getattr(old, "gaussian_weight", 0.0),
+        loss_weight=getattr(old, "loss_weight", 1.0), oks_type=getattr(old, "oks_type", "minus"))
+    dev_codec = _device_codec(loss_module.codec)
 
-        visibility_loss = self.visibility_loss_module(dt_vis, gt_vis.float(), weighted)
-        oks_loss = self.oks_loss_module(dt_oks, gt_oks, annotated_in)
-        error_loss = self.error_loss_module(dt_errs, gt_errs, annotated_in)
-        losses = dict(kpt=heatmap_loss, probability=probability_loss, visibility=visibility_loss, oks=oks_loss,
-                      error=error_loss)
-        if not compute_acc:
-            return losses
-        acc = {
-            "kpt": self.get_pose_accuracy(dt_heatmaps, gt_heatmaps, keypoint_weights > 0.5),
-            "probability": self.get_binary_accuracy(dt_probs, gt_probs, gt_annotated > 0.5, force_balanced=True)[0],
-            "visibility": self.get_binary_accuracy(dt_vis, gt_vis, annotated_in > 0.5, force_balanced=True)[0],
-            "oks": self.get_mae(dt_oks, gt_oks, annotated_in > 0.5),
-            "error": self.get_mae(dt_errs, gt_errs, annotated_in > 0.5),
-        }
-        return losses, acc
+    def _oks(gt_heatmaps, dt_heatmaps, weight, heatmap_size=(48, 64)):
+        return oks_from_heatmaps(dev_codec, gt_heatmaps, dt_heatmaps, weight, heatmap_size=heatmap_size)
 
-    # ---- loss.py:512-640 ------------------------------------------------------------------------------
-    def _error_from_heatmaps(self, gt_heatmaps: Tensor, dt_heatmaps: Tensor) -> Tensor:
-        """(B, K) float64 distance between the DARK-decoded target and prediction, on the device."""
-        return error_from_heatmaps(self.codec, gt_heatmaps, dt_heatmaps)
+    def _error(gt_heatmaps, dt_heatmaps):
+        return error_from_heatmaps(dev_codec, gt_heatmaps, dt_heatmaps).cpu().numpy()
 
-    def _oks_from_heatmaps(self, gt_heatmaps: Tensor, dt_heatmaps: Tensor, weight: Tensor,
-                           heatmap_size: Sequence[int] = (48, 64)):
-        return oks_from_heatmaps(self.codec, gt_heatmaps, dt_heatmaps, weight, heatmap_size=heatmap_size)
+    def _binary_accuracy(dt, gt, mask, force_balanced=False):
+        if force_balanced:
+            sel = _balanced_subset(gt, mask)
+            if sel is None:
+                zero = torch.tensor([0.0], device=gt.device)
+                return zero, zero.clone()
+            return metrics.get_binary_accuracy(torch.as_tensor(dt).reshape(-1), torch.as_tensor(gt).reshape(-1).to(torch.float32),
+                                               torch.from_numpy(sel))
+        return metrics.get_binary_accuracy(dt, gt, mask)
 
-    # ---- loss.py:642-712 ------------------------------------------------------------------------------
-    def get_pose_accuracy(self, dt, gt, mask):
-        return metrics.get_pose_accuracy(dt, gt, mask)
+    loss_module._oks_from_heatmaps = _oks
+    loss_module._error_from_heatmaps = _error
+    loss_module.get_pose_accuracy = metrics.get_pose_accuracy
+    loss_module.get_binary_accuracy = _binary_accuracy
+    loss_module.get_mae = lambda dt, gt, mask: metrics.get_mae(dt, torch.as_tensor(gt).to(torch.float32), mask)
+    loss_module.device_codec = dev_codec
+    return loss_module
 
-    def get_binary_accuracy(self, dt, gt, mask, force_balanced=False):
-        """With ``force_balanced`` the reference keeps an equal number of randomly chosen positives and
-        negatives (``np.random.shuffle`` on the host, loss.py:666-682).  The same draws are made here from
-        NumPy's global generator -- the selection is (B, K) booleans -- and the counting stays on the device."""
-        if not force_balanced:
-            return metrics.get_binary_accuracy(dt, gt, mask)
-        device = gt.device
-        m = np.asarray(torch.as_tensor(mask).detach().cpu().numpy(), dtype=bool).reshape(-1)
-        g = torch.as_tensor(gt).detach().cpu().numpy().reshape(-1)[m].astype(bool)
-        num = min(int(g.sum()), int(len(g) - g.sum()))
-        if num == 0:
-            return torch.tensor([0.0], device=device), torch.tensor([0.0], device=device)
-        pos_idx, neg_idx = np.where(g)[0], np.where(~g)[0]
-        np.random.shuffle(pos_idx)
-        np.random.shuffle(neg_idx)
-        chosen = np.zeros(len(g), dtype=bool)
-        chosen[np.concatenate([pos_idx[:num], neg_idx[:num]])] = True
-        sel = np.zeros(m.shape, dtype=bool)
-        sel[np.where(m)[0][chosen]] = True
-        return metrics.get_binary_accuracy(torch.as_tensor(dt).reshape(-1), torch.as_tensor(gt).reshape(-1).to(torch.float32),
-                                           torch.from_numpy(sel))
 
-    def get_mae(self, dt, gt, mask):
-        return metrics.get_mae(dt, torch.as_tensor(gt).to(torch.float32), mask)
+def ground_truth_from_keypoints(codec, keypoints, keypoints_visible, keypoints_visibility, *,
+                                dtype: torch.dtype = torch.float32, device: torch.device | None = None) -> dict:
+    """The ground-truth dictionary of one batch (what the reference's collate yields from ``Codec.encode``,
+    dataset.py:116-135) built on the device from (B, K, 2) input-space keypoints: ``heatmaps`` (B, K, H, W),
+    ``in_image``, ``keypoints_visible`` (= annotated) and ``keypoints_visibility``.  ``codec``: this package's
+    ``Codec(ArgMaxProbMap)`` or the object :func:`patch_probpose_loss` returned."""
+    codec = getattr(codec, "device_codec", codec)
+    enc = codec.probmap.encode_batch(torch.as_tensor(keypoints), torch.as_tensor(keypoints_visible).to(torch.float32),
+                                     dtype=dtype, device=device)
+    dev = enc["heatmaps"].device
+    return dict(heatmaps=enc["heatmaps"], in_image=enc["in_image"], keypoints_visible=enc["annotated"],
+                keypoints_visibility=torch.as_tensor(keypoints_visibility).to(dev), keypoint_weights=enc["keypoint_weights"])

@@ -39,7 +39,10 @@ def test_binding_covers_header():
 def test_version_and_error_string(lib):
     lib.pp_version.restype = ctypes.c_int
     lib.pp_last_error_string.restype = ctypes.c_char_p
-    assert lib.pp_version() == 1
+    assert lib.pp_version() == 2
+    lib.pp_source_hash.restype = ctypes.c_char_p
+    from probpose_pytorch_b200.build import source_hash
+    assert lib.pp_source_hash().decode() == source_hash()   # the binary was compiled from the sources in the tree
     assert isinstance(lib.pp_last_error_string(), bytes)
 
 
@@ -57,7 +60,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.EncodeParams) == 44
     assert ctypes.sizeof(_lib.DecodeParams) == 48
     assert ctypes.sizeof(_lib.LossParams) == 72
-    assert ctypes.sizeof(_lib.OksTable) == 32
+    assert ctypes.sizeof(_lib.OksTable) == 56
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

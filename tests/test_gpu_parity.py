@@ -30,20 +30,28 @@ def pp():
 
 
 
-@pytest.fixture(params=["auto", "team1", "team2", "team1-fulltaps", "cta"])
+@pytest.fixture(params=["auto", "mma-grid2", "nomma", "team1", "team2", "team1-fulltaps", "team1-grid3", "cta", "cta-grid5"])
 def expected_kernel(request, monkeypatch):
-    """Which kernel runs the expected-OKS decode: the library's size rule ("auto": small batches such as the ones in
-    these tests take the CTA-per-heatmap kernel), the team-per-heatmap kernel (pp_decode_warp.cuh) with one or two
-    warps per heatmap, or the CTA-per-heatmap kernel (pp_decode_fast.cuh) forced."""
+    """Which kernel runs the expected-OKS decode: the library's rule ("auto": the tensor-core kernel pp_decode_mma.cuh
+    for the 64x48 / 96x72 shapes it is built for, else the size rule of the general kernels = "nomma"), the
+    team-per-heatmap kernel (pp_decode_warp.cuh) with one or two warps per heatmap, or the CTA-per-heatmap kernel
+    (pp_decode_fast.cuh) forced.  "-gridN" caps the launch at N CTAs, so that every warp / CTA decodes MANY heatmaps:
+    the work-queue pull, the single-slot TMA refill and the mbarrier phase flips of the persistent loops run against
+    the oracle."""
     mode = request.param
-    if mode == "cta":
+    if "-grid" in mode:
+        monkeypatch.setenv("PP_DECODE_GRID", mode.split("-grid")[1])
+        mode = mode.split("-grid")[0]
+    if mode == "nomma":
+        monkeypatch.setenv("PP_DECODE_MMA", "0")
+    elif mode == "cta":
         monkeypatch.setenv("PP_DECODE_WARP", "0")
-    elif mode != "auto":
+    elif mode.startswith("team"):
         monkeypatch.setenv("PP_DECODE_WARP", "1")
         monkeypatch.setenv("PP_DECODE_TEAM", mode[4])
         if mode.endswith("fulltaps"):   # prefilter with every tap instead of the truncated wide kernels
             monkeypatch.setenv("PP_DECODE_FULLTAPS", "1")
-    return mode
+    return request.param
 
 
 def _oracle_encode(kind, wl, kps, vis, sigma=None):
@@ -1004,17 +1012,22 @@ def test_pck_metrics_wholebody_batch_against_oracle(pp):
                                                 ("zeros", False, dict(learn_heatmaps_from_zeros=True)),
                                                 ("weights", True, dict(keypoint_weights=True))])
 def test_probpose_loss_matches_reference_forward_and_backward(pp, golden_dir, name, freeze, kwargs):
-    """The training-step caller: ProbPoseLoss.forward(gt dict, 5-tuple) -> five losses (+ five accuracies) and the
-    gradients of their sum, against the reference's own run (tests/golden/probpose_loss.npz)."""
+    """The training-step caller with the hot-path members patched (patch_probpose_loss): five losses, five accuracies
+    and the gradients of the losses' sum against the reference's own run (tests/golden/probpose_loss.npz).  The
+    reference's class is not importable on the GPU box: the patched object is the oracle's stand-in with the same
+    member names, driven by the oracle's restatement of the reference's forward (pinned on the CPU by
+    tests/test_oracle_golden.py; the real instance is patched in tests/test_reference_patch.py)."""
     g = np.load(golden_dir / "probpose_loss.npz")
     wl = synth.WORKLOADS[3]
-    mod = pp.ProbPoseLoss(pp.Codec(pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)), freeze_error=freeze)
+    codec = pp.Codec(pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas))
+    mod = pp.patch_probpose_loss(oc.ProbPoseLossLayout(codec, freeze_error=freeze))
+    assert isinstance(mod.keypoint_loss_module, pp.FusedOKSHeatmapLoss)
     gt = {k.split("/", 1)[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith("gt/")}     # host tensors, as a DataLoader yields
     pred = [torch.from_numpy(g[k]).cuda().requires_grad_(True) for k in ("dt_heatmaps", "dt_probs", "dt_vis", "dt_oks", "dt_errs")]
     if kwargs.get("keypoint_weights"):
         kwargs = dict(keypoint_weights=torch.from_numpy(g["keypoint_weights"]).cuda())
     np.random.seed(99)
-    losses, acc = mod(gt, tuple(pred), compute_acc=True, **kwargs)
+    losses, acc = oc.training_losses(mod, gt, tuple(pred), compute_acc=True, **kwargs)
     sum(losses.values()).backward()
     for k, v in losses.items():
         want = float(g[f"{name}/loss/{k}"])
@@ -1029,90 +1042,84 @@ def test_probpose_loss_matches_reference_forward_and_backward(pp, golden_dir, na
         else:   # the OKS / error targets come out of a DARK decode (1e-6 apart): 1e-5 of the gradient's scale
             np.testing.assert_allclose(p_.grad.cpu().numpy(), want, rtol=RTOL32, atol=RTOL32 * np.abs(want).max())
     # without accuracies the call returns the dictionary alone
-    assert set(mod(gt, tuple(p_.detach() for p_ in pred))) == {"kpt", "probability", "visibility", "oks", "error"}
+    assert set(oc.training_losses(mod, gt, tuple(p_.detach() for p_ in pred))) == {"kpt", "probability", "visibility", "oks", "error"}
 
 
-def test_probpose_loss_keypoint_ground_truth_front_end(pp):
-    """A GT dict that carries keypoints instead of heatmaps (section 8 f-3) gives the same losses as the
-    reference-layout dict built by per-sample ``encode`` on the host."""
+def test_lazy_per_pixel_loss_is_the_fused_mean_or_the_real_map(pp):
+    """What the patched keypoint_loss_module returns for per_pixel=True: .mean() is the fused forward+backward kernel,
+    anything else materialises the reference's (B, K, H, W) map."""
+    torch.manual_seed(5)
+    out, tgt, w = torch.rand(3, 5, 64, 48), torch.rand(3, 5, 64, 48), (torch.rand(3, 5) < 0.7).float()
+    o_ref = out.clone().requires_grad_(True)
+    ref_map = oc.oks_heatmap_loss(o_ref, tgt, w, per_pixel=True, smoothing_weight=0.05, oks_type="minus")
+    ref_map.mean().backward()
+    mod = pp.FusedOKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus")
+    o = out.cuda().requires_grad_(True)
+    lazy = mod(o, tgt.cuda(), w.cuda(), per_pixel=True)
+    m = lazy.mean()
+    assert lazy._tensor is None                      # nothing (B, K, H, W)-sized was written
+    m.backward()
+    assert abs(m.item() - ref_map.mean().item()) <= RTOL32 * abs(ref_map.mean().item())
+    _close(o.grad.cpu().numpy(), o_ref.grad.numpy(), RTOL32)
+    lazy2 = mod(o.detach(), tgt.cuda(), w.cuda(), per_pixel=True)
+    _close((lazy2 * 2.0).cpu().numpy(), 2.0 * ref_map.detach().numpy(), RTOL32)
+    _close(torch.sum(lazy2, dim=(2, 3)).cpu().numpy(), ref_map.detach().sum(dim=(2, 3)).numpy(), RTOL32)
+    assert lazy2[0, 0].shape == (64, 48) and lazy2._tensor is not None
+
+
+def test_ground_truth_from_keypoints_front_end(pp):
+    """A loader that ships keypoints (section 8 f-3): ground_truth_from_keypoints builds the reference-layout GT dict
+    on the device; the losses equal the ones from the dict built by per-sample ``encode`` on the host."""
     wl = synth.WORKLOADS[3]
     B = 5
     kps, vis, visibility = synth.make_keypoints(wl, batch=B, seed=21)
     am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
-    mod = pp.ProbPoseLoss(pp.Codec(am), freeze_error=False)
+    mod = pp.patch_probpose_loss(oc.ProbPoseLossLayout(pp.Codec(am), freeze_error=False))
     enc = [am.encode(kps[b:b + 1], vis[b:b + 1] > 0.5) for b in range(B)]
     gt_ref = dict(heatmaps=torch.from_numpy(np.stack([e["heatmaps"] for e in enc])),
                   in_image=torch.from_numpy(np.concatenate([e["in_image"] for e in enc])),
                   keypoints_visible=torch.from_numpy(vis > 0.5), keypoints_visibility=torch.from_numpy(visibility > 0.5))
-    gt_kp = dict(keypoints=torch.from_numpy(kps), keypoints_visible=gt_ref["keypoints_visible"],
-                 keypoints_visibility=gt_ref["keypoints_visibility"])
+    gt_kp = pp.ground_truth_from_keypoints(mod, kps, vis > 0.5, visibility > 0.5)
+    assert gt_kp["heatmaps"].is_cuda and gt_kp["heatmaps"].shape == (B, 17, 64, 48)
     jit = torch.from_numpy(synth.jitter_keypoints(wl, kps, seed=22)).cuda()
     hm = (am.encode_batch(jit, None)["heatmaps"] * 0.7 + 0.002).clamp(0, 1)
     torch.manual_seed(2)
     heads = [torch.rand(B, 17, 1, 1, device="cuda") * 0.9 + 0.05 for _ in range(4)]
-    a = mod(gt_ref, (hm, *heads))
-    b = mod(gt_kp, (hm, *heads))
+    a = oc.training_losses(mod, gt_ref, (hm, *heads))
+    b = oc.training_losses(mod, gt_kp, (hm, *heads))
     for k in a:
         assert abs(a[k].item() - b[k].item()) <= 1e-6 * abs(a[k].item()) + 1e-9, k
 
 
-# ---- kernel variants that are off by default (kept with their measurements in DESIGN.md / profiles) -----------
-def test_dense_decoder_variant_matches_golden_and_default(pp, golden_dir, monkeypatch):
-    """PP_DECODE_DENSE=1 selects the unpruned, per-radius specialised expected-OKS kernel (pp_decode_dense.cuh):
-    same bit-exact argmax / values and the same coordinates as the reference and as the default kernel."""
-    g = np.load(golden_dir / "decode.npz")
-    wl = synth.WORKLOADS[3]
+def test_head_tail_matches_reference_head_outputs(pp, golden_dir):
+    """tests/golden/head.npz: activations entering the tail of the REFERENCE's ProbMapHead.forward_heatmap (captured
+    with a hook on its final_layer) and what the reference returned (head.py:513-534).  The fused tail -- alone, through
+    patch_probmap_head on a module with the reference's member names, and fused into both decoders' load -- must give
+    the reference's heatmaps bit for bit."""
+    g = np.load(golden_dir / "head.npz")
+    pre = torch.from_numpy(g["pre_tail"]).cuda()
+    want = torch.from_numpy(g["heatmaps"]).cuda()
+    t = float(g["temperature"])
+    assert np.array_equal(g["heatmaps"], g["forward_heatmaps"])
+    assert torch.equal(pp.heatmap_tail(pre, t), want)
+
+    class Carrier(torch.nn.Module):     # the reference head's member names; the layer stacks are identities here
+        def __init__(self):
+            super().__init__()
+            self.deconv_layers = self.conv_layers = self.final_layer = torch.nn.Identity()
+            self.temperature, self.normalize = t, None
+
+    head = pp.patch_probmap_head(Carrier())
+    assert torch.equal(head.forward_heatmap(pre), want)
+    wl = synth.WORKLOADS[2]
     pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
-    maps = {n: torch.from_numpy(g[n]).cuda() for n in ("blob", "uniform", "clean")}
-    const = torch.zeros(2, 17, 64, 48, device="cuda")
-    const[1] = 0.25
-    plateau = torch.zeros(1, 17, 64, 48, device="cuda")
-    plateau[:, :, 20:40, 10:30] = 0.5                              # thousands of tied candidates -> overflow walk
-    ref = {n: pm.decode_device(m) for n, m in {**maps, "const": const, "plateau": plateau}.items()}
-    monkeypatch.setenv("PP_DECODE_DENSE", "1")
-    for n, m in {**maps, "const": const, "plateau": plateau}.items():
-        out = pm.decode_device(m)
-        assert torch.equal(out["argmax"], ref[n]["argmax"]), n
-        assert torch.equal(out["vals"], ref[n]["vals"]), n
-        assert torch.equal(out["locs"], ref[n]["locs"]), n
-        if n in maps:
-            assert np.array_equal(out["vals"].cpu().numpy(), g[f"{n}_vals"])
-            np.testing.assert_allclose(out["locs"].cpu().numpy(), g[f"{n}_locs"], rtol=RTOL32, atol=1e-5)
-    # fused head tail and bf16 through the same variant
-    x = (maps["blob"] * 0.5)
-    a = pm.decode_device(x, temperature=0.5)
-    monkeypatch.setenv("PP_DECODE_DENSE", "0")
-    b = pm.decode_device(x, temperature=0.5)
-    assert torch.equal(a["argmax"], b["argmax"]) and torch.equal(a["locs"], b["locs"])
-    monkeypatch.setenv("PP_DECODE_DENSE", "1")
-    xb = maps["blob"].bfloat16()
-    a = pm.decode_device(xb)
-    monkeypatch.setenv("PP_DECODE_DENSE", "0")
-    b = pm.decode_device(xb)
-    assert torch.equal(a["argmax"], b["argmax"]) and torch.equal(a["locs"], b["locs"])
-
-
-def test_paired_loss_variant_matches_default(pp, monkeypatch):
-    """PP_LOSS_PAIR=1 selects the two-heatmaps-per-thread FADD2 / FFMA2 loss kernel (pp_loss_pair.cuh); odd and even
-    heatmap counts, with and without the MSE term."""
-    torch.manual_seed(8)
-    for B, K in ((3, 5), (2, 4), (1, 1)):
-        out, tgt = torch.rand(B, K, 64, 48), torch.rand(B, K, 64, 48)
-        tw = (torch.rand(B, K) < 0.7).float()
-        for kw in (dict(smoothing_weight=0.05, oks_type="minus"), dict(smoothing_weight=0.2, gaussian_weight=0.15, oks_type="both")):
-            res = []
-            for flag in ("0", "1"):
-                monkeypatch.setenv("PP_LOSS_PAIR", flag)
-                o = out.cuda().requires_grad_(True)
-                l = pp.OKSHeatmapLoss(use_target_weight=True, **kw).forward_mean(o, tgt.cuda(), tw.cuda())
-                l.backward()
-                res.append((l.item(), o.grad.cpu().numpy()))
-            o_ref = out.clone().requires_grad_(True)
-            l_ref = oc.oks_heatmap_loss(o_ref, tgt, tw, per_pixel=True, **kw).mean()
-            l_ref.backward()
-            for l, gr in res:
-                assert abs(l - l_ref.item()) <= RTOL32 * abs(l_ref.item()) + 1e-9
-                _close(gr, o_ref.grad.numpy(), RTOL32)
+    a, b = pm.decode_device(pre, temperature=t), pm.decode_device(want)
+    for key in ("locs", "vals", "argmax", "keypoints"):
+        assert torch.equal(a[key], b[key]), key
+    for bi in range(want.shape[0]):
+        l, v, conv = oc.heatmap_expected_value(g["heatmaps"][bi], wl.sigmas, return_heatmap=True, conv="scipy")
+        assert np.array_equal(a["argmax"][bi].cpu().numpy(), conv.reshape(17, -1).argmax(1))
+        assert np.array_equal(a["vals"][bi].cpu().numpy(), v)
 
 
 # --------------------------------------------------------------------------- records + peer mailbox
@@ -1165,14 +1172,17 @@ def test_pack_records_and_single_process_mailbox(pp):
 
 
 def test_expected_decoder_kernel_selection(pp, monkeypatch):
-    """pp_decode_expected_last_kernel reports the kernel the size rule picked: small batches take the CTA-per-heatmap
-    kernel, batches with at least two heatmaps per resident warp the warp-per-heatmap kernel, odd shapes the generic
-    one; both fast kernels agree bit for bit."""
+    """pp_decode_expected_last_kernel reports the kernel that ran: the tensor-core kernel for the shapes it is built
+    for; without it small batches take the CTA-per-heatmap kernel, batches with at least two heatmaps per resident warp
+    the warp-per-heatmap kernel, odd shapes the generic one; all of them agree bit for bit."""
     from probpose_pytorch_b200 import _lib
     wl = synth.WORKLOADS[2]
     pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
     last = _lib.lib().pp_decode_expected_last_kernel
     small = torch.rand(4, 17, 64, 48, device="cuda")
+    m = pm.decode_device(small)
+    assert last() == 5
+    monkeypatch.setenv("PP_DECODE_MMA", "0")
     a = pm.decode_device(small)
     assert last() == 1
     monkeypatch.setenv("PP_DECODE_WARP", "1")
@@ -1180,7 +1190,7 @@ def test_expected_decoder_kernel_selection(pp, monkeypatch):
     assert last() == 2
     monkeypatch.delenv("PP_DECODE_WARP")
     for key in ("locs", "vals", "argmax", "keypoints"):
-        assert torch.equal(a[key], b[key]), key
+        assert torch.equal(a[key], b[key]) and torch.equal(a[key], m[key]), key
     big = torch.rand(256, 17, 64, 48, device="cuda") * 0.02
     big[:, :, 30, 20] = 1.0
     c = pm.decode_device(big)
@@ -1188,8 +1198,187 @@ def test_expected_decoder_kernel_selection(pp, monkeypatch):
     monkeypatch.setenv("PP_DECODE_WARP", "0")
     d = pm.decode_device(big)
     assert last() == 1
-    for key in ("locs", "vals", "argmax", "keypoints"):
-        assert torch.equal(c[key], d[key]), key
     monkeypatch.delenv("PP_DECODE_WARP")
+    monkeypatch.delenv("PP_DECODE_MMA")
+    e = pm.decode_device(big)
+    assert last() == 5
+    for key in ("locs", "vals", "argmax", "keypoints"):
+        assert torch.equal(c[key], d[key]) and torch.equal(c[key], e[key]), key
     l, v = pp.get_heatmap_expected_value(np.random.default_rng(3).random((5, 19, 27), dtype=np.float32), np.full(5, 0.07))
     assert last() == 4
+
+
+# --------------------------------------------------------------------------- tensor-core prefilter + full batches
+def _exact_conv(hm, sigmas, k):
+    """float32 exact convolved map of ONE heatmap of channel k (scipy, the reference's call)."""
+    return oc.heatmap_expected_value(hm[None], np.asarray(sigmas)[k:k + 1], return_heatmap=True, conv="scipy")[2][0]
+
+
+@pytest.mark.parametrize("case", ["blob", "uniform", "range", "negative", "bf16", "c4"])
+def test_mma_prefilter_error_bound(pp, case):
+    """The tensor-core kernel only PROPOSES candidates; its rigorous bound |Z(p) - R(p) - const| <= kMmaErr in units of
+    the scaled range (pp_decode_mma.cuh) is what guarantees that the exact argmax is among them.  The debug entry point
+    returns Z; check the bound against the exact convolution on every pixel."""
+    import ctypes as C
+    from probpose_pytorch_b200 import _lib
+    from probpose_pytorch_b200.heatmap import _oks_table
+    wl = synth.WORKLOADS[4 if case == "c4" else 2]
+    K, (W, H) = wl.num_keypoints, wl.heatmap_size
+    rng = np.random.default_rng(77)
+    B = 3
+    if case in ("blob", "bf16", "c4"):
+        kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=71)
+        tgt = _oracle_encode("argmax", wl, synth.jitter_keypoints(wl, kps, 72), vis)["heatmaps"]
+        maps = synth.blob_predictions_numpy(tgt, synth.blob_params(tgt.shape[:2], 73), 74)
+    elif case == "uniform":
+        maps = rng.random((B, K, H, W), dtype=np.float32)
+    elif case == "range":      # values spread over 40 binary orders of magnitude, tiny and huge overall scales
+        maps = (rng.random((B, K, H, W)) * np.exp2(rng.integers(-40, 1, size=(B, K, H, W)))).astype(np.float32)
+        maps[0] *= np.float32(1e-20)
+        maps[1] *= np.float32(1e20)
+    else:                      # negative: raw logits, small variation on a large offset
+        maps = rng.normal(0.0, 1.0, size=(B, K, H, W)).astype(np.float32)
+        maps[1] = (100.0 + 1e-2 * maps[1]).astype(np.float32)
+        maps[2] = -np.abs(maps[2])
+    t = torch.from_numpy(maps).cuda()
+    if case == "bf16":
+        t = t.bfloat16()
+        maps = t.float().cpu().numpy()
+    tab = _oks_table(wl.sigmas, K, H, W, t.device)
+    assert tab.mma_tables is not None
+    p = _lib.DecodeParams(B, K, H, W, _lib.dtype_code(t.dtype), 0, 1.0, 0.0, 0.0)
+    locs = torch.empty((B, K, 2), device="cuda")
+    vals = torch.empty((B, K), device="cuda")
+    arg = torch.full((B, K), -1, dtype=torch.int32, device="cuda")
+    pre = torch.full((B, K, H, W), float("nan"), device="cuda")
+    scratch = torch.zeros(int(_lib.lib().pp_decode_expected_scratch_bytes_for(p)) // 4 + 1, dtype=torch.int32, device="cuda")
+    fn = _lib.lib().pp_debug_decode_mma_prefilter
+    fn.argtypes = [C.POINTER(_lib.DecodeParams), C.POINTER(_lib.OksTable)] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
+    rc = fn(p, tab.descriptor(), _lib.ptr(t), _lib.ptr(locs), _lib.ptr(vals), _lib.ptr(arg), _lib.ptr(pre), _lib.ptr(scratch),
+            scratch.numel() * 4, _lib.stream_ptr(t.device))
+    _lib.check(rc, "pp_debug_decode_mma_prefilter")
+    torch.cuda.synchronize()
+    pre = pre.cpu().numpy().astype(np.float64)
+    handed = set(scratch[4:4 + int(scratch[2])].cpu().tolist())
+    worst = 0.0
+    for b in range(B):
+        for k in range(K):
+            if b * K + k in handed:
+                assert np.isnan(pre[b, k]).all()
+                continue
+            R = _exact_conv(maps[b, k], wl.sigmas, k).astype(np.float64)
+            rng_ = float(maps[b, k].max()) - float(maps[b, k].min())
+            unit = np.exp2(np.floor(np.log2(np.float32(rng_))) + 1)      # 1 / sc: the scaled range lies in [0.5, 1)
+            diff = (pre[b, k] - R) / unit
+            # the constant is (sum of taps)^2 - 1 times min h, plus float32 rounding of Z / sc + vmin: centre it
+            diff -= 0.5 * (diff.max() + diff.min())
+            f32 = 2.0 ** -22 * max(abs(float(maps[b, k].max())), abs(float(maps[b, k].min()))) / unit
+            worst = max(worst, float(np.abs(diff).max()) - f32)
+            assert np.abs(diff).max() <= 2.2e-3 + f32, (case, b, k, np.abs(diff).max())
+            assert int(arg[b, k]) == int(R.astype(np.float32).argmax())
+    assert case in ("range", "negative") or not handed
+    print(f"{case}: worst proposal error {worst:.2e} of the 2.2e-3 bound; {len(handed)} handed over")
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_expected_decoder_full_c2_batch_vs_oracle(pp, dtype, expected_kernel):
+    """ALL 4 352 heatmaps of BASELINE config 2 (B = 256, bench.py's inputs) against the oracle's scipy convolution:
+    argmax and scores bit-exact, coordinates within 1e-5 -- on the persistent multi-heatmap-per-warp paths the
+    benchmark times."""
+    if expected_kernel not in ("auto", "mma-grid2", "nomma", "team1-grid3", "cta"):
+        pytest.skip("covered by the other kernels' runs")
+    wl = synth.WORKLOADS[2]
+    B, K = wl.batch, wl.num_keypoints
+    kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=1002)
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    blob = am.encode_batch(synth.jitter_keypoints(wl, kps, seed=5000), vis)["heatmaps"]
+    amp = torch.from_numpy(synth.blob_params((B, K), seed=6000)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    pred = (blob * amp[:, :, None, None] + torch.rand(blob.shape, device="cuda", generator=g) * 0.02).clamp_(0, 1)
+    if dtype == "bf16":
+        pred = pred.bfloat16()
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = pm.decode_device(pred)
+    host = pred.float().cpu().numpy()
+    arg, locs, vals = dev["argmax"].cpu().numpy(), dev["locs"].cpu().numpy(), dev["vals"].cpu().numpy()
+    mism = 0
+    for b in range(B):
+        l, v, conv = oc.heatmap_expected_value(host[b], wl.sigmas, return_heatmap=True, conv="scipy")
+        mism += int(np.count_nonzero(arg[b] != conv.reshape(K, -1).argmax(1)))
+        np.testing.assert_allclose(locs[b], l, rtol=RTOL32, atol=1e-5)
+        assert np.array_equal(vals[b], v)
+    assert mism == 0, f"{mism} argmax mismatches in {B * K} heatmaps"
+
+
+@pytest.mark.parametrize("cid,dtype", [(4, "fp32"), (4, "bf16"), (5, "fp32"), (5, "bf16")])
+def test_expected_decoder_full_size_sampled_vs_oracle(pp, cid, dtype):
+    """BASELINE configs 4 (8 704 heatmaps of 96x72) and 5 (68 096 heatmaps, K = 133) decoded at full size with the
+    auto-selected kernel; 2 048 randomly chosen heatmaps of each are checked against the oracle (scipy convolution):
+    argmax / scores bit-exact, coordinates 1e-5."""
+    wl = synth.WORKLOADS[cid]
+    B, K = wl.batch, wl.num_keypoints
+    W, H = wl.heatmap_size
+    kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=1000 + cid)
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    blob = am.encode_batch(synth.jitter_keypoints(wl, kps, seed=5000), vis)["heatmaps"]
+    amp = torch.from_numpy(synth.blob_params((B, K), seed=6000)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    pred = (blob * amp[:, :, None, None]).add_(torch.rand(blob.shape, device="cuda", generator=g) * 0.02).clamp_(0, 1)
+    del blob
+    if dtype == "bf16":
+        pred = pred.bfloat16()
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = pm.decode_device(pred)
+    from probpose_pytorch_b200 import _lib
+    assert _lib.lib().pp_decode_expected_last_kernel() == 5
+    pick = np.random.default_rng(cid).choice(B * K, size=2048, replace=False)
+    flat = pred.reshape(B * K, H, W)[torch.from_numpy(pick).cuda()].float().cpu().numpy()
+    arg = dev["argmax"].reshape(-1).cpu().numpy()[pick]
+    locs = dev["locs"].reshape(-1, 2).cpu().numpy()[pick]
+    vals = dev["vals"].reshape(-1).cpu().numpy()[pick]
+    sig = np.asarray(wl.sigmas)
+    mism = 0
+    for i, n in enumerate(pick):
+        k = int(n % K)
+        l, v, conv = oc.heatmap_expected_value(flat[i][None], sig[k:k + 1], return_heatmap=True, conv="scipy")
+        mism += int(arg[i] != conv.reshape(-1).argmax())
+        np.testing.assert_allclose(locs[i], l[0], rtol=RTOL32, atol=1e-5)
+        assert vals[i] == v[0]
+    assert mism == 0, f"{mism} argmax mismatches in 2048 sampled heatmaps of C{cid}"
+
+
+def test_dark_and_loss_persistent_loops_vs_oracle(pp, monkeypatch):
+    """decode_dark_fast_kernel and oks_loss_fast_kernel with the launch capped at a few CTAs (PP_DARK_GRID / PP_LOSS_GRID):
+    every CTA walks >= 8 heatmaps / units through its work queue, TMA refill and double-buffered stages -- the loops
+    bench.py times -- and must still match the oracle."""
+    wl = synth.WORKLOADS[2]
+    B, K = 6, wl.num_keypoints
+    kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=311)
+    tgt = _oracle_encode("argmax", wl, kps, vis)["heatmaps"]
+    clean = _oracle_encode("argmax", wl, synth.jitter_keypoints(wl, kps, 312), np.ones_like(vis))["heatmaps"]
+    monkeypatch.setenv("PP_DARK_GRID", "4")
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = am.decode_device(torch.from_numpy(clean).cuda())
+    for b in range(B):
+        kp_ref, sc_ref = oc.decode_argmax_dark(clean[b], wl.input_size, wl.heatmap_size, backend="cv2")
+        peaks, _ = oc.heatmap_maximum(clean[b])
+        assert np.array_equal(dev["peaks"][b].cpu().numpy(), peaks)
+        assert np.array_equal(dev["scores"][b].cpu().numpy(), sc_ref[0])
+        ok = peaks[:, 0] >= 0
+        bound = RTOL32 * np.maximum(np.abs(kp_ref[0]), 1.0) + _dark_tolerance(clean[b], peaks, wl, RTOL32)
+        assert (np.abs(dev["keypoints"][b].cpu().numpy() - kp_ref[0])[ok] <= bound[ok]).all()
+    # loss: 102 heatmaps, G = 2 per unit -> 51 units over 3 CTAs = 17 units per CTA through both stages
+    monkeypatch.setenv("PP_LOSS_GRID", "3")
+    pred = synth.blob_predictions_numpy(clean, synth.blob_params(clean.shape[:2], 313), 314)
+    for dt, rtol in ((torch.float32, RTOL32), (torch.bfloat16, RTOL16)):
+        o_ref = torch.from_numpy(pred).to(dt).float().requires_grad_(True)
+        t_ref = torch.from_numpy(tgt).to(dt).float()
+        w = torch.from_numpy(vis)
+        l_ref = oc.oks_heatmap_loss(o_ref, t_ref, w, per_pixel=True, smoothing_weight=0.05, oks_type="minus").mean()
+        l_ref.backward()
+        o = torch.from_numpy(pred).cuda().to(dt).requires_grad_(True)
+        l = pp.OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus").forward_mean(
+            o, torch.from_numpy(tgt).cuda().to(dt), w.cuda())
+        l.backward()
+        assert abs(l.item() - l_ref.item()) <= rtol * abs(l_ref.item()) + 1e-9
+        _close(o.grad.float().cpu().numpy(), o_ref.grad.numpy(), rtol)

@@ -206,3 +206,40 @@ def test_metrics_oracle_matches_reference_outputs(golden_dir):
     a, t = mo.binary_accuracy(m["scalar_dt"], m["scalar_gt"], m["mask"])
     assert a == m["binary/acc"] and t == m["binary/thr"]
     assert mo.masked_mae(m["scalar_dt"], m["scalar_gt"], m["mask"]) == m["mae"]
+
+
+@pytest.mark.parametrize("name,freeze,kwargs", [("frozen", True, {}), ("live", False, {}),
+                                                ("zeros", False, dict(learn_heatmaps_from_zeros=True)),
+                                                ("weights", True, dict(keypoint_weights=True))])
+def test_training_losses_restatement_matches_reference_forward(golden_dir, name, freeze, kwargs):
+    """oracle.training_losses + oracle.ProbPoseLossLayout (the stand-in the GPU tests patch) against the reference's
+    own ProbPoseLoss.forward run (tests/golden/probpose_loss.npz): losses, accuracies and gradients."""
+    g = np.load(golden_dir / "probpose_loss.npz")
+    wl = synth.WORKLOADS[3]
+
+    class PM:
+        input_size, heatmap_size, sigmas = wl.input_size, wl.heatmap_size, wl.sigmas
+
+    mod = oc.ProbPoseLossLayout(PM(), freeze_error=freeze)
+    gt = {k.split("/", 1)[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith("gt/")}
+    pred = [torch.from_numpy(g[k]).clone().requires_grad_(True) for k in ("dt_heatmaps", "dt_probs", "dt_vis", "dt_oks", "dt_errs")]
+    if kwargs.get("keypoint_weights"):
+        kwargs = dict(keypoint_weights=torch.from_numpy(g["keypoint_weights"]))
+    np.random.seed(99)
+    losses, acc = oc.training_losses(mod, gt, tuple(pred), compute_acc=True, **kwargs)
+    sum(losses.values()).backward()
+    for k, v in losses.items():
+        np.testing.assert_allclose(v.item(), float(g[f"{name}/loss/{k}"]), rtol=1e-6, atol=1e-9, err_msg=k)
+    for k, v in acc.items():
+        np.testing.assert_allclose(float(v), float(g[f"{name}/acc/{k}"]), rtol=1e-6, atol=1e-9, err_msg=k)
+    for n, p_ in zip(("heatmaps", "probs", "vis", "oks", "errs"), pred):
+        want = g[f"{name}/grad/{n}"]
+        np.testing.assert_allclose(p_.grad.numpy(), want, rtol=1e-5, atol=1e-6 * np.abs(want).max(), err_msg=n)
+
+
+def test_head_golden_is_the_reference_tail(golden_dir):
+    """tests/golden/head.npz (reference ProbMapHead outputs): the tail restatement reproduces them bit for bit."""
+    g = np.load(golden_dir / "head.npz")
+    assert np.array_equal(oc.head_tail(g["pre_tail"], float(g["temperature"])), g["heatmaps"])
+    frac = (g["heatmaps"] == 0).mean(), (g["heatmaps"] == 1).mean()
+    assert 0.2 < frac[0] < 0.6 and 0.05 < frac[1] < 0.4      # all three regimes of the clamp are populated
