@@ -243,6 +243,21 @@ PP_API int pp_oks_loss_forward(const pp_loss_params* p,
                         int32_t* target_out_of_range,
                         void* scratch, int64_t scratch_bytes, pp_stream_t stream);
 
+/* Encode-inside-loss: pp_encode (generate_probmaps, codec.py:11-70 + the flags of codec.py:187-200) followed by
+ * pp_oks_loss_forward(PP_LOSS_PIXEL_MEAN) with the fused gradient (loss.py:428-431), as ONE pass that never
+ * materialises the target: the kernel forms target[y][x] from the keypoint's separable float64 factors.  Per heatmap
+ * it reads `output` and writes `grad`: 2 H W e bytes instead of 1 (encode) + 3 (loss).
+ *   ep               : the encoder's parameters for the same (B, K, H, W); ep->heatmap_dtype is ignored (= p->dtype)
+ *   keypoints/visible/two_s : as for pp_encode
+ *   keypoint_weights : (B, K) weights of the loss, or NULL = the weights the encoder would return (codec.py:46,68)
+ *   weights_out, in_image, annotated : the encoder's (B, K) outputs, each may be NULL
+ * Shapes the fused kernel does not cover return PP_ERR_UNSUPPORTED_SHAPE (use pp_encode + pp_oks_loss_forward). */
+PP_API int pp_oks_loss_forward_encoded(const pp_loss_params* p, const pp_encode_params* ep, const void* output,
+                                       const void* keypoints, const float* visible, const double* two_s,
+                                       const float* keypoint_weights, float* loss_scalar, void* grad, float grad_scale,
+                                       float* weights_out, uint8_t* in_image, uint8_t* annotated, void* scratch,
+                                       int64_t scratch_bytes, pp_stream_t stream);
+
 typedef enum pp_upstream_kind {
   PP_UPSTREAM_SCALAR = 0, /* one float32 on the device, broadcast over the forward's output
                              (d L / d loss for PIXEL_MEAN; an expanded gradient for the other modes) */

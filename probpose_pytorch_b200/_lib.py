@@ -29,7 +29,7 @@ EXPORTS = (
     "pp_heatmap_maximum", "pp_decode_argmax_dark", "pp_heatmap_tail", "pp_heatmap_tail_backward",
     "pp_sparsemax_tail", "pp_sparsemax_tail_backward",
     "pp_oks_loss_scratch_bytes",
-    "pp_oks_loss_forward", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
+    "pp_oks_loss_forward", "pp_oks_loss_forward_encoded", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
     "pp_pck_accuracy", "pp_binary_accuracy", "pp_masked_mae",
     "pp_mailbox_block_bytes", "pp_pack_records", "pp_mailbox_commit", "pp_mailbox_wait",
 )
@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
     L.pp_oks_loss_scratch_bytes.argtypes = [C.POINTER(LossParams)]
     L.pp_oks_loss_scratch_bytes.restype = i64
     L.pp_oks_loss_forward.argtypes = [C.POINTER(LossParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, i64, vp]
+    L.pp_oks_loss_forward_encoded.argtypes = [C.POINTER(LossParams), C.POINTER(EncodeParams), vp, vp, vp, vp, vp, vp, vp, f32,
+                                              vp, vp, vp, vp, i64, vp]
     L.pp_oks_loss_backward.argtypes = [C.POINTER(LossParams), vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp]
     L.pp_scale_inplace.argtypes = [vp, i32, i64, vp, vp]
     L.pp_pose_targets.argtypes = [vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, vp]

@@ -26,7 +26,8 @@
 // map in float16) -> per block of 16 output columns: GEMM 1 (Y^T = Tx . H^T, <= 3 x 8 HMMA, A-fragments of Tx from a
 // per-channel table in L1 / L2), accumulators repacked in registers into the A-fragments of GEMM 2 (the C layout of two
 // adjacent n-blocks IS the A layout of one k-block), GEMM 2 (Z^T = Y^T . Ty^T, B-fragments of Ty from the table),
-// running maximum + candidate list.  No shared-memory writes besides the candidate list.
+// per-lane block maximum; after all blocks the warp-wide maximum fixes the threshold and the one or two blocks that
+// reach it are recomputed to list their candidates.  No shared-memory writes besides the candidate list.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -167,7 +168,6 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
   const T* plane = reinterpret_cast<const T*>(slot);
   T* plane_rw = reinterpret_cast<T*>(slot);
   int* cand = reinterpret_cast<int*>(slot + geo.cand_off);          // cand[0 .. kWCand) pixels, cand[kWCand] count
-  float* cand_val = reinterpret_cast<float*>(cand + kWCand + 4);    // their prefilter values
   uint64_t* bar = &bars[warp];
 
   const int N = p.B * p.K;   // the launcher guarantees N < 2^31
@@ -287,104 +287,100 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
 
         if (lane == 0) cand[kWCand] = 0;
         __syncwarp();
-        float gm = -INFINITY;
+        // Two passes over the blocks of 16 output columns.  Pass 0 computes every block and keeps only the lane's
+        // maximum per block; the warp-wide maximum then fixes the candidate threshold, and pass 1 recomputes just the
+        // blocks that reach it (one, rarely two) and lists their pixels above the threshold.  (Listing against a
+        // running maximum in a single pass does not work here: the band is ~0.5 % of the map's range, so the flat
+        // background of the blocks visited before the blob would be listed wholesale.)
+        float gm = -INFINITY, thr = INFINITY;
+        float mblk[S::MB];
+        unsigned need = 0u;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-        for (int mb = 0; mb < S::MB; ++mb) {
-          // GEMM 1: Y^T[16 mb + ..][y] = sum_x Tx[x'][x] h~[y][x]; only |mb - kb| <= 1 tiles are non-zero (radius <= 9)
-          float acc1[S::NB][4];
+          for (int mb = 0; mb < S::MB; ++mb) {
+            if (pass == 1 && !((need >> mb) & 1u)) continue;
+            // GEMM 1: Y^T[16 mb + ..][y] = sum_x Tx[x'][x] h~[y][x]; only |mb - kb| <= 1 tiles are non-zero (radius <= 9)
+            float acc1[S::NB][4];
 #pragma unroll
-          for (int nbk = 0; nbk < S::NB; ++nbk)
+            for (int nbk = 0; nbk < S::NB; ++nbk)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc1[nbk][c] = 0.0f;
+              for (int c = 0; c < 4; ++c) acc1[nbk][c] = 0.0f;
 #pragma unroll
-          for (int kb = 0; kb < S::KB; ++kb) {
-            if (kb < mb - 1 || kb > mb + 1) continue;
-            const uint4 a4 = __ldg(t1 + (mb * S::KB + kb) * 32 + lane);
-            const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
+            for (int kb = 0; kb < S::KB; ++kb) {
+              if (kb < mb - 1 || kb > mb + 1) continue;
+              const uint4 a4 = __ldg(t1 + (mb * S::KB + kb) * 32 + lane);
+              const uint32_t a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int nbk = 0; nbk < S::NB; ++nbk) mma16816(acc1[nbk], a, hf[kb][nbk][0], hf[kb][nbk][1]);
-          }
-          // the accumulators of n-blocks (2 j, 2 j + 1) are the A fragment of k-block j of GEMM 2
-          uint32_t ya[S::KB2][4];
-#pragma unroll
-          for (int j = 0; j < S::KB2; ++j) {
-            ya[j][0] = pack_h2(acc1[2 * j][0], acc1[2 * j][1]);
-            ya[j][1] = pack_h2(acc1[2 * j][2], acc1[2 * j][3]);
-            ya[j][2] = pack_h2(acc1[2 * j + 1][0], acc1[2 * j + 1][1]);
-            ya[j][3] = pack_h2(acc1[2 * j + 1][2], acc1[2 * j + 1][3]);
-          }
-          // GEMM 2: Z^T[x'][y'] = sum_y Y^T[x'][y] Ty[y'][y]; tiles with |kb2 - nbp| <= 1 only
-          float z[S::NB][4];
-#pragma unroll
-          for (int nbk = 0; nbk < S::NB; ++nbk)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) z[nbk][c] = 0.0f;
-#pragma unroll
-          for (int nbp = 0; nbp < S::NBP; ++nbp)
-#pragma unroll
-            for (int kb2 = 0; kb2 < S::KB2; ++kb2) {
-              if (kb2 < nbp - 1 || kb2 > nbp + 1) continue;
-              const uint4 b4 = __ldg(t2 + (kb2 * S::NBP + nbp) * 32 + lane);
-              mma16816(z[2 * nbp], ya[kb2], b4.x, b4.y);
-              mma16816(z[2 * nbp + 1], ya[kb2], b4.z, b4.w);
+              for (int nbk = 0; nbk < S::NB; ++nbk) mma16816(acc1[nbk], a, hf[kb][nbk][0], hf[kb][nbk][1]);
             }
-          // z[nb][c]: column x' = 16 mb + g + 8 (c >> 1), row y' = 8 nb + 2 t + (c & 1)
-          const bool hi_ok = 16 * mb + 8 + 8 <= W;   // the rows g + 8 of the last block lie beyond W when W = 8 mod 16
-          float m = -INFINITY;
+            // the accumulators of n-blocks (2 j, 2 j + 1) are the A fragment of k-block j of GEMM 2
+            uint32_t ya[S::KB2][4];
 #pragma unroll
-          for (int nbk = 0; nbk < S::NB; ++nbk) {
-            m = fmaxf(m, fmaxf(z[nbk][0], z[nbk][1]));
-            if (hi_ok) m = fmaxf(m, fmaxf(z[nbk][2], z[nbk][3]));
-          }
-          if (dbg_prefilter) {
-            const float inv = 1.0f / sc;
-#pragma unroll
-            for (int nbk = 0; nbk < S::NB; ++nbk)
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (c < 2 || hi_ok)
-                  dbg_prefilter[static_cast<size_t>(hm) * HW + (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1)] =
-                      z[nbk][c] * inv + vmin;
-          }
-          gm = fmaxf(gm, warp_max(m));
-          const float lo = gm - band;
-          if (m >= lo) {   // rare: new running maxima and near ties
+            for (int j = 0; j < S::KB2; ++j) {
+              ya[j][0] = pack_h2(acc1[2 * j][0], acc1[2 * j][1]);
+              ya[j][1] = pack_h2(acc1[2 * j][2], acc1[2 * j][3]);
+              ya[j][2] = pack_h2(acc1[2 * j + 1][0], acc1[2 * j + 1][1]);
+              ya[j][3] = pack_h2(acc1[2 * j + 1][2], acc1[2 * j + 1][3]);
+            }
+            // GEMM 2: Z^T[x'][y'] = sum_y Y^T[x'][y] Ty[y'][y]; tiles with |kb2 - nbp| <= 1 only
+            float z[S::NB][4];
 #pragma unroll
             for (int nbk = 0; nbk < S::NB; ++nbk)
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if ((c < 2 || hi_ok) && z[nbk][c] >= lo) {
-                  const int s = atomicAdd(&cand[kWCand], 1);
-                  if (s < kWCand) {
-                    cand[s] = (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1);
-                    cand_val[s] = z[nbk][c];
+              for (int c = 0; c < 4; ++c) z[nbk][c] = 0.0f;
+#pragma unroll
+            for (int nbp = 0; nbp < S::NBP; ++nbp)
+#pragma unroll
+              for (int kb2 = 0; kb2 < S::KB2; ++kb2) {
+                if (kb2 < nbp - 1 || kb2 > nbp + 1) continue;
+                const uint4 b4 = __ldg(t2 + (kb2 * S::NBP + nbp) * 32 + lane);
+                mma16816(z[2 * nbp], ya[kb2], b4.x, b4.y);
+                mma16816(z[2 * nbp + 1], ya[kb2], b4.z, b4.w);
+              }
+            // z[nb][c]: column x' = 16 mb + g + 8 (c >> 1), row y' = 8 nb + 2 t + (c & 1)
+            const bool hi_ok = 16 * mb + 8 + 8 <= W;   // the rows g + 8 of the last block lie beyond W when W = 8 mod 16
+            if (pass == 0) {
+              float m = -INFINITY;
+#pragma unroll
+              for (int nbk = 0; nbk < S::NB; ++nbk) {
+                m = fmaxf(m, fmaxf(z[nbk][0], z[nbk][1]));
+                if (hi_ok) m = fmaxf(m, fmaxf(z[nbk][2], z[nbk][3]));
+              }
+              mblk[mb] = m;
+              gm = fmaxf(gm, m);
+              if (dbg_prefilter) {
+                const float inv = 1.0f / sc;
+#pragma unroll
+                for (int nbk = 0; nbk < S::NB; ++nbk)
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    if (c < 2 || hi_ok)
+                      dbg_prefilter[static_cast<size_t>(hm) * HW + (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1)] =
+                          z[nbk][c] * inv + vmin;
+              }
+            } else if (mblk[mb] >= thr) {
+#pragma unroll
+              for (int nbk = 0; nbk < S::NB; ++nbk)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if ((c < 2 || hi_ok) && z[nbk][c] >= thr) {
+                    const int s = atomicAdd(&cand[kWCand], 1);
+                    if (s < kWCand) cand[s] = (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1);
                   }
-                }
+            }
+          }
+          if (pass == 0) {
+            gm = warp_max(gm);
+            thr = gm - band;
+#pragma unroll
+            for (int mb = 0; mb < S::MB; ++mb) need |= (__any_sync(0xffffffffu, mblk[mb] >= thr) ? 1u : 0u) << mb;
           }
         }
         __syncwarp();
-        const float thr = gm - band;
-        const int raw = cand[kWCand];
-        handed_over = raw > kWCand;
+        const int count = cand[kWCand];
+        handed_over = count > kWCand;
         if (!handed_over) {
-          // keep the listed pixels that are inside the band of the final maximum
-          int keep_id[kWCand / 32];
-          bool keep[kWCand / 32];
-#pragma unroll
-          for (int u = 0; u < kWCand / 32; ++u) {
-            const int e = lane + u * 32;
-            keep[u] = e < raw && cand_val[min(e, kWCand - 1)] >= thr;
-            keep_id[u] = cand[min(e, kWCand - 1)];
-          }
-          __syncwarp();
-          if (lane == 0) cand[kWCand] = 0;
-          __syncwarp();
-#pragma unroll
-          for (int u = 0; u < kWCand / 32; ++u)
-            if (keep[u]) cand[atomicAdd(&cand[kWCand], 1)] = keep_id[u];
-          __syncwarp();
-          const int count = cand[kWCand];
-
           // ---- G: exact values of the candidates and of the winner's four neighbours
           TeamExact<T> te;
           te.plane = plane; te.w2d = w2dk; te.ex = nullptr; te.H = H; te.W = W; te.r = r; te.d = 2 * r + 1;

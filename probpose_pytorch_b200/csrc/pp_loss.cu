@@ -299,10 +299,10 @@ bool fast_path_ok(const pp_loss_params& p, const void* output, const void* targe
          static_cast<int64_t>(p.H) * p.W * e + 512 <= pp_smem_optin();
 }
 
-template <typename T, bool kFwd, bool kGrad, bool kTgtSmem>
+template <typename T, bool kFwd, bool kGrad, int kTgt>
 int launch_fast_tt(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
   int per_sm = 1;
-  auto kern = pp_loss_fast::oks_loss_fast_kernel<T, kFwd, kGrad, kTgtSmem>;
+  auto kern = pp_loss_fast::oks_loss_fast_kernel<T, kFwd, kGrad, kTgt>;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), threads, smem, &per_sm)) return rc;
   if (const int cap = env_int("PP_LOSS_CTAS", 0); cap > 0) per_sm = std::min(per_sm, cap);
   const int64_t units = (a.N + a.G - 1) / a.G;
@@ -333,15 +333,33 @@ int launch_pair_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cud
 
 template <typename T, bool kFwd, bool kGrad>
 int launch_fast_t(const pp_loss_fast::FastArgs& a, int threads, size_t smem, cudaStream_t st, int* grid_out) {
-  if (a.tgt_off != 0) return launch_fast_tt<T, kFwd, kGrad, true>(a, threads, smem, st, grid_out);
-  return launch_fast_tt<T, kFwd, kGrad, false>(a, threads, smem, st, grid_out);
+  if (a.keypoints) return launch_fast_tt<T, kFwd, kGrad, pp_loss_fast::kTgtEncode>(a, threads, smem, st, grid_out);
+  if (a.tgt_off != 0) return launch_fast_tt<T, kFwd, kGrad, pp_loss_fast::kTgtSmem>(a, threads, smem, st, grid_out);
+  return launch_fast_tt<T, kFwd, kGrad, pp_loss_fast::kTgtGlobal>(a, threads, smem, st, grid_out);
 }
+
+// the encoder's inputs for the encode-inside-loss variant (target == nullptr)
+struct EncodeSource {
+  const pp_encode_params* ep = nullptr;
+  const void* keypoints = nullptr;
+  const float* visible = nullptr;
+  const double* two_s = nullptr;
+  float* weights_out = nullptr;
+  uint8_t* in_image = nullptr;
+  uint8_t* annotated = nullptr;
+};
 
 // Runs the fused mean-mode kernel; *grid_out = number of per-CTA partial sums written (forward).
 int launch_fast(const pp_loss_params& p, const void* output, const void* target, const float* kp_weights, void* grad,
                 double* partials, int32_t* range_flag, const float* upstream, float host_scale, bool fwd,
-                cudaStream_t st, int* grid_out) {
+                cudaStream_t st, int* grid_out, const EncodeSource* enc = nullptr) {
   pp_loss_fast::FastArgs a{};
+  if (enc) {
+    a.keypoints = enc->keypoints; a.visible = enc->visible; a.two_s = enc->two_s;
+    a.weights_out = enc->weights_out; a.in_image = enc->in_image; a.annotated = enc->annotated;
+    a.K = p.K; a.kp_dim = enc->ep->keypoint_dim; a.kp_f64 = enc->ep->keypoint_dtype == PP_F64;
+    a.scale_x = enc->ep->scale_x; a.scale_y = enc->ep->scale_y; a.input_w = enc->ep->input_w; a.input_h = enc->ep->input_h;
+  }
   const int e = p.dtype == PP_F32 ? 4 : 2;
   a.output = output; a.target = target; a.kp_weights = kp_weights; a.grad = grad; a.partials = partials;
   a.range_flag = range_flag; a.upstream = upstream; a.host_scale = host_scale;
@@ -396,20 +414,31 @@ int launch_fast(const pp_loss_params& p, const void* output, const void* target,
   }
 #endif
 
-  for (;; --a.G) {
-    a.tgt_off = (16 + a.G * a.plane_bytes + 16 + 127) / 128 * 128;
-    a.stage_bytes = (a.tgt_off + a.G * a.plane_bytes + 127) / 128 * 128;
-    if (a.stage_bytes <= static_cast<size_t>(pp_smem_optin()) || a.G == 1) break;
-  }
-  if (a.stage_bytes > static_cast<size_t>(pp_smem_optin())) {
-    // very large maps: only the output plane is staged, the target is read from global memory (tgt_off = 0)
-    a.tgt_off = 0;
-    a.stage_bytes = (16 + a.plane_bytes + 16 + 127) / 128 * 128;
+  const size_t fac_bytes = enc ? sizeof(float) * 2 * (p.W + p.H + 4) : 0;   // per heatmap slot of a unit
+  if (enc) {
+    // only the output planes are staged; the target is formed from the keypoint's factors
+    for (;; --a.G) {
+      a.tgt_off = 0;
+      a.stage_bytes = (16 + a.G * a.plane_bytes + 16 + 127) / 128 * 128;
+      if (a.stage_bytes + a.G * fac_bytes <= static_cast<size_t>(pp_smem_optin()) || a.G == 1) break;
+    }
+  } else {
+    for (;; --a.G) {
+      a.tgt_off = (16 + a.G * a.plane_bytes + 16 + 127) / 128 * 128;
+      a.stage_bytes = (a.tgt_off + a.G * a.plane_bytes + 127) / 128 * 128;
+      if (a.stage_bytes <= static_cast<size_t>(pp_smem_optin()) || a.G == 1) break;
+    }
+    if (a.stage_bytes > static_cast<size_t>(pp_smem_optin())) {
+      // very large maps: only the output plane is staged, the target is read from global memory (tgt_off = 0)
+      a.tgt_off = 0;
+      a.stage_bytes = (16 + a.plane_bytes + 16 + 127) / 128 * 128;
+    }
   }
   // two stages (the next unit lands while the current one is processed) whenever they fit
   a.stages = env_int("PP_LOSS_STAGES", 2);
-  if (static_cast<size_t>(a.stages) * a.stage_bytes > static_cast<size_t>(pp_smem_optin())) a.stages = 1;
-  const size_t smem = static_cast<size_t>(a.stages) * a.stage_bytes;
+  if (static_cast<size_t>(a.stages) * a.stage_bytes + a.G * fac_bytes > static_cast<size_t>(pp_smem_optin())) a.stages = 1;
+  a.fac_off = static_cast<unsigned>(static_cast<size_t>(a.stages) * a.stage_bytes);
+  const size_t smem = a.fac_off + a.G * fac_bytes;
   const int threads = a.strips * a.segs * a.G;
   if (p.dtype == PP_F32) {
     if (fwd && g) return launch_fast_t<float, true, true>(a, threads, smem, st, grid_out);
@@ -477,6 +506,39 @@ int pp_oks_loss_forward(const pp_loss_params* p, const void* output, const void*
     finalize_kernel<<<1, 256, 0, st>>>(a.partials, N, scale, loss_scalar);
     PP_CUDA_OK(cudaGetLastError());
   }
+  return PP_OK;
+}
+
+int pp_oks_loss_forward_encoded(const pp_loss_params* p, const pp_encode_params* ep, const void* output,
+                                const void* keypoints, const float* visible, const double* two_s,
+                                const float* keypoint_weights, float* loss_scalar, void* grad, float grad_scale,
+                                float* weights_out, uint8_t* in_image, uint8_t* annotated, void* scratch,
+                                int64_t scratch_bytes, pp_stream_t stream) {
+  if (int rc = check_loss_params("pp_oks_loss_forward_encoded", p)) return rc;
+  PP_REQUIRE(ep != nullptr && ep->B == p->B && ep->K == p->K && ep->H == p->H && ep->W == p->W, PP_ERR_INVALID_ARG,
+             "pp_oks_loss_forward_encoded: encode and loss parameters disagree on the shape");
+  PP_REQUIRE(ep->keypoint_dim >= 2 && (ep->keypoint_dtype == PP_F32 || ep->keypoint_dtype == PP_F64) &&
+                 ep->scale_x != 0.0f && ep->scale_y != 0.0f,
+             PP_ERR_INVALID_ARG, "pp_oks_loss_forward_encoded: bad encode parameters");
+  const int64_t N = static_cast<int64_t>(p->B) * p->K;
+  if (N == 0) return PP_OK;
+  PP_REQUIRE(output && keypoints && two_s && loss_scalar, PP_ERR_INVALID_ARG, "pp_oks_loss_forward_encoded: null argument");
+  PP_REQUIRE(scratch && scratch_bytes >= pp_oks_loss_scratch_bytes(p), PP_ERR_SCRATCH,
+             "pp_oks_loss_forward_encoded: scratch too small");
+  PP_REQUIRE(p->mode == PP_LOSS_PIXEL_MEAN && fast_path_ok(*p, output, output, nullptr, nullptr, grad) && p->W + p->H <= 4096,
+             PP_ERR_UNSUPPORTED_SHAPE,
+             "pp_oks_loss_forward_encoded: needs PP_LOSS_PIXEL_MEAN without skip_empty_channel, W %% 4 == 0, 16-byte aligned "
+             "planes that fit shared memory; encode with pp_encode and call pp_oks_loss_forward otherwise");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EncodeSource enc;
+  enc.ep = ep; enc.keypoints = keypoints; enc.visible = visible; enc.two_s = two_s;
+  enc.weights_out = weights_out; enc.in_image = in_image; enc.annotated = annotated;
+  int parts = 0;
+  if (int rc = launch_fast(*p, output, nullptr, keypoint_weights, grad, static_cast<double*>(scratch), nullptr, nullptr,
+                           grad_scale, true, st, &parts, &enc))
+    return rc;
+  finalize_kernel<<<1, 256, 0, st>>>(static_cast<double*>(scratch), parts, 1.0 / (static_cast<double>(N) * p->H * p->W), loss_scalar);
+  PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }
 

@@ -17,6 +17,12 @@
 //     barrier inside a heatmap;
 //   * `target` rides in the same TMA stage (second bulk copy on the same mbarrier): no thread ever
 //     waits on a global load.
+//
+// Encode-inside-loss (kTgt == kTgtEncode, pp_oks_loss_forward_encoded): the target is the OKS probability map of a
+// keypoint, t[y][x] = ex[x] ey[y] (generate_probmaps, codec.py:56-66, separable), so it is never read -- and never
+// written by an encode kernel either: the CTA evaluates the W + H float64 factors of the next heatmap while it
+// processes the current one, keeps them in shared memory as float32 and forms t with one multiply per pixel.  The
+// pass then moves 2 H W e bytes per heatmap (read `output`, write `grad`) instead of 3 + the encode's 1.
 #pragma once
 
 #include "pp_common.cuh"
@@ -42,7 +48,19 @@ struct FastArgs {
   float d_a, d_b;            // d oks / d o = d_a + d_b t
   float inv_count;           // 1 / (N H W)
   unsigned plane_bytes, stage_bytes, tgt_off;   // tgt_off: byte offset of the target planes inside a stage
+  // encode-inside-loss: the target of heatmap (b, k) is the probability map of keypoint (b, k)
+  const void* keypoints;     // (N, kp_dim) input-image space, float32 or float64 (kp_f64)
+  const float* visible;      // (N) or null (all ones)
+  const double* two_s;       // (K) divisor 2 s per keypoint (codec.py:65)
+  float* weights_out;        // (N) keypoint weights as the encoder defines them (codec.py:46,68), or null
+  uint8_t* in_image;         // (N) or null (codec.py:189-200)
+  uint8_t* annotated;        // (N) or null (codec.py:187)
+  int K, kp_dim, kp_f64;
+  float scale_x, scale_y, input_w, input_h;
+  unsigned fac_off;          // byte offset of the factor buffers (after the stages): 2 x G x (W + H + 4) floats
 };
+
+enum TgtMode : int { kTgtGlobal = 0, kTgtSmem = 1, kTgtEncode = 2 };
 
 struct RowState {
   float hd[3][6], hs[3][6];  // row factors of the Sobel pair, rows r-2, r-1, r
@@ -123,12 +141,14 @@ __device__ __forceinline__ void load_strip4_global<__nv_bfloat16>(const __nv_bfl
   v[2] = __uint_as_float(w.y << 16); v[3] = __uint_as_float(w.y & 0xffff0000u);
 }
 
-// kTgtSmem: the target plane was staged in shared memory with the output plane (the normal case); otherwise
-// (maps so large that only one plane fits) it is read from global memory where it is consumed.
-template <typename T, bool kFwd, bool kGrad, bool kTgtSmem, int PH>
+// kTgt: kTgtSmem -- the target plane was staged in shared memory with the output plane (the normal case);
+// kTgtGlobal -- (maps so large that only one plane fits) it is read from global memory where it is consumed;
+// kTgtEncode -- it is the product of the keypoint's separable factors: tx[4] (this strip's columns, registers) x ey[row].
+template <typename T, bool kFwd, bool kGrad, int kTgt, int PH>
 __device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& cf, int q, int y0, int y1, int H, int W,
                                          int x0, bool left_ok, bool right_ok, const T* __restrict__ plane,
-                                         const T* __restrict__ tgt, T* __restrict__ grad) {
+                                         const T* __restrict__ tgt, T* __restrict__ grad, const float (&tx)[4],
+                                         const float* __restrict__ ey) {
   constexpr int cur = PH, p1 = (PH + 2) % 3, p2 = (PH + 1) % 3;  // rows r, r-1, r-2 (and r-3 == cur for dP/sQ)
   const int r = y0 - 2 + q;
 
@@ -179,16 +199,23 @@ __device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& c
   if (ro >= y0 && ro < y1) {
     float g[4], ov[4], tv[4];
     load_strip4<T>(plane + ro * W + x0, ov);
-    if (kTgtSmem) load_strip4<T>(tgt + ro * W + x0, tv);
-    else load_strip4_global<T>(tgt + ro * W + x0, tv);
+    if (kTgt == kTgtSmem) load_strip4<T>(tgt + ro * W + x0, tv);
+    else if (kTgt == kTgtGlobal) load_strip4_global<T>(tgt + ro * W + x0, tv);
+    else {
+      const float fy = ey[ro];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tv[i] = tx[i] * fy;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float o = ov[i], t = tv[i];
       if (kFwd) {
         sums.so += cf.a_o * o + cf.a_t * t - o * t;
         if (cf.has_mse) { const float d = o - t; sums.sm += d * d; }
-        sums.tmin = fminf(sums.tmin, t);
-        sums.tmax = fmaxf(sums.tmax, t);
+        if (kTgt != kTgtEncode) {   // an encoded target lies in [0, 1] by construction
+          sums.tmin = fminf(sums.tmin, t);
+          sums.tmax = fmaxf(sums.tmax, t);
+        }
       }
       if (kGrad) {
         float direct = cf.k_a + cf.k_b * t;
@@ -202,7 +229,13 @@ __device__ __forceinline__ void row_step(RowState& st, Sums& sums, const Coef& c
   }
 }
 
-template <typename T, bool kFwd, bool kGrad, bool kTgtSmem>
+// float64 -> heatmap space like NumPy does (float32 keypoints / float32 scale stay float32, codec.py:180)
+__device__ __forceinline__ double fast_to_heatmap_space(const void* kp, int f64, long long idx, float scale) {
+  if (f64) return __ddiv_rn(static_cast<const double*>(kp)[idx], static_cast<double>(scale));
+  return static_cast<double>(__fdiv_rn(static_cast<const float*>(kp)[idx], scale));
+}
+
+template <typename T, bool kFwd, bool kGrad, int kTgt>
 __global__ void __launch_bounds__(256)
 oks_loss_fast_kernel(FastArgs a) {
   extern __shared__ __align__(128) unsigned char stage_mem[];
@@ -221,6 +254,49 @@ oks_loss_fast_kernel(FastArgs a) {
   const T* out = static_cast<const T*>(a.output);
   const T* tgt_all = static_cast<const T*>(a.target);
   auto tgt_stage_of = [&](int s) { return reinterpret_cast<const T*>(stage_mem + static_cast<size_t>(s) * a.stage_bytes + a.tgt_off); };
+  // encode-inside-loss: factor buffer b (alternating per unit) of heatmap slot g: ex[W], ey[H], then the keypoint weight
+  const int FS = W + H + 4;
+  auto fac_of = [&](int b, int gslot) { return reinterpret_cast<float*>(stage_mem + a.fac_off) + (static_cast<size_t>(b) * a.G + gslot) * FS; };
+  // factors of this thread's heatmap slot of unit `un` -> buffer b (generate_probmaps, codec.py:45-68; the flag
+  // outputs of ProbMap.encode / ArgMaxProbMap.encode, codec.py:187-200)
+  auto encode_unit = [&](long long un, int b) {
+    const long long h = un * a.G + g;
+    if (g >= a.G || h >= a.N) return;
+    float* f = fac_of(b, g);
+    const float vis = a.visible ? a.visible[h] : 1.0f;
+    const bool labelled = !(vis < 0.5f);   // codec.py:53
+    const double kx = fast_to_heatmap_space(a.keypoints, a.kp_f64, h * a.kp_dim, a.scale_x);
+    const double ky = fast_to_heatmap_space(a.keypoints, a.kp_f64, h * a.kp_dim + 1, a.scale_y);
+    const double div = a.two_s[h % a.K];
+    for (int j = local; j < W + H; j += per) {
+      const double d = (j < W) ? (static_cast<double>(j) - kx) : (static_cast<double>(j - W) - ky);
+      f[j] = labelled ? static_cast<float>(exp(-(d * d / div))) : 0.0f;   // unlabelled channels stay zero (codec.py:45)
+    }
+    if (local == 0) {
+      float wgt = vis;   // unlabelled keypoints keep their visibility value (codec.py:46,53-54)
+      if (labelled) {    // (float64 map).max() > 0 (codec.py:68): the maximum sits at the grid point nearest to the keypoint
+        const double xn = fmin(fmax(rint(kx), 0.0), static_cast<double>(W - 1));
+        const double yn = fmin(fmax(rint(ky), 0.0), static_cast<double>(H - 1));
+        const double dx = xn - kx, dy = yn - ky;
+        const double dist = sqrt(dx * dx + dy * dy);
+        wgt = exp(-(dist * dist / div)) > 0.0 ? 1.0f : 0.0f;
+      }
+      f[W + H] = a.kp_weights ? a.kp_weights[h] : wgt;   // explicit weights (learn_heatmaps_from_zeros etc.) win
+      if (a.weights_out) a.weights_out[h] = wgt;
+      if (a.annotated) a.annotated[h] = vis > 0.0f;
+      if (a.in_image) {
+        bool in;
+        if (a.kp_f64) {
+          const double x = static_cast<const double*>(a.keypoints)[h * a.kp_dim], y = static_cast<const double*>(a.keypoints)[h * a.kp_dim + 1];
+          in = x >= 0.0 && x < static_cast<double>(a.input_w) && y >= 0.0 && y < static_cast<double>(a.input_h);
+        } else {
+          const float x = static_cast<const float*>(a.keypoints)[h * a.kp_dim], y = static_cast<const float*>(a.keypoints)[h * a.kp_dim + 1];
+          in = x >= 0.0f && x < a.input_w && y >= 0.0f && y < a.input_h;
+        }
+        a.in_image[h] = in;
+      }
+    }
+  };
   T* grad_all = static_cast<T*>(a.grad);
   // 16 bytes of slack in front of / behind each stage keep the halo reads of the first / last strip in bounds
   auto stage_of = [&](int s) { return reinterpret_cast<const T*>(stage_mem + static_cast<size_t>(s) * a.stage_bytes + 16); };
@@ -244,11 +320,15 @@ oks_loss_fast_kernel(FastArgs a) {
   long long unit = blockIdx.x;
   auto fetch_unit = [&](long long un, int s) {   // `output` and `target` of a unit land in stage s
     const unsigned bytes = unit_bytes(un);
-    mbar_expect_tx(&bars[s], kTgtSmem ? 2 * bytes : bytes);
+    mbar_expect_tx(&bars[s], kTgt == kTgtSmem ? 2 * bytes : bytes);
     tma_load_1d(const_cast<T*>(stage_of(s)), out + un * a.G * HW, bytes, &bars[s]);
-    if (kTgtSmem) tma_load_1d(const_cast<T*>(tgt_stage_of(s)), tgt_all + un * a.G * HW, bytes, &bars[s]);
+    if (kTgt == kTgtSmem) tma_load_1d(const_cast<T*>(tgt_stage_of(s)), tgt_all + un * a.G * HW, bytes, &bars[s]);
   };
   if (tid == 0 && unit < units) fetch_unit(unit, 0);
+  if (kTgt == kTgtEncode) {
+    if (unit < units) encode_unit(unit, 0);
+    __syncthreads();
+  }
 
   double acc = 0.0;
   Sums sums{0.f, 0.f, 0.f, INFINITY, -INFINITY};
@@ -260,7 +340,20 @@ oks_loss_fast_kernel(FastArgs a) {
     if (a.stages == 2 && tid == 0 && nxt < units) fetch_unit(nxt, s ^ 1);  // prefetch into the other stage
     const long long hm = unit * a.G + g;
     const bool active = g < a.G && hm < a.N && sy < a.segs;
-    const float m = (active && a.kp_weights) ? a.kp_weights[hm] : 1.0f;
+    float m = 1.0f;
+    float tx[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* ey = nullptr;
+    if (kTgt == kTgtEncode) {
+      if (active) {
+        const float* f = fac_of(it & 1, g);
+        m = f[W + H];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tx[i] = f[x0 + i];
+        ey = f + W;
+      }
+    } else if (active && a.kp_weights) {
+      m = a.kp_weights[hm];
+    }
     Coef cf;
     cf.c2 = 2.0f * a.lw * a.w_s * u * m;
     cf.k_a = a.lw * u * m * a.w_o * a.d_a;
@@ -282,14 +375,14 @@ oks_loss_fast_kernel(FastArgs a) {
 
     mbar_wait(&bars[s], (a.stages == 2) ? ((it >> 1) & 1) : (it & 1));
     const T* plane = stage_of(s) + static_cast<size_t>(g) * HW;
-    const T* tgt = kTgtSmem ? tgt_stage_of(s) + static_cast<size_t>(g) * HW : tgt_all + hm * HW;
+    const T* tgt = kTgt == kTgtSmem ? tgt_stage_of(s) + static_cast<size_t>(g) * HW : kTgt == kTgtGlobal ? tgt_all + hm * HW : nullptr;
     if (active) {
       for (int q = 0; q < nsteps; q += 3) {
-        row_step<T, kFwd, kGrad, kTgtSmem, 0>(st, sums, cf, q, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+        row_step<T, kFwd, kGrad, kTgt, 0>(st, sums, cf, q, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad, tx, ey);
         if (q + 1 < nsteps)
-          row_step<T, kFwd, kGrad, kTgtSmem, 1>(st, sums, cf, q + 1, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+          row_step<T, kFwd, kGrad, kTgt, 1>(st, sums, cf, q + 1, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad, tx, ey);
         if (q + 2 < nsteps)
-          row_step<T, kFwd, kGrad, kTgtSmem, 2>(st, sums, cf, q + 2, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad);
+          row_step<T, kFwd, kGrad, kTgt, 2>(st, sums, cf, q + 2, y0, y1, H, W, x0, left_ok, right_ok, plane, tgt, grad, tx, ey);
       }
       if (kFwd) {
         // per-pixel loss = (w_s e + w_o oks + w_g mse) m lw (loss.py:122-127, 143), summed per strip
@@ -297,6 +390,9 @@ oks_loss_fast_kernel(FastArgs a) {
         acc += static_cast<double>(part);
       }
     }
+    // the next unit's target factors go to the other factor buffer (last read one iteration ago); the barrier
+    // below publishes them
+    if (kTgt == kTgtEncode && nxt < units) encode_unit(nxt, (it + 1) & 1);
     __syncthreads();  // every thread is done with stage s before it is refilled
     if (a.stages == 1 && tid == 0 && nxt < units) fetch_unit(nxt, 0);
   }
@@ -304,7 +400,7 @@ oks_loss_fast_kernel(FastArgs a) {
   if (kFwd) {
     acc = warp_sum(acc);
     if ((tid & 31) == 0) red[tid >> 5] = acc;
-    if (a.range_flag && (sums.tmin < 0.0f || sums.tmax > 1.0f)) red_flag = 1;
+    if (kTgt != kTgtEncode && a.range_flag && (sums.tmin < 0.0f || sums.tmax > 1.0f)) red_flag = 1;
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;

@@ -132,6 +132,7 @@ def expected_value_device(heatmaps: torch.Tensor, sigmas, *, input_size=None, re
                                            _lib.ptr(out["argmax"]), _lib.ptr(kp), _lib.ptr(conv), _lib.ptr(scratch),
                                            scratch.numel() * 4, _lib.stream_ptr(dev))
     _lib.check(rc, "pp_decode_expected")
+    out["_scratch"] = scratch   # word 2: number of heatmaps the tensor-core kernel handed on (tools / tests read it)
     return out
 
 

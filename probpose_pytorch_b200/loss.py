@@ -102,6 +102,69 @@ class _Prepared:
         return grad
 
 
+class _PreparedEncoded:
+    """Inputs of the encode-inside-loss pass (``pp_oks_loss_forward_encoded``): the target is never materialised,
+    the kernel forms it from the keypoints.  Mirrors :class:`_Prepared` for the autograd bridge."""
+
+    def __init__(self, module: "OKSHeatmapLoss", output: Tensor, probmap, keypoints, keypoints_visible, target_weights):
+        _lib.require_cuda()
+        if not output.is_cuda or output.ndim != 4:
+            raise RuntimeError("OKSHeatmapLoss (B200) needs (B, K, H, W) CUDA tensors; there is no CPU fallback")
+        B, K, H, W = output.shape
+        dev, dt = output.device, output.dtype
+        if (W, H) != tuple(int(v) for v in probmap.heatmap_size):
+            raise ValueError(f"output is {W}x{H}, the codec encodes {tuple(probmap.heatmap_size)}")
+        self.shape, self.dtype, self.device = (B, K, H, W), dt, dev
+        self.output = output.detach().contiguous()
+        kp = torch.as_tensor(keypoints)
+        if kp.dtype not in (torch.float32, torch.float64):
+            kp = kp.to(torch.float64)
+        self.keypoints = kp.to(dev).reshape(B, K, -1).contiguous()
+        self.visible = None
+        if keypoints_visible is not None:
+            self.visible = torch.as_tensor(keypoints_visible).to(device=dev, dtype=torch.float32).reshape(B, K).contiguous()
+        self.kp_weights = None
+        if target_weights is not None:
+            assert target_weights.shape == (B, K), "the fused encode + loss pass takes per-keypoint weights (B, K)"
+            self.kp_weights = target_weights.detach().to(device=dev, dtype=torch.float32).contiguous()
+        self.divisors = probmap._divisors(K, dev)
+        self.params = _lib.LossParams(B, K, H, W, _lib.dtype_code(dt), _lib.PP_LOSS_PIXEL_MEAN, _OKS_TYPES[module.oks_type],
+                                      int(module.skip_empty_channel), float(module.smoothing_weight),
+                                      float(module.gaussian_weight), float(module.loss_weight), 0, 0)
+        sf = probmap.scale_factor
+        self.enc_params = _lib.EncodeParams(B, K, H, W, _lib.dtype_code(dt), _lib.dtype_code(self.keypoints.dtype),
+                                            self.keypoints.shape[-1], float(sf[0]), float(sf[1]),
+                                            float(probmap.input_size[0]), float(probmap.input_size[1]))
+        self.scratch = _scratch(self.params, dev)
+        self.encoded = {"keypoint_weights": torch.empty((B, K), dtype=torch.float32, device=dev),
+                        "in_image": torch.empty((B, K), dtype=torch.bool, device=dev),
+                        "annotated": torch.empty((B, K), dtype=torch.bool, device=dev)}
+        self.last_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # an encoded target is in [0, 1] by construction
+
+    def forward(self, *, want_grad: bool, grad_scale: float = 1.0):
+        dev = self.device
+        scalar = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty(self.shape, dtype=self.dtype, device=dev) if want_grad else None
+        e = self.encoded
+        with torch.cuda.device(dev):
+            rc = _lib.lib().pp_oks_loss_forward_encoded(
+                self.params, self.enc_params, _lib.ptr(self.output), _lib.ptr(self.keypoints), _lib.ptr(self.visible),
+                _lib.ptr(self.divisors), _lib.ptr(self.kp_weights), _lib.ptr(scalar), _lib.ptr(grad), float(grad_scale),
+                _lib.ptr(e["keypoint_weights"]), _lib.ptr(e["in_image"]), _lib.ptr(e["annotated"]),
+                _lib.ptr(self.scratch), self.scratch.numel() * 8, _lib.stream_ptr(dev))
+        _lib.check(rc, "pp_oks_loss_forward_encoded")
+        return dict(loss_map=None, loss_kpt=None, scalar=scalar, peak=None, grad=grad, flag=self.last_flag)
+
+    def backward(self, upstream: Tensor, kind: int, peak) -> Tensor:
+        # only reached when the fused gradient was already consumed (a second backward): run the pass again
+        grad = self.forward(want_grad=True)["grad"]
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().pp_scale_inplace(_lib.ptr(grad), _lib.dtype_code(grad.dtype), grad.numel(), _lib.ptr(upstream),
+                                             _lib.stream_ptr(self.device))
+        _lib.check(rc, "pp_scale_inplace")
+        return grad
+
+
 def _first_element(g: Tensor) -> Tensor:
     """(1,) float32 copy of g[0, ..., 0] without materialising an expanded tensor."""
     return g.detach()[(0,) * g.ndim].reshape(1).to(torch.float32).contiguous()
@@ -220,3 +283,19 @@ class OKSHeatmapLoss(nn.Module):
                      mask: Tensor | None = None) -> Tensor:
         """``forward(..., per_pixel=True).mean()`` in a single fused kernel (forward + backward)."""
         return self._run(output, target, target_weights, mask, _lib.PP_LOSS_PIXEL_MEAN, False, True)
+
+    def forward_mean_encoded(self, output: Tensor, probmap, keypoints, keypoints_visible=None,
+                             target_weights: Tensor | None = None, return_encoded: bool = False):
+        """``forward_mean(output, probmap.encode_batch(keypoints, keypoints_visible)["heatmaps"], weights)`` without
+        the target: ONE pass reads ``output``, forms the target of every pixel from the keypoint's separable factors
+        (generate_probmaps, codec.py:56-66), reduces the loss and writes ``d loss / d output`` -- 2 H W e bytes per
+        heatmap instead of 1 (encode) + 3 (loss).
+
+        ``probmap`` is this package's ``ProbMap`` / ``ArgMaxProbMap`` (or a ``Codec`` holding one); ``keypoints``
+        (B, K, D) in input-image space.  ``target_weights`` (B, K) defaults to the encoder's ``keypoint_weights``.
+        With ``return_encoded`` the encoder's (B, K) outputs (``keypoint_weights``, ``in_image``, ``annotated``) are
+        returned as a second value."""
+        probmap = getattr(probmap, "probmap", probmap)
+        prep = _PreparedEncoded(self, output, probmap, keypoints, keypoints_visible, target_weights)
+        loss = _OKSLossFunction.apply(output, prep, False, True)
+        return (loss, prep.encoded) if return_encoded else loss

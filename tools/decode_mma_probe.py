@@ -47,7 +47,9 @@ def main():
                 os.environ["PP_DECODE_MMA"] = mma
                 us, out = timed(lambda: pm.decode_device(x), iters=20)
                 kern = _lib.lib().pp_decode_expected_last_kernel()
-                row.append(f"kernel {kern}: {us:8.1f} us {us * 1e3 / n:6.2f} ns/hm {n * x[0, 0].numel() * x.element_size() / us / 1e3:7.1f} GB/s")
+                torch.cuda.synchronize()
+                handed = int(out["_scratch"][2]) if kern == 5 else 0
+                row.append(f"kernel {kern} ({handed} handed on): {us:8.1f} us {us * 1e3 / n:6.2f} ns/hm {n * x[0, 0].numel() * x.element_size() / us / 1e3:7.1f} GB/s")
                 if ref is None:
                     ref = out
                 else:
