@@ -10,11 +10,20 @@ One *step* = one pass of the hot path over one batch of synthetic input (per GPU
     decode         (predicted maps -> keypoint records)      read  1 x HW x e
     loss fwd+bwd   (read prediction + target, write grad)    read 2, write 1
 => 5 x H x W x e algorithmic bytes per heatmap.  Rank 0 prints ONE JSON line.
+
+The headline (`value`, `ms_per_step`, `roofline`, `e2e`) is the largest single-GPU configuration of BASELINE.json
+(C5: COCO-WholeBody 133 keypoints, B = 512, 64x48; 836.8 MB per tensor -- nothing fits L2); `configs` carries the same
+measurement for C2 (the ViT-B head decode shape, B = 256), C3 (the 8-GPU training shape: B = 1024 split over the ranks,
+strong scaling) and C4 (96x72, B = 512; plus its decode-only sweep, split over the ranks), each with its own
+`ms_per_step`, kernel times and roofline fractions.  `fused_step` is the same step with the target encode folded into
+the loss kernel (`OKSHeatmapLoss.forward_mean_encoded`: the target is never written or read, 3 x HW x e per heatmap).
+After the timed region a seeded sample of the timed buffers is checked against the CPU oracle (`parity_check`).
 """
 
 from __future__ import annotations
 
 import argparse
+import collections
 import json
 import os
 import statistics
@@ -31,6 +40,7 @@ if str(ROOT) not in sys.path:
 METRIC = "heatmaps/sec encode+decode+loss (BxKxHxW)"
 UNIT = "heatmaps/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+HEADLINE = 5               # BASELINE.json config the N = 1 line is quoted on (largest single-GPU configuration)
 
 
 def workload_text(wl):
@@ -41,17 +51,18 @@ def workload_text(wl):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configuration (2..5) whose shapes are used")
+    ap.add_argument("--config", type=int, default=HEADLINE, help="BASELINE.json configuration (2..5) of the headline")
     ap.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32")
-    ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set must exceed L2)")
+    ap.add_argument("--sets", type=int, default=0, help="rotating buffer sets (0 = enough for the working set to exceed L2)")
     ap.add_argument("--sample", type=int, default=0, help="reference arm: images per step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-subconfigs", action="store_true", help="headline configuration only (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--exchange-every", type=int, default=0,
-                    help="multi-GPU: steps per all-gather bucket (0 = number of buffer sets; 1 = one collective per step)")
+                    help="multi-GPU, --exchange nccl: steps per all-gather bucket (0 = number of buffer sets)")
     ap.add_argument("--serial", action="store_true", help="run decode after encode on one stream (no fork/join)")
     ap.add_argument("--exchange", choices=["mailbox", "nccl"], default="mailbox",
                     help="multi-GPU record + loss exchange: stores into every rank's mailbox over NVLink peer memory from the "
@@ -61,7 +72,7 @@ def parse_args():
 
 # =============================================================================================
 # reference arm: the oracle port (CPU restatement of the reference, checked bit-exact against it)
-# on the host cores.  This is the only place besides the tests that executes oracle/.
+# on the host cores.  This is the only place besides the tests and parity_check that executes oracle/.
 # =============================================================================================
 def _cpu_chunk(job):
     """encode -> expected-OKS decode -> loss fwd+bwd for a chunk of images, as the reference does it:
@@ -106,7 +117,7 @@ def run_reference(args):
 
     wl = synth.WORKLOADS[args.config]
     cores = os.cpu_count() or 1
-    sample = args.sample or min(wl.batch, max(cores, 64))
+    sample = args.sample or min(wl.batch, max(cores, 32))
     ctx = mp.get_context("fork")
 
     def one_step(pool, images, seed):
@@ -188,10 +199,10 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.005)
 
-    def summary(self):
+    def summary(self, marks=None):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
-        timed = [s for s in self.samples if s[4] == "timed"]
+        timed = [s for s in self.samples if s[4] is not None and (marks is None or s[4] in marks) and str(s[4]).startswith("timed")]
         pool = timed or [s for s in self.samples if s[4] is not None] or self.samples
         names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                  0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost",
@@ -205,202 +216,233 @@ class ClockSampler(threading.Thread):
                 "samples": len(pool), "window": "timed region" if timed else "whole measurement phase"}
 
 
-def run_product(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+def hbm_peak():
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        return float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
-    import probpose_pytorch_b200 as pp
-    from probpose_pytorch_b200 import _lib, synth
-    from probpose_pytorch_b200 import distributed as ppd
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (product arm) needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.lib()
+DECODE_KERNELS = {0: "conv_exact_kernel + argmax_from_conv_kernel", 1: "decode_expected_fast_kernel (one CTA per heatmap)",
+                  2: "decode_expected_warp_kernel (one warp per heatmap, pruned float32 prefilter)",
+                  3: "decode_expected_dense_kernel", 4: "decode_expected_kernel (generic)",
+                  5: "decode_expected_mma_kernel (one warp per heatmap, tensor-core Toeplitz prefilter + exact fp64 re-evaluation)"}
 
-    wl = synth.WORKLOADS[args.config]
-    B, K = wl.batch, wl.num_keypoints            # per-GPU batch: weak scaling (C3 = 128 images per GPU)
-    if args.config == 3:
-        B = wl.batch // 8
-    W, H = wl.heatmap_size
-    tdtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
-    esize = 4 if args.dtype == "fp32" else 2
-    hm_bytes = H * W * esize
-    n_hm = B * K
 
-    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
-    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
-    codec = pp.Codec(pm)
-    loss_fn = pp.OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus", check_target=False)
+class Bench:
+    """One workload (a BASELINE.json configuration, this rank's share of it) on this rank's GPU."""
 
-    # ---- synthetic inputs: `sets` distinct buffer sets so that consecutive steps never find their
-    # inputs in L2 (per set: prediction + target + gradient = 3 x B*K*H*W*e bytes)
-    sets = []
-    rng = np.random.default_rng(1000 + args.config + 17 * rank)
-    for s in range(args.sets):
-        kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=1000 + args.config + 97 * rank + s)
-        kps_d = torch.from_numpy(kps).to(dev)
-        vis_d = torch.from_numpy(vis).to(dev)
-        jit = torch.from_numpy(synth.jitter_keypoints(wl, kps, seed=5000 + s)).to(dev)
-        blob = am.encode_batch(jit, vis_d)["heatmaps"]
-        amp = torch.from_numpy(synth.blob_params((B, K), seed=6000 + s)).to(dev)
-        noise = torch.rand(blob.shape, device=dev) * 0.02
-        pred = (blob * amp[:, :, None, None] + noise).clamp_(0, 1).to(tdtype).contiguous()
-        heads = [torch.rand((B, K, 1, 1), device=dev) for _ in range(4)]
-        sets.append(dict(kps=kps_d, vis=vis_d, pred=pred, heads=heads, kps_host=torch.from_numpy(kps).pin_memory(),
-                         vis_host=torch.from_numpy(vis).pin_memory(), pred_host=pred.cpu().pin_memory()))
-        del blob, noise
-    set_bytes = 3 * n_hm * hm_bytes
-    torch.cuda.synchronize()
+    def __init__(self, ctx, cfg: int, batch: int, label: str, scaling: str):
+        import numpy as np
+        import torch
 
-    side = torch.cuda.Stream(device=dev)
+        import probpose_pytorch_b200 as pp
+        from probpose_pytorch_b200 import synth
 
-    # ---- multi-GPU exchange of the step's results (keypoint records + loss): a mailbox per rank in NVLink peer
-    # memory, written by the record-packing kernel itself; one slot per rotating buffer set
-    mailbox, exchange_note = None, ""
-    if world > 1 and args.exchange == "mailbox":
-        try:
-            mailbox = ppd.PeerMailbox(B, K, len(sets), dev)
-            exchange_note = f"records + loss stored into every rank's mailbox over NVLink by pp_pack_records ({len(sets)} slots)"
-        except Exception as e:   # symmetric memory unavailable on this box: the NCCL path still measures the step
-            exchange_note = f"NCCL (symmetric memory unavailable: {type(e).__name__}: {str(e)[:80]})"
-            mailbox = None
+        self.ctx, self.cfg, self.label, self.scaling = ctx, cfg, label, scaling
+        args, dev, rank = ctx["args"], ctx["dev"], ctx["rank"]
+        self.torch, self.pp, self.np = torch, pp, np
+        self.wl = wl = synth.WORKLOADS[cfg]
+        self.B, self.K = batch, wl.num_keypoints
+        self.W, self.H = wl.heatmap_size
+        self.tdtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+        self.esize = 4 if args.dtype == "fp32" else 2
+        self.hm_bytes = self.H * self.W * self.esize
+        self.n_hm = self.B * self.K
+        tensor_mb = self.n_hm * self.hm_bytes / 1e6
+        # enough rotating sets that consecutive steps never find their inputs in the 126 MB L2
+        self.nsets = args.sets or (2 if 3 * tensor_mb > 400 else 4)
+        self.am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+        self.pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+        self.codec = pp.Codec(self.pm)
+        self.loss_fn = pp.OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus", check_target=False)
+        self.sets = []
+        for s in range(self.nsets):
+            kps, vis, _ = synth.make_keypoints(wl, batch=self.B, seed=1000 + cfg + 97 * rank + s)
+            kps_d, vis_d = torch.from_numpy(kps).to(dev), torch.from_numpy(vis).to(dev)
+            jit = torch.from_numpy(synth.jitter_keypoints(wl, kps, seed=5000 + s)).to(dev)
+            pred = self.am.encode_batch(jit, vis_d)["heatmaps"]
+            amp = torch.from_numpy(synth.blob_params((self.B, self.K), seed=6000 + s)).to(dev)
+            g = torch.Generator(device=dev).manual_seed(7000 + 13 * rank + s)
+            pred.mul_(amp[:, :, None, None]).add_(torch.rand(pred.shape, device=dev, generator=g).mul_(0.02)).clamp_(0, 1)
+            pred = pred.to(self.tdtype).contiguous()
+            heads = [torch.rand((self.B, self.K, 1, 1), device=dev, generator=g) for _ in range(4)]
+            self.sets.append(dict(kps=kps_d, vis=vis_d, pred=pred, heads=heads, kps_np=kps, vis_np=vis))
+        self.set_bytes = 3 * self.n_hm * self.hm_bytes
+        self.side = torch.cuda.Stream(device=dev)
+        self.mailbox, self.exchange_note = None, ""
+        torch.cuda.synchronize()
 
-    def step_device(s, slot=0):
-        """The hot path on device-resident inputs.  The decode only depends on the prediction, so it runs on
-        a second stream next to encode -> loss (fork / join; inside the captured graph these are two branches);
-        the records are packed (and, on several GPUs, published together with the loss) after the join."""
-        cur = torch.cuda.current_stream(dev)
+    # ---- the step on device-resident inputs -------------------------------------------------------------
+    def step(self, s, slot=0, fused=False, mailbox=None):
+        """encode -> loss on the current stream, decode + record packing beside them on a second stream (fork / join;
+        inside a captured graph these are two branches).  `fused`: the encode happens inside the loss kernel."""
+        torch, args = self.torch, self.ctx["args"]
+        cur = torch.cuda.current_stream(self.ctx["dev"])
         pred5 = (s["pred"], *s["heads"])
         rec = None
         if not args.serial:
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                dec = pm.decode_device(s["pred"])
-                # the records are packed right behind the decode and, on several GPUs, stored into every rank's
-                # mailbox by the same kernel; the loss joins them after the join (commit)
-                rec = codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
-        enc = am.encode_batch(s["kps"], s["vis"], dtype=tdtype)
-        if args.serial:
-            dec = pm.decode_device(s["pred"])
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                dec = self.pm.decode_device(s["pred"])
+                rec = self.codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
         out = s["pred"].detach().requires_grad_(True)
-        loss = loss_fn.forward_mean(out, enc["heatmaps"], enc["keypoint_weights"])
+        tgt = None
+        pub = mailbox.descriptor(slot) if mailbox is not None else None   # the loss' finalize kernel publishes it
+        if fused:
+            loss = self.loss_fn.forward_mean_encoded(out, self.am, s["kps"], s["vis"], publish=pub)
+        else:
+            enc = self.am.encode_batch(s["kps"], s["vis"], dtype=self.tdtype)
+            tgt = enc["heatmaps"]
+            loss = self.loss_fn.forward_mean(out, tgt, enc["keypoint_weights"], publish=pub)
+        if args.serial:
+            dec = self.pm.decode_device(s["pred"])
         loss.backward()
         if not args.serial:
-            cur.wait_stream(side)
+            cur.wait_stream(self.side)
         if rec is None:
-            rec = codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
+            rec = self.codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
         if mailbox is not None:
-            mailbox.commit(slot, loss.detach())
-        return rec, loss.detach(), out.grad
+            mailbox.loss_enqueued(slot)
+        return dict(rec=rec, loss=loss.detach(), grad=out.grad, dec=dec, tgt=tgt)
 
-    # ---- CUDA graphs of the step, one per buffer set
-    graphs, results = [], []
-    use_graph = not args.no_graph
-    for j, s in enumerate(sets):
-        for _ in range(2):
-            step_device(s, j)
-    torch.cuda.synchronize()
-    if use_graph:
-        for j, s in enumerate(sets):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                results.append(step_device(s, j))
-            graphs.append(g)
+    def _graphs(self, fn, mailbox=None):
+        torch = self.torch
+        for j, s in enumerate(self.sets):
+            for _ in range(2):
+                fn(s, j)
+                if mailbox is not None:
+                    mailbox.skip(j)       # flow control: every publication is consumed before its slot comes round again
         torch.cuda.synchronize()
+        graphs, results = [], []
+        if not self.ctx["args"].no_graph:
+            for j, s in enumerate(self.sets):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    results.append(fn(s, j))
+                graphs.append(g)
+            torch.cuda.synchronize()
+        return graphs, results
 
-    def run_step(i):
-        j = i % len(sets)
-        if use_graph:
-            graphs[j].replay()
-            rec, loss, _ = results[j]
+    def time_step(self, steps, warmup, fused=False, exchange=True, mark="timed"):
+        """ms for exactly `steps` steps (max over ranks), the last results and what the exchange did."""
+        torch, ctx = self.torch, self.ctx
+        import torch.distributed as dist
+        from probpose_pytorch_b200 import distributed as ppd
+        args, world, dev = ctx["args"], ctx["world"], ctx["dev"]
+        mailbox = None
+        note = ""
+        if world > 1 and exchange and args.exchange == "mailbox":
+            try:
+                if self.mailbox is None:
+                    self.mailbox = ppd.PeerMailbox(self.B, self.K, len(self.sets), dev)
+                mailbox = self.mailbox
+                note = f"records + loss stored into every rank's mailbox over NVLink by pp_pack_records ({len(self.sets)} slots)"
+            except Exception as e:   # symmetric memory unavailable on this box: the NCCL path still measures the step
+                note = f"NCCL (symmetric memory unavailable: {type(e).__name__}: {str(e)[:80]})"
+        graphs, results = self._graphs(lambda s, j: self.step(s, j, fused=fused, mailbox=mailbox), mailbox)
+        use_graph = bool(graphs)
+        cons = torch.cuda.Stream(device=dev) if mailbox is not None else None
+        pending, bucket = collections.deque(), []
+        every = max(1, min(args.exchange_every or len(self.sets), len(self.sets)))
+        consumed = {"reads": 0}
+        nccl = world > 1 and exchange and mailbox is None
+
+        def run_step(i):
+            j = i % len(self.sets)
+            if use_graph:
+                graphs[j].replay()
+                res = results[j]
+                if mailbox is not None:
+                    mailbox.published(j)      # the replayed graph published slot j again
+            else:
+                res = self.step(self.sets[j], j, fused=fused, mailbox=mailbox)
             if mailbox is not None:
-                mailbox.published(j)      # the replayed graph published slot j again
-        else:
-            rec, loss, _ = step_device(sets[j], j)
-        if world > 1 and mailbox is None:
-            # the only exchange on the path: keypoint records + loss partials.  It is latency bound, so the results
-            # of `--exchange-every` consecutive steps (<= the number of rotating buffer sets, whose outputs are
-            # still intact) travel in ONE all-gather, issued asynchronously so that it overlaps the next steps'
-            # kernels (bounded number in flight).
-            bucket.append((rec, loss))
-            if len(bucket) == exchange_every:
+                # the consumer side, inside the timed region, on its own stream behind this step: every rank waits for
+                # what ALL ranks published into the step's slot and acknowledges it (flow control: a slot is not
+                # rewritten before everybody is done with it); once per cycle of slots the blocks are also copied out
+                # (what a logger / evaluator does).  No host synchronisation.
+                cons.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(cons):
+                    if j == len(self.sets) - 1:
+                        mailbox.read_async(j)
+                        consumed["reads"] += 1
+                    else:
+                        mailbox.skip(j)
+            if nccl:
+                bucket.append((res["rec"], res["loss"]))
+                if len(bucket) == every:
+                    pending.append(ppd.exchange_bucket([b[0] for b in bucket], [b[1] for b in bucket], async_op=True))
+                    bucket.clear()
+                    if len(pending) > 2:
+                        pending.popleft().wait()
+            return res
+
+        def drain():
+            if bucket:
                 pending.append(ppd.exchange_bucket([b[0] for b in bucket], [b[1] for b in bucket], async_op=True))
                 bucket.clear()
-                if len(pending) > 2:
-                    pending.popleft().wait()
-        return rec, loss
+            while pending:
+                pending.popleft().wait()
+            if cons is not None:
+                torch.cuda.current_stream(dev).wait_stream(cons)
 
-    import collections
-    pending = collections.deque()
+        sampler = ctx["sampler"]
+        sampler.mark = "warm"
+        for i in range(max(warmup, 3)):
+            run_step(i)
+        drain()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler.mark = mark
+        ev0.record()
+        res = None
+        for i in range(steps):
+            res = run_step(i)
+        drain()          # the main stream waits for the last exchanges: they are inside the timed region
+        ev1.record()
+        torch.cuda.synchronize()
+        sampler.mark = "post"
+        if world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        checked = None
+        if mailbox is not None:
+            mailbox.check_async()    # raises if a consumer wait timed out / a producer waited in vain for an acknowledgement
+            # what arrived in this rank's mailbox for the last step must be what an all-gather of the ranks' results gives
+            j = (steps - 1) % len(self.sets)
+            got_rec, got_loss = mailbox.peek(j)
+            last = results[j] if use_graph else res
+            want = ppd.exchange_step_results(last["rec"], last["loss"].to(torch.float64))
+            checked = bool(torch.equal(got_rec.view(want.records.shape), want.records)
+                           and torch.allclose(got_loss.mean(), want.loss.double(), rtol=1e-6, atol=0))
+            if not checked:
+                raise RuntimeError("mailbox exchange does not match the all-gather of the ranks' results")
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        last = (results[(steps - 1) % len(self.sets)] if use_graph else res)
+        info = {"exchange": (note + f"; consumer reads inside the timed region: {consumed['reads']}; last step checked against an "
+                             f"all-gather: {checked}") if mailbox is not None else
+                (f"records + loss of {every} step(s) per asynchronous NCCL all-gather" + (f" [{note}]" if note else "")) if nccl else "",
+                "launch": ("CUDA graph replay" if use_graph else "eager")
+                          + (", one stream" if args.serial else ", decode on a second stream beside encode->loss")}
+        del graphs
+        return ms, last, info
 
-    bucket = []
-    exchange_every = max(1, min(args.exchange_every or len(sets), len(sets)))
-
-    def drain():
-        if bucket:      # a partial bucket at the end of a run still travels
-            pending.append(ppd.exchange_bucket([b[0] for b in bucket], [b[1] for b in bucket], async_op=True))
-            bucket.clear()
-        while pending:
-            pending.popleft().wait()
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    sampler.mark = "warm"
-    for i in range(max(args.warmup, 3)):
-        run_step(i)
-    drain()
-    torch.cuda.synchronize()
-
-    # ---- timed region: EXACTLY args.steps steps, barrier + synchronize on both sides
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.mark = "timed"
-    ev0.record()
-    for i in range(args.steps):
-        run_step(i)
-    drain()          # the main stream waits for the last exchanges: they are inside the timed region
-    ev1.record()
-    torch.cuda.synchronize()
-    sampler.mark = "post"
-    if world > 1:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
-    exchange_checked = None
-    if mailbox is not None:
-        # what arrived in this rank's mailbox for the last step must be what an all-gather of the ranks' results gives
-        j = (args.steps - 1) % len(sets)
-        got_rec, got_loss = mailbox.read(j)
-        rec_l, loss_l = (results[j][0], results[j][1]) if use_graph else step_device(sets[j], j)[:2]
-        want = ppd.exchange_step_results(rec_l, loss_l.to(torch.float64))
-        exchange_checked = bool(torch.equal(got_rec.view(want.records.shape), want.records)
-                                and torch.allclose(got_loss.mean(), want.loss.double(), rtol=1e-6, atol=0))
-        if not exchange_checked:
-            raise RuntimeError("mailbox exchange does not match the all-gather of the ranks' results")
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
-    value = world * n_hm * args.steps / (ms * 1e-3)
-
-    # ---- per-kernel timings (CUDA events on the launching stream, same rotating sets)
-    def time_kernel(fn, iters):
+    def time_kernel(self, fn, iters):
         """Average device time of one launch: each buffer set's launch is captured in a CUDA graph so that
         the Python/ctypes call overhead (~20 us) does not hide a ~10 us kernel; events on the launching stream."""
-        for s in sets:
+        torch = self.torch
+        for s in self.sets:
             fn(s)
         torch.cuda.synchronize()
         gs = []
-        for s in sets:
+        for s in self.sets:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 keep = fn(s)
@@ -414,154 +456,294 @@ def run_product(args):
             gs[i % len(gs)][0].replay()
         b.record()
         torch.cuda.synchronize()
-        return a.elapsed_time(b) * 1e-3 / iters
+        t = a.elapsed_time(b) * 1e-3 / iters
+        del gs
+        return t
 
-    targets = [am.encode_batch(s["kps"], s["vis"], dtype=tdtype) for s in sets]
-    for s, t in zip(sets, targets):
-        s["tgt"], s["w"] = t["heatmaps"], t["keypoint_weights"]
-    grads = [torch.empty_like(s["pred"]) for s in sets]
+    def kernel_times(self, iters, extra=False):
+        torch, pp = self.torch, self.pp
+        from probpose_pytorch_b200 import _lib
+        from probpose_pytorch_b200.loss import _Prepared, _PreparedEncoded
+        for s in self.sets:
+            t = self.am.encode_batch(s["kps"], s["vis"], dtype=self.tdtype)
+            s["tgt"], s["w"] = t["heatmaps"], t["keypoint_weights"]
+        prep, prep_e = {}, {}
 
-    def k_encode(s):
-        return am.encode_batch(s["kps"], s["vis"], dtype=tdtype)
+        def k_loss(s):
+            if id(s) not in prep:
+                prep[id(s)] = _Prepared(self.loss_fn, s["pred"], s["tgt"], s["w"], None, _lib.PP_LOSS_PIXEL_MEAN)
+            return prep[id(s)].forward(want_grad=True)
 
-    def k_decode(s):
-        return pm.decode_device(s["pred"])
+        def k_loss_encoded(s):
+            if id(s) not in prep_e:
+                prep_e[id(s)] = _PreparedEncoded(self.loss_fn, s["pred"], self.am, s["kps"], s["vis"], None)
+            return prep_e[id(s)].forward(want_grad=True)
 
-    def k_dark(s):
-        return am.decode_device(s["pred"])
+        fns = {"encode": lambda s: self.am.encode_batch(s["kps"], s["vis"], dtype=self.tdtype),
+               "decode_expected": lambda s: self.pm.decode_device(s["pred"]),
+               "loss_fwd_bwd": k_loss, "loss_encoded_fwd_bwd": k_loss_encoded}
+        alg = {"encode": 1, "decode_expected": 1, "loss_fwd_bwd": 3, "loss_encoded_fwd_bwd": 2}
+        if extra:
+            for s in self.sets:
+                s["logits"] = ((s["pred"].float() - 0.3) * 4.0).to(self.tdtype)
+            fns.update({"decode_dark": lambda s: self.am.decode_device(s["pred"]),
+                        "head_tail": lambda s: pp.heatmap_tail(s["logits"], 0.5)})
+            alg.update({"decode_dark": 1, "head_tail": 2})
+        kt = {k: self.time_kernel(f, iters) for k, f in fns.items()}
+        self.decode_kernel = DECODE_KERNELS.get(_lib.lib().pp_decode_expected_last_kernel(), "?")
+        peak, _ = hbm_peak()
+        out = {k: {"ms": 1e3 * t, "GBps": alg[k] * self.n_hm * self.hm_bytes / t / 1e9,
+                   "frac": alg[k] * self.n_hm * self.hm_bytes / t / 1e9 / peak, "heatmaps_per_s": self.n_hm / t,
+                   "algorithmic_planes": alg[k]} for k, t in kt.items()}
+        for s in self.sets:
+            s.pop("tgt", None); s.pop("logits", None)
+        return out
 
-    prep_cache = {}
+    def record(self, steps, warmup, extra_kernels=False, mark="timed"):
+        """ms_per_step, throughput, kernel times and roofline fractions of this workload."""
+        world = self.ctx["world"]
+        peak, peak_src = hbm_peak()
+        ms, last, info = self.time_step(steps, warmup, fused=False, mark=mark)
+        ms_f, last_f, _ = self.time_step(steps, warmup, fused=True, mark=mark + "_fused")
+        kernels = self.kernel_times(max(20, min(200, steps)), extra=extra_kernels)
+        n_job = world * self.n_hm
+        per_step = ms / steps
+        names = {"encode": "encode_kernel (OKS target encode, separable fp64 factors)",
+                 "decode_expected": self.decode_kernel,
+                 "loss_fwd_bwd": "oks_loss_fast_kernel (fused OKS loss forward+backward, TMA-staged planes)"}
+        step_kernels = ("encode", "decode_expected", "loss_fwd_bwd")
+        dom = max(step_kernels, key=lambda k: kernels[k]["ms"])
+        serial = sum(kernels[k]["ms"] for k in step_kernels)
+        traffic = None
+        tfile = ROOT / "profiles" / "traffic.json"
+        if tfile.exists():
+            traffic = json.loads(tfile.read_text()).get(f"{dom}/C{self.cfg}/{self.ctx['args'].dtype}")
+        gb = lambda planes, ms_step: planes * self.n_hm * self.hm_bytes / (ms_step * 1e-3) / 1e9
+        rec = {
+            "workload": self.wl.name, "scaling": self.scaling, "batch_per_gpu": self.B, "keypoints": self.K,
+            "heatmap": [self.W, self.H], "heatmaps_per_step_per_gpu": self.n_hm, "tensor_MB": self.n_hm * self.hm_bytes / 1e6,
+            "l2": f"rotating {self.nsets} buffer sets x {self.set_bytes / 1e6:.0f} MB (> 126 MB L2)",
+            "steps": steps, "ms_per_step": per_step, "value": n_job * steps / (ms * 1e-3), "unit": UNIT,
+            "launch": info["launch"], "exchange": info["exchange"],
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_planes"] * self.n_hm * self.hm_bytes,
+                         "share_of_step": {k: kernels[k]["ms"] / serial for k in step_kernels},
+                         "other_step_kernels": {k: {"kernel": names[k], "achieved": kernels[k]["GBps"], "frac": kernels[k]["frac"]}
+                                                for k in step_kernels if k != dom},
+                         "step": {"GBps": gb(5, per_step), "frac": gb(5, per_step) / peak,
+                                  "note": "whole step, 5 x H x W x e bytes per heatmap (write target, read prediction twice, "
+                                          "read target, write gradient)"}},
+            "fused_step": {"what": "same step with the target encode inside the loss kernel (forward_mean_encoded): the target is "
+                                   "never written or read -- 3 x H x W x e bytes per heatmap (prediction read by decode and by "
+                                   "the loss, gradient written)",
+                           "ms_per_step": ms_f / steps, "value": n_job * steps / (ms_f * 1e-3),
+                           "GBps_own_bytes": gb(3, ms_f / steps), "frac_own_bytes": gb(3, ms_f / steps) / peak,
+                           "frac_if_counted_as_5_planes": gb(5, ms_f / steps) / peak},
+            "kernels": kernels,
+        }
+        return rec, last, last_f
 
-    def k_loss(s):
-        from probpose_pytorch_b200.loss import _Prepared
-        key = id(s)
-        if key not in prep_cache:
-            prep_cache[key] = _Prepared(loss_fn, s["pred"], s["tgt"], s["w"], None, _lib.PP_LOSS_PIXEL_MEAN)
-        return prep_cache[key].forward(want_grad=True)
 
-    # head tails (section 8 a10 / f-2), not part of the step: logits with the spread of a trained head
-    for s in sets:
-        s["logits"] = ((s["pred"].float() - 0.3) * 4.0).to(tdtype).requires_grad_(True)
-        s["up"] = torch.rand_like(s["pred"])
+def parity_check(bench, last, last_f, n_sample=64):
+    """A seeded sample of the TIMED buffers against the CPU oracle: decode outputs of the last timed step (argmax / scores
+    bit-exact, coordinates 1e-5), the encoded targets and the loss gradient on the sampled heatmaps, and the loss value
+    of a sub-batch.  The oracle is the checker here, never the thing measured."""
+    import numpy as np
+    import torch
 
-    def k_tail(s):
-        return pp.heatmap_tail(s["logits"].detach(), 0.5)
+    import oracle as oc
+    wl, B, K, H, W = bench.wl, bench.B, bench.K, bench.H, bench.W
+    j = (last["_set"] if "_set" in last else 0)
+    s = bench.sets[j]
+    rng = np.random.default_rng(2024)
+    pick = np.sort(rng.choice(B * K, size=min(n_sample, B * K), replace=False))
+    pick_t = torch.from_numpy(pick).to(s["pred"].device)
+    pred = s["pred"].reshape(B * K, H, W)[pick_t].float().cpu().numpy()
+    sig = np.asarray(wl.sigmas)
+    arg = last["dec"]["argmax"].reshape(-1)[pick_t].cpu().numpy()
+    vals = last["dec"]["vals"].reshape(-1)[pick_t].cpu().numpy()
+    locs = last["dec"]["locs"].reshape(-1, 2)[pick_t].cpu().numpy()
+    tgt = last["tgt"].reshape(B * K, H, W)[pick_t].float().cpu().numpy()
+    grad = last["grad"].reshape(B * K, H, W)[pick_t].float().cpu().numpy()
+    grad_f = last_f["grad"].reshape(B * K, H, W)[pick_t].float().cpu().numpy()
+    out = {"heatmaps_checked": int(pick.size), "argmax_mismatch": 0, "score_mismatch": 0, "locs_max_rel": 0.0,
+           "target_max_rel": 0.0, "grad_max_rel": 0.0, "fused_grad_max_rel": 0.0}
+    scale_n = 1.0 / (B * K * H * W)
+    for i, n in enumerate(pick):
+        b, k = divmod(int(n), K)
+        l, v, conv = oc.heatmap_expected_value(pred[i][None], sig[k:k + 1], return_heatmap=True, conv="scipy")
+        out["argmax_mismatch"] += int(arg[i] != conv.reshape(-1).argmax())
+        out["score_mismatch"] += int(vals[i] != v[0])
+        out["locs_max_rel"] = max(out["locs_max_rel"], float(np.max(np.abs(locs[i] - l[0]) / np.maximum(np.abs(l[0]), 1.0))))
+        enc = oc.encode("argmax", wl.input_size, wl.heatmap_size, wl.sigmas, s["kps_np"][b:b + 1], s["vis_np"][b:b + 1])
+        t_ref = enc["heatmaps"][k]
+        if bench.esize == 2:
+            t_ref = torch.from_numpy(t_ref).bfloat16().float().numpy()
+        out["target_max_rel"] = max(out["target_max_rel"], float(np.max(np.abs(tgt[i] - t_ref) / np.maximum(np.abs(t_ref), 1e-30)
+                                                                        * (np.abs(t_ref) > 1e-30))))
+        w = float(enc["keypoint_weights"][0, k])
+        g_ref = oc.oks_heatmap_loss_grad_closed_form(torch.from_numpy(pred[i][None, None]), torch.from_numpy(t_ref[None, None]),
+                                                     torch.full((1, 1, 1, 1), w), smoothing_weight=0.05, oks_type="minus")
+        g_ref = np.asarray(g_ref)[0, 0] * scale_n * (H * W)     # the closed form is the gradient of the mean over ONE heatmap
+        den = np.abs(g_ref).max() * 0.05 + np.abs(g_ref) + 1e-30
+        out["grad_max_rel"] = max(out["grad_max_rel"], float(np.max(np.abs(grad[i] - g_ref) / den)))
+        out["fused_grad_max_rel"] = max(out["fused_grad_max_rel"], float(np.max(np.abs(grad_f[i] - g_ref) / den)))
+    # loss value of a sub-batch (the mean over the whole batch would take the CPU minutes)
+    nb = max(1, min(B, 1024 // K))
+    o = s["pred"][:nb].float().cpu()
+    encs = [oc.encode("argmax", wl.input_size, wl.heatmap_size, wl.sigmas, s["kps_np"][b:b + 1], s["vis_np"][b:b + 1]) for b in range(nb)]
+    t = torch.from_numpy(np.stack([e["heatmaps"] for e in encs]))
+    wts = torch.from_numpy(np.concatenate([e["keypoint_weights"] for e in encs]).astype(np.float32))
+    if bench.esize == 2:
+        t = t.bfloat16().float()
+    l_ref = float(oc.oks_heatmap_loss(o, t, wts, per_pixel=True, smoothing_weight=0.05, oks_type="minus").mean())
+    enc_d = bench.am.encode_batch(s["kps"][:nb], s["vis"][:nb], dtype=bench.tdtype)
+    l_got = float(bench.loss_fn.forward_mean(s["pred"][:nb], enc_d["heatmaps"], enc_d["keypoint_weights"]))
+    l_fused = float(bench.loss_fn.forward_mean_encoded(s["pred"][:nb], bench.am, s["kps"][:nb], s["vis"][:nb]))
+    out["loss_value_rel"] = abs(l_got - l_ref) / abs(l_ref)
+    out["fused_loss_value_rel"] = abs(l_fused - l_ref) / abs(l_ref)
+    tol = 1e-5 if bench.esize == 4 else 1e-2
+    out["tolerance"] = tol
+    out["ok"] = bool(out["argmax_mismatch"] == 0 and out["score_mismatch"] == 0 and out["locs_max_rel"] <= 1e-5
+                     and out["target_max_rel"] <= tol and out["grad_max_rel"] <= tol and out["fused_grad_max_rel"] <= tol
+                     and out["loss_value_rel"] <= tol and out["fused_loss_value_rel"] <= tol)
+    return out
 
-    def k_sparse_fwd(s):
-        return pp.heatmap_tail(s["logits"].detach(), 0.5, normalize=1.0)
 
-    def k_sparse_fwd_bwd(s):
-        s["logits"].grad = None
-        y = pp.heatmap_tail(s["logits"], 0.5, normalize=1.0)
-        y.backward(s["up"])
-        return y, s["logits"].grad
-
-    sampler.mark = "kernels"
-    iters = max(20, min(400, args.steps))
-    kt = {"encode": time_kernel(k_encode, iters), "decode_expected": time_kernel(k_decode, iters),
-          "decode_dark": time_kernel(k_dark, iters), "loss_fwd_bwd": time_kernel(k_loss, iters),
-          "head_tail": time_kernel(k_tail, iters), "sparsemax_tail_fwd": time_kernel(k_sparse_fwd, iters),
-          "sparsemax_tail_fwd_bwd": time_kernel(k_sparse_fwd_bwd, iters)}
-    peaks_file = ROOT / "MEASURED_PEAKS.json"
-    if peaks_file.exists():
-        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    alg = {"encode": 1, "decode_expected": 1, "decode_dark": 1, "loss_fwd_bwd": 3, "head_tail": 2,
-           "sparsemax_tail_fwd": 2, "sparsemax_tail_fwd_bwd": 5}
-    kernels = {k: {"ms": 1e3 * t, "GBps": alg[k] * n_hm * hm_bytes / t / 1e9,
-                   "frac": alg[k] * n_hm * hm_bytes / t / 1e9 / peak,
-                   "heatmaps_per_s": n_hm / t} for k, t in kt.items()}
-    # the dominant kernel = the one of the three step kernels with the largest share of the step's device time
-    step_kernels = ("encode", "decode_expected", "loss_fwd_bwd")
-    dom = max(step_kernels, key=lambda k: kt[k])
-    decode_kernel = {0: "conv_exact_kernel + argmax_from_conv_kernel", 1: "decode_expected_fast_kernel (one CTA per heatmap)",
-                     2: "decode_expected_warp_kernel (one warp per heatmap)", 3: "decode_expected_dense_kernel",
-                     4: "decode_expected_kernel (generic)"}.get(_lib.lib().pp_decode_expected_last_kernel(), "?")
-    names = {"encode": "encode_kernel (OKS target encode, separable fp64 factors)",
-             "decode_expected": decode_kernel + ": expected-OKS decode, TMA-staged plane, pruned separable prefilter + exact fp64 "
-                                                "re-evaluation; bounded by per-heatmap instruction latency, not by HBM",
-             "loss_fwd_bwd": "oks_loss_fast_kernel (fused OKS loss forward+backward, TMA-staged)"}
-    traffic = None
-    tfile = ROOT / "profiles" / "traffic.json"
-    if tfile.exists():
-        traffic = json.loads(tfile.read_text()).get(f"{dom}/C{args.config}/{args.dtype}")
-    serial = sum(kt[k] for k in step_kernels)
-    roofline = {"bound": "hbm", "kernel": names[dom],
-                "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
-                "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dom] * n_hm * hm_bytes,
-                "share_of_step": {k: kt[k] / serial for k in step_kernels},
-                "other_step_kernels": {k: {"kernel": names[k], "achieved": kernels[k]["GBps"], "frac": kernels[k]["frac"]}
-                                       for k in step_kernels if k != dom},
-                "step": {"GBps": 5 * n_hm * hm_bytes * args.steps / (ms * 1e-3) / 1e9,
-                         "frac": 5 * n_hm * hm_bytes * args.steps / (ms * 1e-3) / 1e9 / peak,
-                         "note": "whole step, 5 x H x W x e bytes per heatmap"}}
-
-    # ---- end to end through the public API with HOST buffers (pinned): every step's inputs (keypoints,
-    # visibility, predicted heatmaps, the four scalar heads) are copied host -> device and its results (decoded
-    # records + loss) device -> host inside the timed region.  `pipelined_steps` double-buffers the copies so
-    # that the PCIe transfer of step i+1 overlaps the kernels of step i.
+def run_e2e(bench, e2e_steps):
+    """The same metric end to end through the public API with HOST buffers (pinned): every step's inputs (keypoints,
+    visibility, predicted heatmaps, the four scalar heads) are copied host -> device and its results (decoded records +
+    loss) device -> host inside the timed region; `pipelined_steps` double-buffers the copies."""
+    import torch
+    import torch.distributed as dist
     from probpose_pytorch_b200.host_io import pipelined_steps
-    for s in sets:
-        s["heads_host"] = [h.cpu().pin_memory() for h in s["heads"]]
-
-    def host_batch(s):
-        return (s["kps_host"], s["vis_host"], s["pred_host"], *s["heads_host"])
+    ctx = bench.ctx
+    dev, world = ctx["dev"], ctx["world"]
+    hosts = []
+    for s in bench.sets:
+        hosts.append((torch.from_numpy(s["kps_np"]).pin_memory(), torch.from_numpy(s["vis_np"]).pin_memory(),
+                      s["pred"].cpu().pin_memory(), *[h.cpu().pin_memory() for h in s["heads"]]))
 
     def step_fn(kps, vis, pred, *heads):
-        enc = am.encode_batch(kps, vis, dtype=tdtype)
-        rec = codec.decode_device((pred, *heads))
+        enc = bench.am.encode_batch(kps, vis, dtype=bench.tdtype)
+        rec = bench.codec.decode_device((pred, *heads))
         out = pred.detach().requires_grad_(True)
-        loss = loss_fn.forward_mean(out, enc["heatmaps"], enc["keypoint_weights"])
+        loss = bench.loss_fn.forward_mean(out, enc["heatmaps"], enc["keypoint_weights"])
         loss.backward()
         return rec, loss.detach()
 
-    def run_e2e(n):
+    def run(n):
         last = None
-        for last in pipelined_steps((host_batch(sets[i % len(sets)]) for i in range(n)), step_fn, dev):
+        for last in pipelined_steps((hosts[i % len(hosts)] for i in range(n)), step_fn, dev):
             pass
         return last
 
-    sampler.mark = "e2e"
-    e2e_steps = max(5, min(50, args.steps))
-    run_e2e(4)
+    run(3)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    rec_h, loss_h = run_e2e(e2e_steps)
+    rec_h, loss_h = run(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t)
-    s0 = sets[0]
-    h2d = sum(t.numel() * t.element_size() for t in host_batch(s0))
+    h2d = sum(t.numel() * t.element_size() for t in hosts[0])
     d2h = rec_h.numel() * rec_h.element_size() + loss_h.numel() * loss_h.element_size()
     # the PCIe copy that bounds this number, timed alone (same pinned buffer, CUDA events)
-    dst = torch.empty_like(s0["pred"])
+    dst = torch.empty_like(bench.sets[0]["pred"])
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dst.copy_(s0["pred_host"], non_blocking=True)
+    dst.copy_(hosts[0][2], non_blocking=True)
     a.record()
-    for _ in range(5):
-        dst.copy_(s0["pred_host"], non_blocking=True)
+    for _ in range(3):
+        dst.copy_(hosts[0][2], non_blocking=True)
     b.record()
     torch.cuda.synchronize()
-    h2d_ms = a.elapsed_time(b) / 5
-    pred_bytes = s0["pred_host"].numel() * s0["pred_host"].element_size()
-    e2e = {"value": world * n_hm * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "h2d_alone": {"ms": h2d_ms, "GBps": pred_bytes / h2d_ms / 1e6,
-                         "note": "host->device copy of one step's predicted heatmaps, timed alone: the floor of e2e"},
-           "note": "public API (host_io.pipelined_steps around encode_batch, Codec.decode_device, "
-                   "OKSHeatmapLoss.forward_mean + backward) on pinned host buffers; copies of neighbouring steps "
-                   "overlap the kernels"}
+    h2d_ms = a.elapsed_time(b) / 3
+    pred_bytes = hosts[0][2].numel() * hosts[0][2].element_size()
+    if world > 1:
+        t = torch.tensor([h2d_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d_ms = float(t)
+    return {"value": world * bench.n_hm * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+            "h2d_alone": {"ms": h2d_ms, "GBps": pred_bytes / h2d_ms / 1e6, "ranks_copying_at_once": world,
+                          "ceiling_heatmaps_per_s": world * bench.n_hm / (h2d_ms * 1e-3),
+                          "note": "host->device copy of one step's predicted heatmaps timed alone (slowest rank when all ranks copy "
+                                  "at once): the PCIe / host-memory ceiling of e2e"},
+            "note": "public API (host_io.pipelined_steps around encode_batch, Codec.decode_device, "
+                    "OKSHeatmapLoss.forward_mean + backward) on pinned host buffers; copies of neighbouring steps "
+                    "overlap the kernels"}
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+
+    from probpose_pytorch_b200 import _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (product arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx = dict(args=args, dev=dev, world=world, rank=rank, sampler=sampler)
+
+    # ---- headline: the configuration's full batch on every GPU (weak scaling)
+    wl = synth.WORKLOADS[args.config]
+    head = Bench(ctx, args.config, wl.batch if args.config != 3 else wl.batch // 8, f"C{args.config}", "weak")
+    rec, last, last_f = head.record(args.steps, args.warmup, extra_kernels=True, mark="timed")
+    parity = None
+    if rank == 0:
+        last["_set"] = (args.steps - 1) % len(head.sets)
+        parity = parity_check(head, last, last_f)
+    sampler.mark = "e2e"
+    e2e = run_e2e(head, max(5, min(20, args.steps)))
+    clocks = sampler.summary(marks={"timed", "timed_fused"})
+    del last, last_f
+    head.sets.clear()
+    del head
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations, same measurement, shorter runs
+    configs = {}
+    if not args.no_subconfigs:
+        sub_steps = max(10, min(args.steps, 100))
+        plan = [("C2", 2, synth.WORKLOADS[2].batch, "weak (B = 256 per GPU)"),
+                ("C3", 3, max(1, synth.WORKLOADS[3].batch // world), f"strong (B = 1024 split over {world} GPU(s), loss + records exchanged)"),
+                ("C4", 4, max(1, synth.WORKLOADS[4].batch // world), f"strong (B = 512 split over {world} GPU(s))")]
+        for label, cid, batch, scaling in plan:
+            if cid == args.config:
+                continue
+            b = Bench(ctx, cid, batch, label, scaling)
+            r, _, _ = b.record(sub_steps, 5, mark="timed_" + label)
+            r["clocks"] = sampler.summary(marks={"timed_" + label, "timed_" + label + "_fused"})
+            if cid == 4:
+                # BASELINE configs[3]: decode throughput sweep over 1/2/4/8 GPUs -- decode only, B = 512 split over the ranks
+                t = b.time_kernel(lambda s: b.pm.decode_device(s["pred"]), sub_steps)
+                if world > 1:
+                    tt = torch.tensor([t], device=dev)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    t = float(tt)
+                r["decode_sweep"] = {"what": "expected-OKS decode only, B = 512 split over the ranks (strong scaling), device time of the "
+                                             "slowest rank", "n_gpus": world, "ms": 1e3 * t, "value": world * b.n_hm / t, "unit": "heatmaps/s"}
+            configs[label] = r
+            b.sets.clear()
+            del b
+            torch.cuda.empty_cache()
 
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
-    clocks = sampler.summary()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -570,31 +752,26 @@ def run_product(args):
                    "--config", str(args.config)]
             env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
             res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-            ref = json.loads(res.stdout.strip().splitlines()[-1])
-            cpu_baseline = ref["cpu_baseline"]
+            cpu_baseline = json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as e:  # pragma: no cover
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
     if rank == 0:
-        launches_per_step = 6 + (1 if mailbox is not None else 0)   # encode, decode, loss, loss finalize, grad-scale check, record packing (+ mailbox commit)
+        # kernels of ours inside the timed region, per step: encode, decode (+ its hand-over launch), loss, loss finalize,
+        # grad-scale check, record packing (+ mailbox commit)
+        launches_per_step = 7 + (1 if world > 1 and args.exchange == "mailbox" else 0)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.dtype == "fp32" else "bf16",
-            "data": "synthetic",
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": workload_text(wl),
-                       "arithmetic": "f32 maps; f64 for the encode exponentials and the exact argmax check"
-                                     if args.dtype == "fp32" else "bf16 maps, f32 arithmetic",
-                       "batch_per_gpu": B, "keypoints": K, "heatmap": [W, H], "heatmaps_per_step_per_gpu": n_hm,
-                       "l2": f"rotating {args.sets} buffer sets x {set_bytes / 1e6:.0f} MB (> 126 MB L2)",
-                       "launch": ("CUDA graph replay" if use_graph else "eager")
-                                 + (", one stream" if args.serial else ", decode on a second stream beside encode->loss"),
-                       "parallelism": f"dp{world} (batch sharded by image)"
-                                      + ("" if world == 1 else
-                                         f"; {exchange_note}, checked against an all-gather: {exchange_checked}" if mailbox is not None else
-                                         f"; records + loss of {exchange_every} step(s) per asynchronous all-gather"
-                                         + (f" [{exchange_note}]" if exchange_note else ""))},
-            "roofline": roofline, "kernels": kernels, "e2e": e2e, "cpu_baseline": cpu_baseline,
+                       "arithmetic": "f32 maps; f64 for the encode exponentials and the exact argmax check; f16 tensor-core proposal "
+                                     "step in the decoder" if args.dtype == "fp32" else "bf16 maps, f32 arithmetic",
+                       "batch_per_gpu": rec["batch_per_gpu"], "keypoints": rec["keypoints"], "heatmap": rec["heatmap"],
+                       "heatmaps_per_step_per_gpu": rec["heatmaps_per_step_per_gpu"], "l2": rec["l2"], "launch": rec["launch"],
+                       "parallelism": f"dp{world} (batch sharded by image)" + (f"; {rec['exchange']}" if rec["exchange"] else "")},
+            "roofline": rec["roofline"], "kernels": rec["kernels"], "fused_step": rec["fused_step"], "e2e": e2e,
+            "parity_check": parity, "configs": configs, "cpu_baseline": cpu_baseline,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line))

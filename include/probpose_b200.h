@@ -52,6 +52,8 @@ typedef enum pp_status {
 
 typedef enum pp_dtype { PP_F32 = 0, PP_BF16 = 1, PP_F64 = 2 } pp_dtype;
 
+struct pp_mailbox;   /* peer-memory exchange of a step's results between GPUs, defined with pp_pack_records below */
+
 /* ---- library ---------------------------------------------------------- */
 PP_API int pp_version(void);
 /* hash of the CUDA sources this library was compiled from (the build passes it in); lets a binding detect a stale build */
@@ -241,7 +243,11 @@ PP_API int pp_oks_loss_forward(const pp_loss_params* p,
                         void* loss_map, float* loss_kpt, float* loss_scalar, int32_t* peak_index,
                         void* grad, float grad_scale,
                         int32_t* target_out_of_range,
-                        void* scratch, int64_t scratch_bytes, pp_stream_t stream);
+                        void* scratch, int64_t scratch_bytes,
+                        const struct pp_mailbox* publish, /* or NULL; PIXEL_MEAN only: the kernel that finishes the loss also
+                                                             stores it into the mailbox slot (the loss party, see
+                                                             pp_mailbox_commit) */
+                        pp_stream_t stream);
 
 /* Encode-inside-loss: pp_encode (generate_probmaps, codec.py:11-70 + the flags of codec.py:187-200) followed by
  * pp_oks_loss_forward(PP_LOSS_PIXEL_MEAN) with the fused gradient (loss.py:428-431), as ONE pass that never
@@ -256,7 +262,7 @@ PP_API int pp_oks_loss_forward_encoded(const pp_loss_params* p, const pp_encode_
                                        const void* keypoints, const float* visible, const double* two_s,
                                        const float* keypoint_weights, float* loss_scalar, void* grad, float grad_scale,
                                        float* weights_out, uint8_t* in_image, uint8_t* annotated, void* scratch,
-                                       int64_t scratch_bytes, pp_stream_t stream);
+                                       int64_t scratch_bytes, const struct pp_mailbox* publish, pp_stream_t stream);
 
 typedef enum pp_upstream_kind {
   PP_UPSTREAM_SCALAR = 0, /* one float32 on the device, broadcast over the forward's output
@@ -298,14 +304,21 @@ PP_API int pp_pck_accuracy(const float* pred, const float* gt, const uint8_t* ma
  * 16 bytes before the end of the block. */
 typedef struct pp_mailbox {
   void* const* peer_bufs;   /* device array of `world` pointers: base of every rank's mailbox (own rank included) */
-  uint32_t* state;          /* local device memory, slots + 1 words, zero before the first call: sequence number of
-                               each slot (the last word is reserved) */
+  uint32_t* state;          /* local device memory, pp_mailbox_state_words(slots) words, zero before the first call:
+                               sequence number, arrival counter and finished-block counter of each slot, then a status
+                               word (1 + rank of a consumer whose acknowledgement did not arrive in time) */
   int32_t world, rank;
   int32_t slots, slot;      /* the block (slot, rank) of every mailbox is written */
   int64_t block_bytes;      /* pp_mailbox_block_bytes(N) */
+  int32_t flow_control;     /* 1: a slot is not rewritten before every rank has acknowledged its previous publication
+                               (pp_mailbox_ack); every rank must then consume every publication */
+  int32_t reserved;
 } pp_mailbox;
 
 PP_API int64_t pp_mailbox_block_bytes(int64_t n_records);
+/* size of one rank's mailbox (slots x world blocks + slots x world acknowledgement words) and of its local state */
+PP_API int64_t pp_mailbox_bytes(int64_t n_records, int32_t world, int32_t slots);
+PP_API int64_t pp_mailbox_state_words(int32_t slots);
 PP_API int pp_pack_records(int64_t N,
                            const double* keypoints,      /* (N, 2) input-space coordinates (pp_decode_expected) */
                            const float* scores,          /* (N) */
@@ -315,11 +328,18 @@ PP_API int pp_pack_records(int64_t N,
                            double* records,              /* out (N, 7) local, or NULL when only the mailbox is wanted */
                            const pp_mailbox* mailbox,    /* or NULL: local records only */
                            pp_stream_t stream);
-/* Completes the publication of `mailbox->slot`: stores the step's local loss (device scalar, or NULL for 0) into the
- * block and raises its flag on every rank.  Must be ordered after the pp_pack_records of the same slot. */
+/* The loss party of the publication of `mailbox->slot`: stores the step's local loss (device scalar, or NULL for 0) into
+ * the block on every rank.  A slot is published (its flag raised on every rank) by whichever of its two parties --
+ * pp_pack_records and this call, or pp_oks_loss_forward[_encoded] with `publish` -- finishes last; they may run on
+ * different streams without an ordering between them.  Exactly one of each per publication. */
 PP_API int pp_mailbox_commit(const pp_mailbox* mailbox, int64_t n_records, const float* loss, pp_stream_t stream);
-/* Wait until all `world` sources have published sequence number >= expected_seq into `slot` of this rank's mailbox.
- * *status (device int, zero before the call) becomes 1 + source rank if a source did not arrive within timeout_us. */
+/* Consumer side, after the blocks of `mailbox->slot` have been used: tell every producer that this rank is done with
+ * sequence number `seq` of the slot (required with flow_control). */
+PP_API int pp_mailbox_ack(const pp_mailbox* mailbox, uint32_t seq, pp_stream_t stream);
+/* Wait until all `world` sources have published sequence number expected_seq into `slot` of this rank's mailbox.
+ * *status (device int, zero before the call) becomes 1 + source rank if a source did not arrive within timeout_us and
+ * -(1 + source rank) if a source has already published a LATER sequence number (the block was overwritten: only
+ * possible without flow control). */
 PP_API int pp_mailbox_wait(const void* local_mailbox, int32_t world, int32_t slot, int64_t n_records, uint32_t expected_seq,
                            int64_t timeout_us, int32_t* status, pp_stream_t stream);
 

@@ -31,7 +31,8 @@ EXPORTS = (
     "pp_oks_loss_scratch_bytes",
     "pp_oks_loss_forward", "pp_oks_loss_forward_encoded", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
     "pp_pck_accuracy", "pp_binary_accuracy", "pp_masked_mae",
-    "pp_mailbox_block_bytes", "pp_pack_records", "pp_mailbox_commit", "pp_mailbox_wait",
+    "pp_mailbox_block_bytes", "pp_mailbox_bytes", "pp_mailbox_state_words", "pp_pack_records", "pp_mailbox_commit",
+    "pp_mailbox_wait", "pp_mailbox_ack",
 )
 
 
@@ -62,7 +63,8 @@ class LossParams(C.Structure):
 
 class Mailbox(C.Structure):
     _fields_ = [("peer_bufs", C.c_void_p), ("state", C.c_void_p), ("world", C.c_int32), ("rank", C.c_int32),
-                ("slots", C.c_int32), ("slot", C.c_int32), ("block_bytes", C.c_int64)]
+                ("slots", C.c_int32), ("slot", C.c_int32), ("block_bytes", C.c_int64),
+                ("flow_control", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -115,14 +117,20 @@ def lib() -> C.CDLL:
     L.pp_sparsemax_tail_backward.argtypes = [vp, vp, vp, vp, i32, i64, i64, f32, f32, vp]
     L.pp_oks_loss_scratch_bytes.argtypes = [C.POINTER(LossParams)]
     L.pp_oks_loss_scratch_bytes.restype = i64
-    L.pp_oks_loss_forward.argtypes = [C.POINTER(LossParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, i64, vp]
+    L.pp_oks_loss_forward.argtypes = [C.POINTER(LossParams), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, i64,
+                                      C.POINTER(Mailbox), vp]
     L.pp_oks_loss_forward_encoded.argtypes = [C.POINTER(LossParams), C.POINTER(EncodeParams), vp, vp, vp, vp, vp, vp, vp, f32,
-                                              vp, vp, vp, vp, i64, vp]
+                                              vp, vp, vp, vp, i64, C.POINTER(Mailbox), vp]
     L.pp_oks_loss_backward.argtypes = [C.POINTER(LossParams), vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp]
     L.pp_scale_inplace.argtypes = [vp, i32, i64, vp, vp]
     L.pp_pose_targets.argtypes = [vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, vp]
     L.pp_mailbox_block_bytes.argtypes = [i64]
     L.pp_mailbox_block_bytes.restype = i64
+    L.pp_mailbox_bytes.argtypes = [i64, i32, i32]
+    L.pp_mailbox_bytes.restype = i64
+    L.pp_mailbox_state_words.argtypes = [i32]
+    L.pp_mailbox_state_words.restype = i64
+    L.pp_mailbox_ack.argtypes = [C.POINTER(Mailbox), C.c_uint32, vp]
     L.pp_pack_records.argtypes = [i64, vp, vp, vp, vp, vp, vp, f32, vp, C.POINTER(Mailbox), vp]
     L.pp_mailbox_commit.argtypes = [C.POINTER(Mailbox), i64, vp, vp]
     L.pp_mailbox_wait.argtypes = [vp, i32, i32, i64, C.c_uint32, i64, vp, vp]
@@ -131,7 +139,7 @@ def lib() -> C.CDLL:
         if name not in ("pp_version", "pp_source_hash", "pp_last_error_string", "pp_oks_loss_scratch_bytes",
                         "pp_oks_mma_table_bytes", "pp_decode_expected_scratch_bytes_for",
                         "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes",
-                        "pp_mailbox_block_bytes"):
+                        "pp_mailbox_block_bytes", "pp_mailbox_bytes", "pp_mailbox_state_words"):
             fn.restype = C.c_int
     if L.pp_version() != PP_ABI_VERSION:
         raise RuntimeError(f"{LIB_PATH}: ABI version {L.pp_version()} != {PP_ABI_VERSION}; rebuild the extension")

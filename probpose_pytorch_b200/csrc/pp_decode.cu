@@ -885,8 +885,9 @@ int mma_launch_shape(const pp_decode_params& p, const pp_oks_table& tab, const T
   geo.cand_off = (geo.plane_bytes + 15) / 16 * 16;
   geo.slot_bytes = (geo.cand_off + static_cast<unsigned>(sizeof(int)) * (2 * kWCand + 4) + 127) / 128 * 128;
   geo.div_W = div_magic(static_cast<unsigned>(W));
+  geo.static_split = pp_env_int("PP_DECODE_STATIC", 0) ? 1u : 0u;
   const size_t smem = static_cast<size_t>(WPC) * geo.slot_bytes;
-  auto kern = decode_expected_mma_kernel<T, H, W, WPC, MINB>;
+  auto kern = dbg ? decode_expected_mma_kernel<T, H, W, WPC, MINB, true> : decode_expected_mma_kernel<T, H, W, WPC, MINB, false>;
   int per = 0;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), 32 * WPC, smem, &per)) return rc;
   if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) per = std::min(per, cap);
@@ -903,7 +904,7 @@ int mma_launch_shape(const pp_decode_params& p, const pp_oks_table& tab, const T
 template <typename T>
 int mma_launch(const pp_decode_params& p, const pp_oks_table& tab, const T* hm, float* locs, float* vals, int32_t* argmax,
                double* keypoints, unsigned* scratch, float* dbg, cudaStream_t st) {
-  if (!pp_aligned16(hm) || (p.apply_tail && !(p.temperature > 0.0f))) return PP_ERR_UNSUPPORTED_SHAPE;
+  if (!pp_aligned16(hm) || (p.apply_tail && !(p.temperature > 0.0f)) || p.K > kMmaMaxK) return PP_ERR_UNSUPPORTED_SHAPE;
   if (p.H == 64 && p.W == 48) return mma_launch_shape<T, 64, 48, 4, 4>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
   if (p.H == 96 && p.W == 72) return mma_launch_shape<T, 96, 72, 4, 2>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
   return PP_ERR_UNSUPPORTED_SHAPE;

@@ -119,30 +119,70 @@ struct MmaGeom {
   unsigned cand_off;      // byte offset of the candidate list inside a warp's slot
   unsigned slot_bytes;    // per-warp slot (multiple of 128)
   unsigned div_W;
+  unsigned static_split;  // 1: items are split statically over the warps (PP_DECODE_STATIC=1) instead of pulled from a counter
 };
 
 // scratch layout (unsigned words): [0] work counter of this kernel, [1] work counter of the hand-over launch,
 // [2] number of handed-over heatmaps, [3] unused, [4 ..] their indices
 constexpr int kMmaScratchHead = 4;
 
-// exact values of an interior pixel whose five windows lie inside the map (no reflection): same sums as team_exact5
-template <typename T>
-__device__ __noinline__ void mma_exact5_inside(const T* __restrict__ plane, const double* __restrict__ w2d, int W, int r,
-                                               int y, int x, int lane, float (&out)[5]) {
+// ---- exact values (float64 accumulation of the reference's d x d table, float32 result: what scipy stores,
+// heatmap.py:362-364), one warp, G = 1 versions of team_exact1 / team_exact5 of pp_decode_warp.cuh.  A lane owns the
+// taps lane, lane + 32, ...; its (at most U) table entries are requested up front so that their L1 / L2 latency is paid
+// once instead of once per tap (capture r02c: the dependent table load of every loop iteration was the largest stall
+// of the kernel after the work-queue atomic).  U = 4 covers d <= 11, U = 12 every radius (19 x 19 = 361 <= 384 taps).
+template <typename T, int U>
+__device__ __noinline__ float mma_exact1(const T* __restrict__ plane, const double* __restrict__ w2d, int H, int W, int r,
+                                         int y, int x, int lane) {
   const int d = 2 * r + 1, n = d * d;
   const int qs = 32 / d, rs = 32 - qs * d;
+  double w[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) w[u] = (lane + 32 * u < n) ? __ldg(w2d + lane + 32 * u) : 0.0;
   int ti = lane / d, tj = lane - ti * d;
-  const T* base = plane + (y - r) * W + (x - r);
+  double a = 0.0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (lane + 32 * u < n) {
+      const float v = plane_value<T>(plane, reflect1(y + ti - r, H) * W + reflect1(x + tj - r, W));
+      a = fma(w[u], static_cast<double>(v), a);
+    }
+    tj += rs; ti += qs;
+    if (tj >= d) { tj -= d; ++ti; }
+  }
+  return static_cast<float>(warp_sum(a));
+}
+
+// an interior pixel and its left / right / upper / lower neighbours (out[0..4]); the five windows share every tap.
+// kInside: all five windows lie inside the map (no reflection) -- the common case.
+template <typename T, int U, bool kInside>
+__device__ __noinline__ void mma_exact5(const T* __restrict__ plane, const double* __restrict__ w2d, int H, int W, int r,
+                                        int y, int x, int lane, float (&out)[5]) {
+  const int d = 2 * r + 1, n = d * d;
+  const int qs = 32 / d, rs = 32 - qs * d;
+  double w[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) w[u] = (lane + 32 * u < n) ? __ldg(w2d + lane + 32 * u) : 0.0;
+  int ti = lane / d, tj = lane - ti * d;
   double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll 1
-  for (int i = lane; i < n; i += 32) {
-    const T* q = base + ti * W + tj;
-    const double w = __ldg(w2d + i);
-    a[0] = fma(w, static_cast<double>(Elem<T>::to_f32(q[0])), a[0]);
-    a[1] = fma(w, static_cast<double>(Elem<T>::to_f32(q[-1])), a[1]);
-    a[2] = fma(w, static_cast<double>(Elem<T>::to_f32(q[1])), a[2]);
-    a[3] = fma(w, static_cast<double>(Elem<T>::to_f32(q[-W])), a[3]);
-    a[4] = fma(w, static_cast<double>(Elem<T>::to_f32(q[W])), a[4]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (lane + 32 * u < n) {
+      const int yy = y + ti - r, xx = x + tj - r;
+      int i0, i1, i2, i3, i4;   // centre, left, right, up, down
+      if (kInside) {
+        i0 = yy * W + xx; i1 = i0 - 1; i2 = i0 + 1; i3 = i0 - W; i4 = i0 + W;
+      } else {
+        const int r0 = reflect1(yy - 1, H) * W, r1 = reflect1(yy, H) * W, r2 = reflect1(yy + 1, H) * W;
+        const int c0 = reflect1(xx - 1, W), c1 = reflect1(xx, W), c2 = reflect1(xx + 1, W);
+        i0 = r1 + c1; i1 = r1 + c0; i2 = r1 + c2; i3 = r0 + c1; i4 = r2 + c1;
+      }
+      a[0] = fma(w[u], static_cast<double>(plane_value<T>(plane, i0)), a[0]);
+      a[1] = fma(w[u], static_cast<double>(plane_value<T>(plane, i1)), a[1]);
+      a[2] = fma(w[u], static_cast<double>(plane_value<T>(plane, i2)), a[2]);
+      a[3] = fma(w[u], static_cast<double>(plane_value<T>(plane, i3)), a[3]);
+      a[4] = fma(w[u], static_cast<double>(plane_value<T>(plane, i4)), a[4]);
+    }
     tj += rs; ti += qs;
     if (tj >= d) { tj -= d; ++ti; }
   }
@@ -150,7 +190,9 @@ __device__ __noinline__ void mma_exact5_inside(const T* __restrict__ plane, cons
   for (int q = 0; q < 5; ++q) out[q] = static_cast<float>(warp_sum(a[q]));
 }
 
-template <typename T, int H, int W, int WPC, int MINB>
+constexpr int kMmaMaxK = 256;    // channels whose work-queue order / radius / table index are staged in shared memory
+
+template <typename T, int H, int W, int WPC, int MINB, bool kDebug>
 __global__ void __launch_bounds__(32 * WPC, MINB)
 decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict__ heatmaps,
                            float* __restrict__ locs, float* __restrict__ vals, int32_t* __restrict__ argmax,
@@ -159,6 +201,9 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
   using S = MmaShape<H, W>;
   extern __shared__ __align__(128) unsigned char msm[];
   __shared__ __align__(8) uint64_t bars[WPC];
+  __shared__ int ch_hm[kMmaMaxK];                 // channel of queue position q (the table's `order`)
+  __shared__ unsigned short ch_tab[kMmaMaxK];     // operand table of channel k
+  __shared__ unsigned char ch_rad[kMmaMaxK];      // radius of channel k
 
   constexpr int V = Elem<T>::kVec;
   constexpr int HW = H * W, NV = HW / V;
@@ -173,44 +218,54 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
   const int N = p.B * p.K;   // the launcher guarantees N < 2^31
   const bool tail = p.apply_tail != 0;
   const float temp = p.temperature;
-  unsigned* work_counter = scratch;
   unsigned* retry_count = scratch + 2;
   int* retry_list = reinterpret_cast<int*>(scratch + kMmaScratchHead);
 
+  // per-channel constants: staged once per CTA, so that nothing on a heatmap's path waits for a dependent global load
+  for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
+    ch_hm[i] = tab.order ? tab.order[i] : i;
+    ch_tab[i] = static_cast<unsigned short>(tab.mma_index[i]);
+    ch_rad[i] = static_cast<unsigned char>(tab.radius[i]);
+  }
   if (lane == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
   }
-  __syncwarp();
+  __syncthreads();
 
-  // work queue: items are pulled one at a time from a global counter, channel-major (item j -> channel order[j / B],
-  // image j % B) so that the warps of an SM mostly share one channel's operand tables in L1
+  // Work distribution.  Items are channel-major (item j -> channel order[j / B], image j % B; consecutive warps take
+  // consecutive items), so the warps of an SM mostly share one channel's operand tables in L1.  A warp's first two
+  // items are fixed (warp, warp + warps: no atomic on the way in -- 2 x 2368 same-address atomics at kernel start cost
+  // ~15 us, measured); from the third on it pulls them from a global counter, TWO heatmaps ahead: the item after the
+  // next one is claimed at the top of an iteration and looked at at its end, so the atomic's round trip never stalls
+  // the warp (consumed half an iteration later it cost 17 % of the samples, capture r02c), while the tail of a large
+  // batch still balances (B = 1024: 146 us against 173 us with a purely static split).  geo.static_split: static only.
+  const int gwarp = blockIdx.x * WPC + warp, nwarps = gridDim.x * WPC;
+  const bool dynamic = geo.static_split == 0;
+  unsigned* work_counter = scratch;
   auto item_to_hm = [&](int j) -> int {
     const int slot_k = j / p.B, b = j - slot_k * p.B;
-    const int kk = tab.order ? tab.order[slot_k] : slot_k;
-    return b * p.K + kk;
+    return b * p.K + ch_hm[slot_k];
   };
-  int cur_item = 0, cur_hm = 0;
-  if (lane == 0) {
-    cur_item = static_cast<int>(min(atomicAdd(work_counter, 1u), static_cast<unsigned>(N)));
-    cur_hm = cur_item < N ? item_to_hm(cur_item) : N;
-    if (cur_item < N) {
-      mbar_expect_tx(bar, geo.plane_bytes);
-      tma_load_1d(slot, heatmaps + static_cast<size_t>(cur_hm) * HW, geo.plane_bytes, bar);
-    }
+  int cur_item = min(gwarp, N), next_item = min(gwarp + nwarps, N);
+  if (lane == 0 && cur_item < N) {
+    mbar_expect_tx(bar, geo.plane_bytes);
+    tma_load_1d(slot, heatmaps + static_cast<size_t>(item_to_hm(cur_item)) * HW, geo.plane_bytes, bar);
   }
-  cur_item = __shfl_sync(0xffffffffu, cur_item, 0);
-  cur_hm = __shfl_sync(0xffffffffu, cur_hm, 0);
 
   for (int it = 0; cur_item < N; ++it) {
-    const int hm = cur_hm;
-    // claim the next item now, look at the answer after the scan (the atomic's round trip is covered by it)
+    const int hm = item_to_hm(cur_item);
     unsigned pulled_raw = 0u;
-    if (lane == 0) pulled_raw = atomicAdd(work_counter, 1u);
+    if (dynamic && lane == 0) pulled_raw = atomicAdd(work_counter, 1u);   // the item after the next one
+    const int next_hm = next_item < N ? item_to_hm(next_item) : 0;
+    if (lane == 0 && next_item < N)   // the next plane is on its way into L2 while this one is decoded
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(heatmaps + static_cast<size_t>(next_hm) * HW),
+                   "r"(geo.plane_bytes)
+                   : "memory");
 
     const int k = hm % p.K;
-    const int r = tab.radius[k];
-    const uint4* t1 = reinterpret_cast<const uint4*>(tab.mma_tables) + static_cast<size_t>(tab.mma_index[k]) * (S::kT1 + S::kT2);
+    const int r = ch_rad[k];
+    const uint4* t1 = reinterpret_cast<const uint4*>(tab.mma_tables) + static_cast<size_t>(ch_tab[k]) * (S::kT1 + S::kT2);
     const uint4* t2 = t1 + S::kT1;
     const double* w2dk = tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
 
@@ -241,16 +296,6 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
     }
     vmax = warp_max(vmax);
     vmin = -warp_max(-vmin);
-
-    int next_item = 0, next_hm = 0;
-    if (lane == 0) {
-      next_item = static_cast<int>(min(pulled_raw, static_cast<unsigned>(N)));
-      next_hm = next_item < N ? item_to_hm(next_item) : N;
-      if (next_item < N)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(heatmaps + static_cast<size_t>(next_hm) * HW),
-                     "r"(geo.plane_bytes)
-                     : "memory");
-    }
 
     int best = 0;
     float best_val = 0.0f, score = vmax;
@@ -349,7 +394,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
               }
               mblk[mb] = m;
               gm = fmaxf(gm, m);
-              if (dbg_prefilter) {
+              if (kDebug && dbg_prefilter) {
                 const float inv = 1.0f / sc;
 #pragma unroll
                 for (int nbk = 0; nbk < S::NB; ++nbk)
@@ -360,14 +405,22 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
                           z[nbk][c] * inv + vmin;
               }
             } else if (mblk[mb] >= thr) {
+              // bit (4 nb + c) of the lane's mask: value (nb, c) is a candidate; the listing loop is one small body
+              // (a first version with one push site per value was 1.2 k instructions of rarely executed code that
+              // kept missing the instruction cache)
+              unsigned long long mask = 0ull;
 #pragma unroll
               for (int nbk = 0; nbk < S::NB; ++nbk)
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                  if ((c < 2 || hi_ok) && z[nbk][c] >= thr) {
-                    const int s = atomicAdd(&cand[kWCand], 1);
-                    if (s < kWCand) cand[s] = (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1);
-                  }
+                  if ((c < 2 || hi_ok) && z[nbk][c] >= thr) mask |= 1ull << (4 * nbk + c);
+              while (mask) {
+                const int e = __ffsll(static_cast<long long>(mask)) - 1;
+                mask &= mask - 1ull;
+                const int nbk = e >> 2, c = e & 3;
+                const int s = atomicAdd(&cand[kWCand], 1);
+                if (s < kWCand) cand[s] = (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1);
+              }
             }
           }
           if (pass == 0) {
@@ -382,24 +435,30 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
         handed_over = count > kWCand;
         if (!handed_over) {
           // ---- G: exact values of the candidates and of the winner's four neighbours
-          TeamExact<T> te;
-          te.plane = plane; te.w2d = w2dk; te.ex = nullptr; te.H = H; te.W = W; te.r = r; te.d = 2 * r + 1;
-          te.tl = lane; te.tw = 0; te.team = 0; te.calls = 0;
+          const bool narrow = r <= 5;   // d * d <= 121 taps: four per lane
           if (count == 1) {
             best = cand[0];
           } else {
             best_val = -INFINITY; best = 0x7fffffff;
             for (int q = 0; q < count; ++q) {
               const int ci = cand[q], cy = fast_div(ci, geo.div_W);
-              argmax_combine(best_val, best, team_exact1<T, 1>(te, cy, ci - cy * W), ci);
+              const float v = narrow ? mma_exact1<T, 4>(plane, w2dk, H, W, r, cy, ci - cy * W, lane)
+                                     : mma_exact1<T, 12>(plane, w2dk, H, W, r, cy, ci - cy * W, lane);
+              argmax_combine(best_val, best, v, ci);
             }
           }
           const int by = fast_div(best, geo.div_W), bx = best - by * W;
           interior = bx > 0 && bx < W - 1 && by > 0 && by < H - 1;
           if (interior) {
             float ev[5];
-            if (bx - r >= 1 && bx + r < W - 1 && by - r >= 1 && by + r < H - 1) mma_exact5_inside<T>(plane, w2dk, W, r, by, bx, lane, ev);
-            else team_exact5<T, 1>(te, by, bx, ev);
+            const bool inside = bx - r >= 1 && bx + r < W - 1 && by - r >= 1 && by + r < H - 1;
+            if (narrow) {
+              if (inside) mma_exact5<T, 4, true>(plane, w2dk, H, W, r, by, bx, lane, ev);
+              else mma_exact5<T, 4, false>(plane, w2dk, H, W, r, by, bx, lane, ev);
+            } else {
+              if (inside) mma_exact5<T, 12, true>(plane, w2dk, H, W, r, by, bx, lane, ev);
+              else mma_exact5<T, 12, false>(plane, w2dk, H, W, r, by, bx, lane, ev);
+            }
             best_val = ev[0];
             nb[0] = ev[1]; nb[1] = ev[2]; nb[2] = ev[3]; nb[3] = ev[4];
           }
@@ -440,7 +499,8 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
       mbar_expect_tx(bar, geo.plane_bytes);
       tma_load_1d(slot, heatmaps + static_cast<size_t>(next_hm) * HW, geo.plane_bytes, bar);
     }
-    cur_item = __shfl_sync(0xffffffffu, next_item, 0);
-    cur_hm = __shfl_sync(0xffffffffu, next_hm, 0);
+    cur_item = next_item;
+    next_item = dynamic ? static_cast<int>(min(__shfl_sync(0xffffffffu, pulled_raw, 0) + 2u * nwarps, static_cast<unsigned>(N)))
+                        : min(next_item + nwarps, N);
   }
 }

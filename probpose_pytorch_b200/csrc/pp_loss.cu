@@ -15,6 +15,7 @@
 
 #include "pp_common.cuh"
 #include "pp_loss_fast.cuh"
+#include "pp_mailbox.cuh"
 #ifdef PP_EXPERIMENTS   // measured-and-rejected variant, outside the default build
 #include "../../tools/experiments/pp_loss_pair.cuh"
 #endif
@@ -231,9 +232,11 @@ oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad, int band_h) {
   if (a.range_flag && bad_target) atomicOr(a.range_flag, 1);
 }
 
-// sum of N doubles * scale -> one float; single CTA, fixed order
+// sum of N doubles * scale -> one float; single CTA, fixed order.  With a mailbox (has_mb) the same thread also stores
+// the loss into the step's slot on every rank and arrives at the slot's publication (pp_records.cu): the multi-GPU
+// exchange needs no launch after the loss.
 __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int64_t n, double scale,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, pp_mailbox mb, int64_t mb_records, int has_mb) {
   __shared__ double red[8];
   double s = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += 256) s += partials[i];
@@ -243,8 +246,18 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += red[w];
-    out[0] = static_cast<float>(t * scale);
+    const float loss = static_cast<float>(t * scale);
+    out[0] = loss;
+    if (has_mb) pp_mailbox_dev::mailbox_store_loss_and_arrive(mb, mb_records, static_cast<double>(loss));
   }
+}
+
+int check_publish(const char* fn, const pp_mailbox* mb, int64_t n_records) {
+  if (!mb) return PP_OK;
+  PP_REQUIRE(mb->peer_bufs && mb->state && mb->world >= 1 && mb->rank >= 0 && mb->rank < mb->world && mb->slots >= 1 &&
+                 mb->slot >= 0 && mb->slot < mb->slots && mb->block_bytes == pp_mailbox_block_bytes(n_records),
+             PP_ERR_INVALID_ARG, "%s: inconsistent mailbox", fn);
+  return PP_OK;
 }
 
 template <typename T>
@@ -462,8 +475,12 @@ int64_t pp_oks_loss_scratch_bytes(const pp_loss_params* p) {
 int pp_oks_loss_forward(const pp_loss_params* p, const void* output, const void* target, const float* keypoint_weights,
                         const void* pixel_weights, const void* mask, void* loss_map, float* loss_kpt,
                         float* loss_scalar, int32_t* peak_index, void* grad, float grad_scale,
-                        int32_t* target_out_of_range, void* scratch, int64_t scratch_bytes, pp_stream_t stream) {
+                        int32_t* target_out_of_range, void* scratch, int64_t scratch_bytes, const pp_mailbox* publish,
+                        pp_stream_t stream) {
   if (int rc = check_loss_params("pp_oks_loss_forward", p)) return rc;
+  if (int rc = check_publish("pp_oks_loss_forward", publish, static_cast<int64_t>(p->B) * p->K)) return rc;
+  PP_REQUIRE(!publish || p->mode == PP_LOSS_PIXEL_MEAN, PP_ERR_INVALID_ARG, "pp_oks_loss_forward: `publish` needs PP_LOSS_PIXEL_MEAN");
+  const pp_mailbox mbv = publish ? *publish : pp_mailbox{};
   if (static_cast<int64_t>(p->B) * p->K == 0) return PP_OK;
   PP_REQUIRE(output && target, PP_ERR_INVALID_ARG, "pp_oks_loss_forward: null heatmaps");
   PP_REQUIRE(scratch && scratch_bytes >= pp_oks_loss_scratch_bytes(p), PP_ERR_SCRATCH,
@@ -485,7 +502,7 @@ int pp_oks_loss_forward(const pp_loss_params* p, const void* output, const void*
                              target_out_of_range, nullptr, grad_scale, true, st, &parts))
       return rc;
     finalize_kernel<<<1, 256, 0, st>>>(static_cast<double*>(scratch), parts, 1.0 / (static_cast<double>(N) * p->H * p->W),
-                                       loss_scalar);
+                                       loss_scalar, mbv, N, publish != nullptr);
     PP_CUDA_OK(cudaGetLastError());
     return PP_OK;
   }
@@ -503,7 +520,7 @@ int pp_oks_loss_forward(const pp_loss_params* p, const void* output, const void*
   if (rc) return rc;
   if (p->mode != PP_LOSS_PER_PIXEL) {
     const double scale = (p->mode == PP_LOSS_PIXEL_MEAN) ? 1.0 / (static_cast<double>(N) * p->H * p->W) : 1.0 / static_cast<double>(N);
-    finalize_kernel<<<1, 256, 0, st>>>(a.partials, N, scale, loss_scalar);
+    finalize_kernel<<<1, 256, 0, st>>>(a.partials, N, scale, loss_scalar, mbv, N, publish != nullptr);
     PP_CUDA_OK(cudaGetLastError());
   }
   return PP_OK;
@@ -513,8 +530,10 @@ int pp_oks_loss_forward_encoded(const pp_loss_params* p, const pp_encode_params*
                                 const void* keypoints, const float* visible, const double* two_s,
                                 const float* keypoint_weights, float* loss_scalar, void* grad, float grad_scale,
                                 float* weights_out, uint8_t* in_image, uint8_t* annotated, void* scratch,
-                                int64_t scratch_bytes, pp_stream_t stream) {
+                                int64_t scratch_bytes, const pp_mailbox* publish, pp_stream_t stream) {
   if (int rc = check_loss_params("pp_oks_loss_forward_encoded", p)) return rc;
+  if (int rc = check_publish("pp_oks_loss_forward_encoded", publish, static_cast<int64_t>(p->B) * p->K)) return rc;
+  const pp_mailbox mbv = publish ? *publish : pp_mailbox{};
   PP_REQUIRE(ep != nullptr && ep->B == p->B && ep->K == p->K && ep->H == p->H && ep->W == p->W, PP_ERR_INVALID_ARG,
              "pp_oks_loss_forward_encoded: encode and loss parameters disagree on the shape");
   PP_REQUIRE(ep->keypoint_dim >= 2 && (ep->keypoint_dtype == PP_F32 || ep->keypoint_dtype == PP_F64) &&
@@ -537,7 +556,8 @@ int pp_oks_loss_forward_encoded(const pp_loss_params* p, const pp_encode_params*
   if (int rc = launch_fast(*p, output, nullptr, keypoint_weights, grad, static_cast<double*>(scratch), nullptr, nullptr,
                            grad_scale, true, st, &parts, &enc))
     return rc;
-  finalize_kernel<<<1, 256, 0, st>>>(static_cast<double*>(scratch), parts, 1.0 / (static_cast<double>(N) * p->H * p->W), loss_scalar);
+  finalize_kernel<<<1, 256, 0, st>>>(static_cast<double*>(scratch), parts, 1.0 / (static_cast<double>(N) * p->H * p->W), loss_scalar,
+                                     mbv, N, publish != nullptr);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }

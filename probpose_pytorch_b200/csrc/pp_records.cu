@@ -6,38 +6,44 @@
 //                      every peer GPU in the same kernel: the final keypoint gather is plain stores into peer memory
 //                      over NVLink (each rank writes its block into every rank's mailbox).  No collective call, no
 //                      intermediate copy; latency-bound (a few hundred KB per rank).
-//  * pp_mailbox_commit: stores the step's local loss next to the records and raises the per-source flag of the slot
-//                      (system-scope release); launched after the records (and after the loss exists).
-//  * pp_mailbox_wait : the consumer side -- waits (bounded) until every source rank's flag of a slot has reached the
-//                      expected sequence number.
+//  * pp_mailbox_commit: stores the step's local loss next to the records (pp_oks_loss_forward[_encoded] does the same
+//                      from its own finalize kernel when it is given the mailbox).
+//  * publication     : a slot is published -- its per-source flag raised on every rank with a system-scope release
+//                      store -- by whichever of the two parties (record packing, loss) finishes LAST: both arrive on
+//                      a device-side counter, so no launch has to be ordered after both of them and the step's two
+//                      streams need no join for the exchange.
+//  * pp_mailbox_wait / pp_mailbox_ack : the consumer side -- wait (bounded) until every source rank's flag of a slot
+//                      has reached the expected sequence number; after using the blocks, acknowledge the sequence
+//                      number to every producer.
+//  * flow control    : with pp_mailbox.flow_control a producer does not touch a slot before every consumer has
+//                      acknowledged the slot's previous publication (bounded wait in pp_pack_records), so a reader can
+//                      never see a block change under it: no torn records, no mixing of steps.  Every rank must then
+//                      consume (wait + ack) every publication.
 //
 // Mailbox layout (identical on every rank, symmetric allocation): slots x world blocks of block_bytes
-//   [ N * 7 doubles | pad to 16 | loss (double) | flag (uint32) | pad ]   with block_bytes = round_up(N * 56, 16) + 16.
+//   [ N * 7 doubles | pad to 16 | loss (double) | flag (uint32) | pad ]   with block_bytes = round_up(N * 56, 16) + 16,
+// followed by slots x world uint32 acknowledgements (ack[slot][consumer], written by the consumers over NVLink).
+// Local state (pp_mailbox.state, 3 * slots + 1 uint32, zero before the first use): sequence number, arrival counter
+// and finished-block counter of every slot, then one status word (1 + rank of a consumer that did not acknowledge
+// in time).
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #include "../../include/probpose_b200.h"
 #include "pp_common.cuh"
+#include "pp_mailbox.cuh"
 
 namespace {
 
+using namespace pp_mailbox_dev;
+
 constexpr int kRecThreads = 256;
-
-__host__ __device__ inline int64_t loss_offset(int64_t n_records) { return (n_records * 56 + 15) / 16 * 16; }
-
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 __global__ void __launch_bounds__(kRecThreads)
 pack_records_kernel(int64_t N, const double* __restrict__ keypoints, const float* __restrict__ scores,
                     const float* __restrict__ prob, const float* __restrict__ vis, const float* __restrict__ oks,
-                    const float* __restrict__ err, float inv_diag, double* __restrict__ rec, pp_mailbox mb) {
+                    const float* __restrict__ err, float inv_diag, double* __restrict__ rec, pp_mailbox mb,
+                    long long ack_timeout_cycles) {
   // the block's records are assembled in shared memory and leave as contiguous 16-byte stores: whole lines to the
   // local output and -- over NVLink -- to every rank's mailbox, instead of 8-byte stores 56 bytes apart
   __shared__ __align__(16) double tile[kRecThreads * 7];
@@ -52,6 +58,21 @@ pack_records_kernel(int64_t N, const double* __restrict__ keypoints, const float
     r[4] = static_cast<double>(vis[n]);
     r[5] = static_cast<double>(oks[n]);
     r[6] = static_cast<double>(__fmul_rn(err[n], inv_diag));   // float32 errors / float32 scalar, as torch does it
+  }
+  if (mb.peer_bufs && mb.flow_control && threadIdx.x < mb.world) {
+    // flow control: consumer `threadIdx.x` must have acknowledged this slot's previous publication (sequence number
+    // state[slot]) before its copy of the block is overwritten.  Normally long true: the slot was published `slots`
+    // steps ago.
+    const unsigned want = mb.state[mb.slot];
+    const unsigned* ack = ack_word(mb.peer_bufs[mb.rank], mb, mb.slot, threadIdx.x);
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_sys(ack) - want) < 0) {
+      if (clock64() - t0 > ack_timeout_cycles) {
+        atomicCAS(mb.state + 3 * mb.slots, 0u, 1u + threadIdx.x);   // reported by the next status check; go on
+        break;
+      }
+      __nanosleep(100);
+    }
   }
   __syncthreads();
   const int count = static_cast<int>(min(static_cast<int64_t>(kRecThreads), N - first)) * 7;   // doubles in this block
@@ -71,23 +92,26 @@ pack_records_kernel(int64_t N, const double* __restrict__ keypoints, const float
     for (int i = threadIdx.x; i < pairs; i += kRecThreads) dst2[i] = src2[i];
     if ((count & 1) && threadIdx.x == 0) dst[count - 1] = tile[count - 1];
   }
-  // one system-scope fence per block, after the block barrier (cumulative over the stores the barrier has ordered):
-  // when this kernel has completed, its records are visible to every rank; pp_mailbox_commit then raises the flags
+  // one system-scope fence per block, after the block barrier (cumulative over the stores the barrier has ordered); the
+  // block that finishes last is this kernel's arrival at the slot's publication
   __syncthreads();
-  if (threadIdx.x == 0) __threadfence_system();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned* done_w = mb.state + 2 * mb.slots + mb.slot;
+    if (atomicAdd(done_w, 1u) == gridDim.x - 1) {
+      *done_w = 0u;
+      mailbox_arrive(mb, N);
+    }
+  }
 }
 
-// loss + flags of one slot: after the records of the same slot (any stream, ordered before this launch)
 __global__ void mailbox_commit_kernel(pp_mailbox mb, int64_t N, const float* __restrict__ loss) {
-  const unsigned seq = mb.state[mb.slot] + 1u;
-  const int64_t off = (static_cast<int64_t>(mb.slot) * mb.world + mb.rank) * mb.block_bytes;
-  for (int p = threadIdx.x; p < mb.world; p += blockDim.x) {
-    unsigned char* blk = static_cast<unsigned char*>(mb.peer_bufs[p]) + off;
-    *reinterpret_cast<double*>(blk + loss_offset(N)) = loss ? static_cast<double>(*loss) : 0.0;
-    st_release_sys(reinterpret_cast<unsigned*>(blk + loss_offset(N) + 8), seq);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) mb.state[mb.slot] = seq;
+  if (threadIdx.x == 0) mailbox_store_loss_and_arrive(mb, N, loss ? static_cast<double>(*loss) : 0.0);
+}
+
+__global__ void mailbox_ack_kernel(pp_mailbox mb, unsigned seq) {
+  const int p = threadIdx.x;
+  if (p < mb.world) st_release_sys(ack_word(mb.peer_bufs[p], mb, mb.slot, mb.rank), seq);
 }
 
 __global__ void mailbox_wait_kernel(const unsigned char* __restrict__ local_buf, int world, int slot, int64_t block_bytes,
@@ -96,14 +120,17 @@ __global__ void mailbox_wait_kernel(const unsigned char* __restrict__ local_buf,
   if (src >= world) return;
   const unsigned* flag = reinterpret_cast<const unsigned*>(local_buf + (static_cast<int64_t>(slot) * world + src) * block_bytes + flag_off);
   const long long t0 = clock64();
-  // sequence numbers only grow; a later one means a newer step already overwrote the slot
-  while (static_cast<int>(ld_acquire_sys(flag) - expected) < 0) {
+  unsigned seen;
+  while (static_cast<int>((seen = ld_acquire_sys(flag)) - expected) < 0) {
     if (clock64() - t0 > timeout_cycles) {
-      atomicExch(status, 1 + src);
+      atomicCAS(status, 0, 1 + src);
       return;
     }
     __nanosleep(200);
   }
+  // sequence numbers only grow: a later one means the producer has already overwritten the block (possible only
+  // without flow control) -- an error, not a success
+  if (seen != expected) atomicCAS(status, 0, -(1 + src));
 }
 
 }  // namespace
@@ -111,6 +138,13 @@ __global__ void mailbox_wait_kernel(const unsigned char* __restrict__ local_buf,
 extern "C" {
 
 int64_t pp_mailbox_block_bytes(int64_t n_records) { return loss_offset(n_records) + 16; }
+
+int64_t pp_mailbox_bytes(int64_t n_records, int32_t world, int32_t slots) {
+  if (n_records < 0 || world < 1 || slots < 1) return 0;
+  return static_cast<int64_t>(slots) * world * pp_mailbox_block_bytes(n_records) + static_cast<int64_t>(slots) * world * 4;
+}
+
+int64_t pp_mailbox_state_words(int32_t slots) { return slots < 1 ? 0 : 3 * static_cast<int64_t>(slots) + 1; }
 
 int pp_pack_records(int64_t N, const double* keypoints, const float* scores, const float* probabilities,
                     const float* visibilities, const float* oks, const float* errors, float inv_diagonal, double* records,
@@ -124,13 +158,14 @@ int pp_pack_records(int64_t N, const double* keypoints, const float* scores, con
   if (mailbox) {
     mb = *mailbox;
     PP_REQUIRE(mb.peer_bufs && mb.state && mb.world >= 1 && mb.rank >= 0 && mb.rank < mb.world && mb.slots >= 1 &&
-                   mb.slot >= 0 && mb.slot < mb.slots && mb.block_bytes == pp_mailbox_block_bytes(N),
+                   mb.slot >= 0 && mb.slot < mb.slots && mb.block_bytes == pp_mailbox_block_bytes(N) && mb.world <= kRecThreads,
                PP_ERR_INVALID_ARG, "pp_pack_records: inconsistent mailbox (world=%d rank=%d slot=%d/%d block_bytes=%lld)",
                mb.world, mb.rank, mb.slot, mb.slots, static_cast<long long>(mb.block_bytes));
   }
   const int grid = static_cast<int>((N + kRecThreads - 1) / kRecThreads);
+  const long long ack_cycles = static_cast<long long>(pp_env_int("PP_MAILBOX_ACK_TIMEOUT_US", 2000000)) * 2000ll;   // ~2 GHz
   pack_records_kernel<<<grid, kRecThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      N, keypoints, scores, probabilities, visibilities, oks, errors, inv_diagonal, records, mb);
+      N, keypoints, scores, probabilities, visibilities, oks, errors, inv_diagonal, records, mb, ack_cycles);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }
@@ -141,7 +176,18 @@ int pp_mailbox_commit(const pp_mailbox* mailbox, int64_t n_records, const float*
   PP_REQUIRE(mb.peer_bufs && mb.state && mb.world >= 1 && mb.rank >= 0 && mb.rank < mb.world && mb.slots >= 1 && mb.slot >= 0 &&
                  mb.slot < mb.slots && mb.block_bytes == pp_mailbox_block_bytes(n_records),
              PP_ERR_INVALID_ARG, "pp_mailbox_commit: inconsistent mailbox");
-  mailbox_commit_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(mb, n_records, loss);
+  mailbox_commit_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(mb, n_records, loss);
+  PP_CUDA_OK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_mailbox_ack(const pp_mailbox* mailbox, uint32_t seq, pp_stream_t stream) {
+  PP_REQUIRE(mailbox != nullptr, PP_ERR_INVALID_ARG, "pp_mailbox_ack: null mailbox");
+  const pp_mailbox mb = *mailbox;
+  PP_REQUIRE(mb.peer_bufs && mb.world >= 1 && mb.world <= 1024 && mb.rank >= 0 && mb.rank < mb.world && mb.slots >= 1 &&
+                 mb.slot >= 0 && mb.slot < mb.slots,
+             PP_ERR_INVALID_ARG, "pp_mailbox_ack: inconsistent mailbox");
+  mailbox_ack_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(mb, seq);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }

@@ -170,27 +170,40 @@ class PeerMailbox:
     """Record / loss exchange over NVLink peer memory, without a collective call.
 
     Every rank owns a mailbox of ``slots x world`` blocks (a symmetric allocation: the same buffer exists on every
-    rank and all of them are mapped into every rank's address space).  ``Codec.decode_device(..., mailbox=mb,
-    slot=s, loss=l)`` packs a step's keypoint records and, in the same kernel, stores them and the local loss into
-    block ``(s, rank)`` of EVERY rank's mailbox (``pp_pack_records``); ``commit(s, loss)`` adds the loss and raises the
-    block's flag (``pp_mailbox_commit``; ``decode_device`` does it itself when it is given the loss).  ``read(s)``
-    waits for the flags of all sources and returns ``(records (B_global, K, 7), losses (world,))`` -- what one
-    all-gather of records + loss would have delivered.  A slot is rewritten when it is published again; a consumer
-    that wants every step reads a slot before ``slots`` further steps have been published (loss logging and
-    evaluation do).  CUDA-graph capturable: the sequence numbers live in device memory.
+    rank and all of them are mapped into every rank's address space).  A step is published into a slot by two parties,
+    in any order and on any streams:
+
+    * ``Codec.decode_device(..., mailbox=mb, slot=s)`` / ``Codec.pack_records`` pack the step's keypoint records and,
+      in the same kernel, store them into block ``(s, rank)`` of EVERY rank's mailbox (``pp_pack_records``);
+    * the loss: ``OKSHeatmapLoss.forward_mean[_encoded](..., publish=mb.descriptor(s))`` stores it from the loss'
+      own finalize kernel, or ``commit(s, loss)`` from a one-thread kernel (``pp_mailbox_commit``).
+
+    Whichever finishes last raises the block's flag on every rank.  ``read(s)`` / ``read_async(s)`` wait for the flags
+    of all sources, copy the slot and acknowledge it; they return ``(records (B_global, K, 7), losses (world,))`` --
+    what one all-gather of records + loss would have delivered.
+
+    Flow control (default): a producer does not rewrite a slot before every rank has acknowledged the slot's previous
+    publication, so a reader never sees a block change under it (no torn records, no mixing of steps) -- every rank
+    must then consume every publication (``read``, ``read_async`` or ``skip``) before the slot comes round again.
+    ``flow_control=False`` drops the acknowledgements: a consumer that is too late gets an error (the sequence number it
+    finds is newer than the one it expected), never silently mixed data.  CUDA-graph capturable on the producer side:
+    the sequence numbers live in device memory.
 
     Plumbing: ``torch.distributed._symmetric_memory`` allocates and maps the buffers (world > 1); with one process an
     ordinary tensor plays every peer.
     """
 
-    def __init__(self, batch_local: int, num_keypoints: int, slots: int, device: torch.device, group=None):
+    def __init__(self, batch_local: int, num_keypoints: int, slots: int, device: torch.device, group=None,
+                 flow_control: bool = True):
         from . import _lib
         self.world, self.rank = world()
         self.slots, self.device = int(slots), torch.device(device)
+        self.flow_control = bool(flow_control)
         self.shape = (int(batch_local), int(num_keypoints), 7)
         self.n_records = int(batch_local) * int(num_keypoints)
-        self.block_bytes = int(_lib.lib().pp_mailbox_block_bytes(self.n_records))
-        nbytes = self.slots * self.world * self.block_bytes
+        L = _lib.lib()
+        self.block_bytes = int(L.pp_mailbox_block_bytes(self.n_records))
+        nbytes = int(L.pp_mailbox_bytes(self.n_records, self.world, self.slots))
         self._handle = None
         if self.world > 1:
             import torch.distributed._symmetric_memory as symm_mem
@@ -205,50 +218,108 @@ class PeerMailbox:
             self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             ptrs = [self.buf.data_ptr()]
         self._peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
-        self._state = torch.zeros(self.slots + 1, dtype=torch.int32, device=self.device)
+        self._state = torch.zeros(int(L.pp_mailbox_state_words(self.slots)), dtype=torch.int32, device=self.device)
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._published = [0] * self.slots       # host copy of the sequence numbers (launch order)
+        self._consumed = [0] * self.slots        # sequence number this rank has acknowledged, per slot
+        self._staging = None                     # private copy of one slot (consumer side)
+        self._pending_reads: list = []
         self._lib = _lib
 
     def descriptor(self, slot: int):
         assert 0 <= slot < self.slots
         return self._lib.Mailbox(self._peer_ptrs.data_ptr(), self._state.data_ptr(), self.world, self.rank, self.slots,
-                                 int(slot), self.block_bytes)
+                                 int(slot), self.block_bytes, int(self.flow_control), 0)
 
     def commit(self, slot: int, loss: Tensor | None = None) -> None:
-        """Complete the publication of ``slot``: the local loss joins the records (stored by ``pp_pack_records`` into the
-        same slot, earlier on this stream or on a stream this one has waited for) and the flags go up on every rank."""
+        """The loss party of the publication of ``slot`` as a kernel of its own: the local loss joins the records (stored
+        by ``pp_pack_records`` into the same slot on any stream); the flags go up when both have finished."""
         if loss is not None:
             loss = loss.detach().reshape(()).to(torch.float32)
         with torch.cuda.device(self.device):
             rc = self._lib.lib().pp_mailbox_commit(self.descriptor(slot), self.n_records, self._lib.ptr(loss),
                                                    self._lib.stream_ptr(self.device))
         self._lib.check(rc, "pp_mailbox_commit")
+        self.loss_enqueued(slot)
+
+    def loss_enqueued(self, slot: int) -> None:
+        """Book-keeping after the loss party of ``slot`` has been enqueued (``commit`` calls it; call it yourself after
+        ``forward_mean(..., publish=descriptor(slot))``): outside CUDA-graph capture that completes one publication."""
         if not torch.cuda.is_current_stream_capturing():
-            self.published(slot)      # a captured commit publishes when (and as often as) its graph is replayed
+            self.published(slot)      # a captured step publishes when (and as often as) its graph is replayed
 
     def published(self, slot: int, times: int = 1) -> None:
         """Book-keeping: ``slot`` was published ``times`` more times (a replayed CUDA graph publishes without
         passing through Python -- call this after each replay)."""
         self._published[slot] += times
 
-    def read(self, slot: int, timeout_us: int = 2_000_000):
-        """(records (world * B_local, K, 7) float64 in rank order, losses (world,) float64) of the latest publication
-        of ``slot`` by every rank.  Every rank must have published the slot equally often."""
-        expected = self._published[slot]
-        assert expected > 0, "nothing published into this slot yet"
-        with torch.cuda.device(self.device):
-            self._status.zero_()
-            rc = self._lib.lib().pp_mailbox_wait(self._lib.ptr(self.buf), self.world, int(slot), self.n_records,
-                                                 expected & 0xFFFFFFFF, int(timeout_us), self._lib.ptr(self._status),
-                                                 self._lib.stream_ptr(self.device))
-        self._lib.check(rc, "pp_mailbox_wait")
-        late = int(self._status.item())
-        if late:
-            raise RuntimeError(f"PeerMailbox.read: rank {late - 1} did not publish slot {slot} (sequence {expected}) in time")
-        blocks = self.buf[slot * self.world * self.block_bytes:(slot + 1) * self.world * self.block_bytes]
-        blocks = blocks.view(self.world, self.block_bytes)
+    def _views(self, buf: Tensor):
+        blocks = buf[:self.world * self.block_bytes].view(self.world, self.block_bytes)
         rec = blocks[:, :self.n_records * 56].contiguous().view(torch.float64)
         rec = rec.view((self.world * self.shape[0],) + self.shape[1:])
         loss = blocks[:, self.block_bytes - 16:self.block_bytes - 8].contiguous().view(torch.float64).reshape(self.world)
         return rec, loss
+
+    def _consume(self, slot: int, timeout_us: int, copy: bool):
+        expected = self._consumed[slot] + 1 if self.flow_control else self._published[slot]
+        assert 0 < expected <= self._published[slot], "nothing (new) published into this slot yet"
+        L = self._lib.lib()
+        with torch.cuda.device(self.device):
+            rc = L.pp_mailbox_wait(self._lib.ptr(self.buf), self.world, int(slot), self.n_records, expected & 0xFFFFFFFF,
+                                   int(timeout_us), self._lib.ptr(self._status), self._lib.stream_ptr(self.device))
+        self._lib.check(rc, "pp_mailbox_wait")
+        out = None
+        if copy:
+            if self._staging is None:
+                self._staging = torch.empty(self.world * self.block_bytes, dtype=torch.uint8, device=self.device)
+            self._staging.copy_(self.buf[slot * self.world * self.block_bytes:(slot + 1) * self.world * self.block_bytes])
+            out = self._views(self._staging)
+        if self.flow_control:
+            with torch.cuda.device(self.device):
+                rc = L.pp_mailbox_ack(self.descriptor(slot), expected & 0xFFFFFFFF, self._lib.stream_ptr(self.device))
+            self._lib.check(rc, "pp_mailbox_ack")
+        self._consumed[slot] = expected
+        self._pending_reads.append((slot, expected))
+        return out
+
+    def read_async(self, slot: int, timeout_us: int = 2_000_000):
+        """Enqueue on the current stream, without a host synchronisation, the consumer side for ``slot``: wait on the
+        device until every source rank has published it (with flow control: the oldest publication this rank has not
+        consumed yet; otherwise the latest), copy the slot's blocks into a private buffer, acknowledge.  Returns that
+        buffer's ``(records, losses)`` views (valid once the stream has run, until the next read); ``check_async()``
+        reports time-outs / overwritten blocks of everything enqueued so far."""
+        return self._consume(slot, timeout_us, True)
+
+    def skip(self, slot: int, timeout_us: int = 2_000_000) -> None:
+        """Consume a publication of ``slot`` without copying it (wait + acknowledge)."""
+        self._consume(slot, timeout_us, False)
+
+    def check_async(self) -> None:
+        """Synchronise and raise if a consumer wait timed out / found a newer sequence number, or a producer of this
+        rank ran out of patience waiting for an acknowledgement."""
+        code = int(self._status.item())
+        prod = int(self._state[3 * self.slots].item())
+        pending, self._pending_reads = self._pending_reads, []
+        self._status.zero_()
+        self._state[3 * self.slots].zero_()
+        if code > 0:
+            raise RuntimeError(f"PeerMailbox: rank {code - 1} did not publish in time (consumed: {pending})")
+        if code < 0:
+            raise RuntimeError(f"PeerMailbox: the block of rank {-code - 1} was overwritten before it was read "
+                               f"(consumed: {pending}); read every slot within `slots` steps or use flow_control=True")
+        if prod:
+            raise RuntimeError(f"PeerMailbox: rank {prod - 1} did not acknowledge a slot before it came round again; with "
+                               "flow control every rank must consume every publication")
+
+    def read(self, slot: int, timeout_us: int = 2_000_000):
+        """(records (world * B_local, K, 7) float64 in rank order, losses (world,) float64) of ``slot`` as published by
+        every rank (see ``read_async`` for which publication); synchronises."""
+        rec, loss = self.read_async(slot, timeout_us)
+        self.check_async()
+        return rec.clone(), loss.clone()
+
+    def peek(self, slot: int):
+        """The slot's current contents without waiting, acknowledging or checking (debugging / tests)."""
+        torch.cuda.synchronize(self.device)
+        rec, loss = self._views(self.buf[slot * self.world * self.block_bytes:(slot + 1) * self.world * self.block_bytes])
+        return rec.clone(), loss.clone()

@@ -68,6 +68,8 @@ class _Prepared:
                                       float(module.gaussian_weight), float(module.loss_weight), sb, sk)
         self.scratch = _scratch(self.params, dev)
 
+    publish = None   # pp_mailbox descriptor: the loss' finalize kernel also publishes it (multi-GPU exchange)
+
     def forward(self, *, want_grad: bool, grad_scale: float = 1.0):
         B, K, H, W = self.shape
         dev, mode = self.device, self.params.mode
@@ -86,7 +88,7 @@ class _Prepared:
                 self.params, _lib.ptr(self.output), _lib.ptr(self.target), _lib.ptr(self.kp_weights),
                 _lib.ptr(self.pix_weights), _lib.ptr(self.mask), _lib.ptr(loss_map), _lib.ptr(loss_kpt),
                 _lib.ptr(scalar), _lib.ptr(peak), _lib.ptr(grad), float(grad_scale), _lib.ptr(flag),
-                _lib.ptr(self.scratch), self.scratch.numel() * 8, _lib.stream_ptr(dev))
+                _lib.ptr(self.scratch), self.scratch.numel() * 8, self.publish, _lib.stream_ptr(dev))
         _lib.check(rc, "pp_oks_loss_forward")
         return dict(loss_map=loss_map, loss_kpt=loss_kpt, scalar=scalar, peak=peak, grad=grad, flag=flag)
 
@@ -141,6 +143,8 @@ class _PreparedEncoded:
                         "annotated": torch.empty((B, K), dtype=torch.bool, device=dev)}
         self.last_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # an encoded target is in [0, 1] by construction
 
+    publish = None
+
     def forward(self, *, want_grad: bool, grad_scale: float = 1.0):
         dev = self.device
         scalar = torch.empty(1, dtype=torch.float32, device=dev)
@@ -151,7 +155,7 @@ class _PreparedEncoded:
                 self.params, self.enc_params, _lib.ptr(self.output), _lib.ptr(self.keypoints), _lib.ptr(self.visible),
                 _lib.ptr(self.divisors), _lib.ptr(self.kp_weights), _lib.ptr(scalar), _lib.ptr(grad), float(grad_scale),
                 _lib.ptr(e["keypoint_weights"]), _lib.ptr(e["in_image"]), _lib.ptr(e["annotated"]),
-                _lib.ptr(self.scratch), self.scratch.numel() * 8, _lib.stream_ptr(dev))
+                _lib.ptr(self.scratch), self.scratch.numel() * 8, self.publish, _lib.stream_ptr(dev))
         _lib.check(rc, "pp_oks_loss_forward_encoded")
         return dict(loss_map=None, loss_kpt=None, scalar=scalar, peak=None, grad=grad, flag=self.last_flag)
 
@@ -257,8 +261,9 @@ class OKSHeatmapLoss(nn.Module):
         self.check_target = check_target
         assert self.oks_type in ["minus", "plus", "both"]
 
-    def _run(self, output, target, target_weights, mask, mode, default_mean, fused):
+    def _run(self, output, target, target_weights, mask, mode, default_mean, fused, publish=None):
         prep = _Prepared(self, output, target, target_weights, mask, mode)
+        prep.publish = publish
         loss = _OKSLossFunction.apply(output, prep, default_mean, fused)
         if self.check_target:
             assert int(prep.last_flag.item()) == 0, "target should be normalized"
@@ -280,12 +285,14 @@ class OKSHeatmapLoss(nn.Module):
         return self._run(output, target, target_weights, mask, _lib.PP_LOSS_PER_KEYPOINT, not per_keypoint, False)
 
     def forward_mean(self, output: Tensor, target: Tensor, target_weights: Tensor | None = None,
-                     mask: Tensor | None = None) -> Tensor:
-        """``forward(..., per_pixel=True).mean()`` in a single fused kernel (forward + backward)."""
-        return self._run(output, target, target_weights, mask, _lib.PP_LOSS_PIXEL_MEAN, False, True)
+                     mask: Tensor | None = None, publish=None) -> Tensor:
+        """``forward(..., per_pixel=True).mean()`` in a single fused kernel (forward + backward).  ``publish``: a
+        ``PeerMailbox.descriptor(slot)`` -- the kernel that finishes the loss also stores it into that mailbox slot on
+        every GPU (the loss party of the multi-GPU exchange; call ``mailbox.loss_enqueued(slot)`` afterwards)."""
+        return self._run(output, target, target_weights, mask, _lib.PP_LOSS_PIXEL_MEAN, False, True, publish)
 
     def forward_mean_encoded(self, output: Tensor, probmap, keypoints, keypoints_visible=None,
-                             target_weights: Tensor | None = None, return_encoded: bool = False):
+                             target_weights: Tensor | None = None, return_encoded: bool = False, publish=None):
         """``forward_mean(output, probmap.encode_batch(keypoints, keypoints_visible)["heatmaps"], weights)`` without
         the target: ONE pass reads ``output``, forms the target of every pixel from the keypoint's separable factors
         (generate_probmaps, codec.py:56-66), reduces the loss and writes ``d loss / d output`` -- 2 H W e bytes per
@@ -297,5 +304,6 @@ class OKSHeatmapLoss(nn.Module):
         returned as a second value."""
         probmap = getattr(probmap, "probmap", probmap)
         prep = _PreparedEncoded(self, output, probmap, keypoints, keypoints_visible, target_weights)
+        prep.publish = publish
         loss = _OKSLossFunction.apply(output, prep, False, True)
         return (loss, prep.encoded) if return_encoded else loss

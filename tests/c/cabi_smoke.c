@@ -17,7 +17,7 @@ int main(void) {
   rc = pp_encode(NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
   if (rc == PP_OK || strlen(pp_last_error_string()) == 0) return 2;
   lp.B = 1; lp.K = 1; lp.H = 4; lp.W = 4; lp.dtype = 7;
-  rc = pp_oks_loss_forward(&lp, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 1.0f, NULL, NULL, 0, NULL);
+  rc = pp_oks_loss_forward(&lp, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 1.0f, NULL, NULL, 0, NULL, NULL);
   if (rc == PP_OK) return 3;
   rc = pp_sparsemax_tail(NULL, NULL, NULL, PP_F32, 1, 0, 0.5f, 1.0f, NULL);
   if (rc == PP_OK) return 4;
@@ -26,6 +26,8 @@ int main(void) {
     memset(&mb, 0, sizeof mb);
     if (pp_mailbox_block_bytes(85) != 85 * 56 + 8 + 16) return 5;      /* records, pad to 16, loss + flag + pad */
     if (pp_mailbox_block_bytes(4352) % 16 != 0) return 6;
+    if (pp_mailbox_bytes(85, 8, 4) != 4 * 8 * pp_mailbox_block_bytes(85) + 4 * 8 * 4) return 6;   /* blocks + acknowledgements */
+    if (pp_mailbox_state_words(4) != 13 || pp_mailbox_ack(&mb, 1u, NULL) == PP_OK) return 6;
     rc = pp_pack_records(4, NULL, NULL, NULL, NULL, NULL, NULL, 1.0f, NULL, NULL, NULL);
     if (rc == PP_OK) return 7;
     rc = pp_mailbox_commit(&mb, 4, NULL, NULL);                          /* inconsistent (all-zero) mailbox */

@@ -1145,7 +1145,7 @@ def test_pack_records_and_single_process_mailbox(pp):
         assert torch.equal(rec[..., c], h.reshape(B, K).double())
     want_err = (heads[3].reshape(B, K) / float(np.sqrt(H ** 2 + W ** 2))).double()       # torch's float32 / scalar
     assert torch.equal(rec[..., 6], want_err)
-    # mailbox: two slots, published twice each; the reader sees the latest publication
+    # mailbox: two slots, published twice each, every publication consumed (flow control) before the slot comes round
     mb = PeerMailbox(B, K, 2, pred.device)
     for rnd in range(2):
         for slot in range(2):
@@ -1156,11 +1156,32 @@ def test_pack_records_and_single_process_mailbox(pp):
             got, got_loss = mb.read(slot)
             assert torch.equal(got.view(r.shape), r)
             assert got_loss.shape == (1,) and abs(got_loss.item() - 0.25 * scale) < 1e-6
+    # the loss party may come first, on another stream, and from the loss' own finalize kernel
+    side = torch.cuda.Stream()
+    loss_fn = pp.OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus", check_target=False)
+    tgt = torch.from_numpy(maps).cuda()
+    w = torch.from_numpy(vis).cuda()
+    want_loss = loss_fn.forward_mean(pred, tgt, w)
+    for order in ("loss-first", "records-first"):
+        if order == "loss-first":
+            got_l = loss_fn.forward_mean(pred, tgt, w, publish=mb.descriptor(0))
+            mb.loss_enqueued(0)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            r = codec.decode_device((pred, *heads), mailbox=mb, slot=0)
+        torch.cuda.current_stream().wait_stream(side)
+        if order == "records-first":
+            got_l = loss_fn.forward_mean(pred, tgt, w, publish=mb.descriptor(0))
+            mb.loss_enqueued(0)
+        got, got_loss = mb.read(0)
+        assert torch.equal(got.view(r.shape), r) and torch.equal(got_l, want_loss)
+        assert got_loss.item() == float(want_loss)
     # captured in a CUDA graph: the sequence numbers advance on the device, the host is told after each replay
     g = torch.cuda.CUDAGraph()
     static_heads = [h.clone() for h in heads]
     loss = torch.tensor(3.0, device="cuda")
     codec.decode_device((pred, *static_heads), mailbox=mb, slot=1, loss=loss)           # warm-up outside the graph
+    mb.skip(1)
     with torch.cuda.graph(g):
         r = codec.decode_device((pred, *static_heads), mailbox=mb, slot=1, loss=loss)
     for k in range(3):
@@ -1169,6 +1190,40 @@ def test_pack_records_and_single_process_mailbox(pp):
         mb.published(1)
         got, got_loss = mb.read(1)
         assert torch.equal(got.view(r.shape), r) and float(got[0, 0, 3]) == 0.5 + k and got_loss.item() == 3.0
+
+
+def test_mailbox_guards_readers_against_overwrites(pp, monkeypatch):
+    """A block never changes under a reader.  With flow control a producer waits (bounded) for every consumer's
+    acknowledgement before it rewrites a slot, and reports the consumer that never acknowledged; without it a reader
+    that comes too late finds a newer sequence number and gets an error -- never silently mixed steps."""
+    from probpose_pytorch_b200.distributed import PeerMailbox
+    wl = synth.WORKLOADS[2]
+    B, K = 2, wl.num_keypoints
+    rng = np.random.default_rng(5)
+    pred = torch.from_numpy(rng.random((B, K, 64, 48), dtype=np.float32)).cuda()
+    heads = [torch.from_numpy(rng.random((B, K, 1, 1), dtype=np.float32)).cuda() for _ in range(4)]
+    codec = pp.Codec(pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas))
+    one = torch.tensor(1.0, device="cuda")
+    # no flow control: two publications, the reader asks for the first one too late
+    mb = PeerMailbox(B, K, 1, pred.device, flow_control=False)
+    codec.decode_device((pred, *heads), mailbox=mb, slot=0, loss=one)
+    r2 = codec.decode_device((pred, *[h * 2 for h in heads]), mailbox=mb, slot=0, loss=one)
+    got, _ = mb.read(0)                                   # the latest publication is fine
+    assert torch.equal(got.view(r2.shape), r2)
+    mb._published[0] = 1                                  # a consumer whose book-keeping is one step behind
+    with pytest.raises(RuntimeError, match="overwritten"):
+        mb.read(0)
+    # flow control: the second publication of an unconsumed slot runs into the acknowledgement time-out
+    monkeypatch.setenv("PP_MAILBOX_ACK_TIMEOUT_US", "2000")
+    mb = PeerMailbox(B, K, 1, pred.device)
+    codec.decode_device((pred, *heads), mailbox=mb, slot=0, loss=one)
+    codec.decode_device((pred, *heads), mailbox=mb, slot=0, loss=one)
+    with pytest.raises(RuntimeError, match="did not acknowledge"):
+        mb.check_async()
+    mb = PeerMailbox(B, K, 1, pred.device)
+    mb._published[0] = 1      # the host believes a step was published; no kernel ever raised the flag
+    with pytest.raises(RuntimeError, match="did not publish in time"):
+        mb.read(0, timeout_us=2000)
 
 
 def test_expected_decoder_kernel_selection(pp, monkeypatch):

@@ -43,8 +43,9 @@ def main():
             x = pred.to(dt)
             row = []
             ref = None
-            for mma in ("1", "0"):
-                os.environ["PP_DECODE_MMA"] = mma
+            for mma in ("1", "static", "0"):
+                os.environ["PP_DECODE_MMA"] = "0" if mma == "0" else "1"
+                os.environ["PP_DECODE_STATIC"] = "1" if mma == "static" else "0"
                 us, out = timed(lambda: pm.decode_device(x), iters=20)
                 kern = _lib.lib().pp_decode_expected_last_kernel()
                 torch.cuda.synchronize()
@@ -53,8 +54,8 @@ def main():
                 if ref is None:
                     ref = out
                 else:
-                    same = all(torch.equal(ref[k], out[k]) for k in ("argmax", "vals", "locs"))
-                    row.append("same" if same else "DIFFERENT")
+                    diff = {k: int((ref[k] != out[k]).sum()) for k in ("argmax", "vals", "locs") if not torch.equal(ref[k], out[k])}
+                    row.append("same" if not diff else f"DIFFERENT {diff}")
             print(f"C{cid} B={B} {kind} {str(dt)[6:]}: " + " | ".join(row), flush=True)
         del pred
 
