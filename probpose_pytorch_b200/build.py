@@ -57,16 +57,17 @@ def source_hash(experiments: bool = False) -> str:
 
 
 def built_hash() -> str | None:
-    """The source hash embedded in the existing library, or None (no library / unreadable)."""
+    """The source hash embedded in the existing library, or None (no library / no tag).  Read from the file's bytes:
+    loading the library here would pin that copy in the process (dlopen returns an already loaded library of the same
+    name even after the file has been replaced)."""
     if not LIB.exists():
         return None
-    import ctypes
-    try:
-        L = ctypes.CDLL(str(LIB))
-        L.pp_source_hash.restype = ctypes.c_char_p
-        return L.pp_source_hash().decode()
-    except (OSError, AttributeError):
+    data = LIB.read_bytes()
+    i = data.find(b"pp_source_hash=")
+    if i < 0:
         return None
+    j = data.find(b";", i)
+    return data[i + 15:j].decode(errors="replace") if 0 < j - i < 64 else None
 
 
 def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> Path:

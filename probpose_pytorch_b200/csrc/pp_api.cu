@@ -96,7 +96,16 @@ int pp_version(void) { return PP_ABI_VERSION; }
 #ifndef PP_SOURCE_HASH
 #define PP_SOURCE_HASH "unknown"
 #endif
-const char* pp_source_hash(void) { return PP_SOURCE_HASH; }
+// the tag lets the build script read the hash out of the file without loading the library (an already loaded copy of a
+// library cannot be replaced within a process)
+static const char kSourceHashTag[] = "pp_source_hash=" PP_SOURCE_HASH ";";
+const char* pp_source_hash(void) {
+  static thread_local char hash[sizeof(kSourceHashTag)];
+  size_t n = 0;
+  for (const char* c = kSourceHashTag + 15; *c && *c != ';'; ++c) hash[n++] = *c;
+  hash[n] = 0;
+  return hash;
+}
 
 const char* pp_last_error_string(void) { return g_error; }
 

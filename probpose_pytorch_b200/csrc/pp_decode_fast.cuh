@@ -84,10 +84,14 @@ struct FastShared {
   int cand_count;
 };
 
-// n / d for small n, d via a precomputed reciprocal (exact for n * d < 2^31)
-__host__ __device__ inline unsigned div_magic(unsigned d) { return 0xFFFFFFFFu / d + 1u; }
+// n / d for small n, d via a precomputed reciprocal (exact for n * d < 2^31).  d == 1 has no 32-bit reciprocal
+// (0xFFFFFFFF / 1 + 1 wraps to 0): magic 0 means "divide by one".  Round 1 shipped without that case and the team
+// kernel split the row tasks of a band with a single row pair wrongly (q = t, xb = 0): a convolved maximum in the last
+// one or two rows of a region whose height is 1 or 2 modulo the band height was missed -- 6 of 408 576 heatmaps of
+// C5, found by comparing against the tensor-core kernel on whole batches (tests: *_maximum_in_a_short_last_band).
+__host__ __device__ inline unsigned div_magic(unsigned d) { return d <= 1u ? 0u : 0xFFFFFFFFu / d + 1u; }
 __device__ __forceinline__ int fast_div(int n, unsigned magic) {
-  return static_cast<int>(__umulhi(static_cast<unsigned>(n), magic));
+  return magic ? static_cast<int>(__umulhi(static_cast<unsigned>(n), magic)) : n;
 }
 
 template <typename T>

@@ -648,15 +648,32 @@ def test_pose_targets_from_heatmaps(pp, golden_dir):
     oks, w = oks_from_heatmaps(codec, gt, dt, torch.from_numpy(t["weight"]).cuda(), heatmap_size=wl.heatmap_size)
     assert oks.dtype == torch.float32 and tuple(oks.shape) == t["oks"].shape
     assert np.array_equal(w.cpu().numpy(), t["oks_weights"])
-    # OKS of noisy predictions inherits the DARK decoder's conditioning; most keypoints agree to 1e-5
+    # The targets are functions of two DARK decodes.  On blob-shaped channels (the only ones DARK is defined for, see
+    # test_dark_decoder_matches_golden_reference) they must agree with the reference to 1e-5 plus what the decoder's own
+    # conditioning allows: the coordinate tolerance of _dark_tolerance (cv2's float32 blur is reproducible to ~2e-7,
+    # amplified by the inverse Hessian of the log-map) propagated through oks = exp(-(dx^2 + dy^2) / (2 var area)).
     got, want = oks.cpu().numpy(), t["oks"]
-    close = np.abs(got - want) <= RTOL32 * np.abs(want) + 1e-7
-    assert close.mean() >= 0.9 and np.abs(got - want).max() <= 2e-2, (close.mean(), np.abs(got - want).max())
-    assert (got[t["weight"] == 0] == 0).all()
     err = error_from_heatmaps(codec, gt, dt).cpu().numpy()
-    live = g["blob_peaks"][:, :, 0] >= 0
-    ok = np.abs(err - t["error"]) <= RTOL32 * np.maximum(t["error"], 1.0) + 1e-3
-    assert ok[live].mean() >= 0.9
+    var = (np.asarray(wl.sigmas) * 2) ** 2
+    area = wl.heatmap_size[0] * wl.heatmap_size[1] * 0.53
+    n_blob = 0
+    for b in range(got.shape[0]):
+        live = g["blob_peaks"][b, :, 0] >= 0
+        blobby = live & (g["blob"][b].reshape(17, -1).max(axis=1) >= 0.1) & (g["clean"][b].reshape(17, -1).max(axis=1) >= 0.1)
+        tol = (_dark_tolerance(g["blob"][b], g["blob_peaks"][b], wl, RTOL32) + _dark_tolerance(g["clean"][b], g["clean_peaks"][b], wl, RTOL32)
+               + RTOL32 * np.maximum(np.abs(g["blob_dark_keypoints"][b]), 1.0))           # (K, 2) input px
+        d = np.abs(g["blob_dark_keypoints"][b] - g["clean_dark_keypoints"][b])           # (K, 2)
+        w_b = t["weight"][b].reshape(-1) > 0
+        d_oks = want[b] * ((d * tol).sum(1) + 0.5 * (tol ** 2).sum(1)) / (var * area)
+        bound = RTOL32 * np.abs(want[b]) + 1e-7 + d_oks
+        sel = blobby & w_b
+        assert (np.abs(got[b] - want[b])[sel] <= bound[sel]).all(), (b, np.max((np.abs(got[b] - want[b]) / bound)[sel]))
+        e_bound = RTOL32 * np.maximum(t["error"][b], 1.0) + np.sqrt((tol ** 2).sum(1))
+        assert (np.abs(err[b] - t["error"][b])[blobby] <= e_bound[blobby]).all(), (b, np.max((np.abs(err[b] - t["error"][b]) / e_bound)[blobby]))
+        assert np.isfinite(got[b]).all() and np.isfinite(err[b][live]).all()
+        n_blob += int(sel.sum())
+    assert n_blob >= 25                                     # the fixture is mostly blob-shaped channels
+    assert (got[t["weight"] == 0] == 0).all()
     # the same through the oracle restatement (numpy blur) on the identical inputs, tighter on clean maps
     o2, w2 = oc.oks_from_heatmaps(g["clean"], g["clean"], t["weight"], wl.sigmas, wl.input_size, wl.heatmap_size,
                                   area_size=wl.heatmap_size)
@@ -1484,3 +1501,76 @@ def test_loss_with_encoded_target_matches_encode_then_loss(pp, cid, batch, dtype
         l2.backward()
         assert abs(loss.item() - l2.item()) <= rtol * abs(l2.item()) + 1e-9
         _close(o.grad.float().cpu().numpy(), 3.0 * o2.grad.float().cpu().numpy(), rtol)
+
+
+def test_c_consumer_runs_kernels_without_torch(tmp_path):
+    """tests/c/cabi_gpu.c -- plain C + the CUDA runtime, no Python, no torch -- allocates with cudaMalloc and launches
+    pp_encode -> pp_decode_expected (tensor-core kernel) -> pp_oks_loss_forward_encoded through the C ABI."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from probpose_pytorch_b200.build import build
+    so = build()
+    root = Path(__file__).resolve().parents[1]
+    gcc = shutil.which("gcc")
+    cuda = Path("/usr/local/cuda")
+    if gcc is None or not (cuda / "include" / "cuda_runtime.h").exists():
+        pytest.skip("gcc / CUDA runtime headers not available")
+    exe = tmp_path / "cabi_gpu"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-I", str(root / "include"), "-I", str(cuda / "include"),
+                    str(root / "tests" / "c" / "cabi_gpu.c"), "-o", str(exe), str(so), f"-L{cuda / 'lib64'}", "-lcudart", "-lm",
+                    f"-Wl,-rpath,{so.parent}", f"-Wl,-rpath,{cuda / 'lib64'}"], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout + res.stderr
+
+
+def test_expected_decoder_maximum_on_the_map_border(pp, expected_kernel):
+    """Noise-only maps whose convolved maximum lies on the first / last row or column (and in the corners): the reflect
+    boundary, the last row pair of a band and the clipped bounding box all meet there.  (Found by comparing the kernels
+    on all 68 096 heatmaps of C5: one noise map with its maximum in the bottom row.)"""
+    wl = synth.WORKLOADS[2]
+    K, (W, H) = wl.num_keypoints, wl.heatmap_size
+    rng = np.random.default_rng(123)
+    spots = [(H - 1, 28), (0, 17), (31, 0), (40, W - 1), (0, 0), (H - 1, W - 1), (H - 1, 0), (0, W - 1), (H - 2, 5), (1, W - 2),
+             (H - 1, 1), (H - 1, W - 2)]
+    maps = (rng.random((len(spots), K, H, W)) * 0.02).astype(np.float32)
+    for i, (y, x) in enumerate(spots):
+        maps[i, :, y, x] = 0.033                      # one raised pixel: raw and convolved maximum sit at the border
+        if i % 2:
+            maps[i, :, max(y - 1, 0):y + 2, max(x - 1, 0):x + 2] += 0.01
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    dev = pm.decode_device(torch.from_numpy(maps).cuda())
+    bad = []
+    for b in range(len(spots)):
+        locs, vals, conv = oc.heatmap_expected_value(maps[b], wl.sigmas, return_heatmap=True, conv="scipy")
+        am = conv.reshape(K, -1).argmax(1)
+        got = dev["argmax"][b].cpu().numpy()
+        for k in np.nonzero(got != am)[0]:
+            bad.append((spots[b], int(k), int(got[k]), int(am[k])))
+        if not bad:
+            np.testing.assert_allclose(dev["locs"][b].cpu().numpy(), locs, rtol=RTOL32, atol=1e-5)
+            assert np.array_equal(dev["vals"][b].cpu().numpy(), vals)
+    assert not bad, f"(spot, channel, got, want): {bad[:12]}"
+
+
+def test_expected_decoder_maximum_in_a_short_last_band(pp, golden_dir, expected_kernel):
+    """tests/golden/decode_short_band.npz: the six heatmaps (of 408 576: C5, six seeds, fp32 + bf16) on which round 1's
+    team kernel disagreed with the tensor-core kernel -- and with the oracle.  Out-of-image keypoints whose tail peaks
+    in the bottom row over a noise floor: the pruned region spans almost the whole map, its last band holds a single
+    row pair and the row-task split divided by one through a reciprocal that wraps to zero (div_magic)."""
+    g = np.load(golden_dir / "decode_short_band.npz")
+    wl = synth.WORKLOADS[5]
+    K, (W, H) = wl.num_keypoints, wl.heatmap_size
+    sig = np.asarray(wl.sigmas)
+    pm = pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    for hm, k in zip(g["maps"], g["channel"]):
+        stack = np.zeros((2, K, H, W), dtype=np.float32)       # the map in its channel, twice (B = 2)
+        stack[:, k] = hm
+        dev = pm.decode_device(torch.from_numpy(stack).cuda())
+        l, v, conv = oc.heatmap_expected_value(hm[None], sig[k:k + 1], return_heatmap=True, conv="scipy")
+        for b in range(2):
+            assert int(dev["argmax"][b, k]) == int(conv.reshape(-1).argmax()), (int(k), b)
+            np.testing.assert_allclose(dev["locs"][b, k].cpu().numpy(), l[0], rtol=RTOL32, atol=1e-5)
+            assert float(dev["vals"][b, k]) == float(v[0])
