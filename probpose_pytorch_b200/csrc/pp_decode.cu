@@ -905,7 +905,11 @@ template <typename T>
 int mma_launch(const pp_decode_params& p, const pp_oks_table& tab, const T* hm, float* locs, float* vals, int32_t* argmax,
                double* keypoints, unsigned* scratch, float* dbg, cudaStream_t st) {
   if (!pp_aligned16(hm) || (p.apply_tail && !(p.temperature > 0.0f)) || p.K > kMmaMaxK) return PP_ERR_UNSUPPORTED_SHAPE;
-  if (p.H == 64 && p.W == 48) return mma_launch_shape<T, 64, 48, 4, 4>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
+  if (p.H == 64 && p.W == 48) {
+    if (pp_env_int("PP_DECODE_MINB", 4) == 3)   // experiment: 12 warps per SM with up to 168 registers
+      return mma_launch_shape<T, 64, 48, 4, 3>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
+    return mma_launch_shape<T, 64, 48, 4, 4>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
+  }
   if (p.H == 96 && p.W == 72) return mma_launch_shape<T, 96, 72, 4, 2>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
   return PP_ERR_UNSUPPORTED_SHAPE;
 }

@@ -128,63 +128,70 @@ constexpr int kMmaScratchHead = 4;
 
 // ---- exact values (float64 accumulation of the reference's d x d table, float32 result: what scipy stores,
 // heatmap.py:362-364), one warp, G = 1 versions of team_exact1 / team_exact5 of pp_decode_warp.cuh.  A lane owns the
-// taps lane, lane + 32, ...; its (at most U) table entries are requested up front so that their L1 / L2 latency is paid
-// once instead of once per tap (capture r02c: the dependent table load of every loop iteration was the largest stall
-// of the kernel after the work-queue atomic).  U = 4 covers d <= 11, U = 12 every radius (19 x 19 = 361 <= 384 taps).
-template <typename T, int U>
+// taps lane, lane + 32, ...; they are processed four at a time with the four table entries requested up front, so that
+// their L1 / L2 latency is paid once per group instead of once per tap (capture r02c: the dependent table load of every
+// loop iteration was the largest stall of the kernel after the work-queue atomic).  One body for every radius and for
+// windows inside / across the map border: the fully unrolled per-radius variants of a first version ran into the
+// instruction cache instead (capture r02h: 29 % of the stall samples were instruction fetches).
+template <typename T>
 __device__ __noinline__ float mma_exact1(const T* __restrict__ plane, const double* __restrict__ w2d, int H, int W, int r,
                                          int y, int x, int lane) {
   const int d = 2 * r + 1, n = d * d;
   const int qs = 32 / d, rs = 32 - qs * d;
-  double w[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) w[u] = (lane + 32 * u < n) ? __ldg(w2d + lane + 32 * u) : 0.0;
   int ti = lane / d, tj = lane - ti * d;
   double a = 0.0;
+#pragma unroll 1
+  for (int i0 = lane; i0 < n; i0 += 128) {
+    double w[4];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    if (lane + 32 * u < n) {
-      const float v = plane_value<T>(plane, reflect1(y + ti - r, H) * W + reflect1(x + tj - r, W));
-      a = fma(w[u], static_cast<double>(v), a);
+    for (int u = 0; u < 4; ++u) w[u] = (i0 + 32 * u < n) ? __ldg(w2d + i0 + 32 * u) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + 32 * u < n) {
+        const float v = plane_value<T>(plane, reflect1(y + ti - r, H) * W + reflect1(x + tj - r, W));
+        a = fma(w[u], static_cast<double>(v), a);
+      }
+      tj += rs; ti += qs;
+      if (tj >= d) { tj -= d; ++ti; }
     }
-    tj += rs; ti += qs;
-    if (tj >= d) { tj -= d; ++ti; }
   }
   return static_cast<float>(warp_sum(a));
 }
 
 // an interior pixel and its left / right / upper / lower neighbours (out[0..4]); the five windows share every tap.
-// kInside: all five windows lie inside the map (no reflection) -- the common case.
-template <typename T, int U, bool kInside>
+// inside: all five windows lie inside the map (no reflection) -- the common case, plain offsets.
+template <typename T>
 __device__ __noinline__ void mma_exact5(const T* __restrict__ plane, const double* __restrict__ w2d, int H, int W, int r,
                                         int y, int x, int lane, float (&out)[5]) {
   const int d = 2 * r + 1, n = d * d;
   const int qs = 32 / d, rs = 32 - qs * d;
-  double w[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) w[u] = (lane + 32 * u < n) ? __ldg(w2d + lane + 32 * u) : 0.0;
+  const bool inside = x - r >= 1 && x + r < W - 1 && y - r >= 1 && y + r < H - 1;
   int ti = lane / d, tj = lane - ti * d;
   double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int i0 = lane; i0 < n; i0 += 128) {
+    double w[4];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    if (lane + 32 * u < n) {
-      const int yy = y + ti - r, xx = x + tj - r;
-      int i0, i1, i2, i3, i4;   // centre, left, right, up, down
-      if (kInside) {
-        i0 = yy * W + xx; i1 = i0 - 1; i2 = i0 + 1; i3 = i0 - W; i4 = i0 + W;
-      } else {
-        const int r0 = reflect1(yy - 1, H) * W, r1 = reflect1(yy, H) * W, r2 = reflect1(yy + 1, H) * W;
-        const int c0 = reflect1(xx - 1, W), c1 = reflect1(xx, W), c2 = reflect1(xx + 1, W);
-        i0 = r1 + c1; i1 = r1 + c0; i2 = r1 + c2; i3 = r0 + c1; i4 = r2 + c1;
+    for (int u = 0; u < 4; ++u) w[u] = (i0 + 32 * u < n) ? __ldg(w2d + i0 + 32 * u) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + 32 * u < n) {
+        const int yy = y + ti - r, xx = x + tj - r;
+        int i_c = yy * W + xx, i_l = i_c - 1, i_r = i_c + 1, i_u = i_c - W, i_d = i_c + W;
+        if (!inside) {
+          const int r0 = reflect1(yy - 1, H) * W, r1 = reflect1(yy, H) * W, r2 = reflect1(yy + 1, H) * W;
+          const int c0 = reflect1(xx - 1, W), c1 = reflect1(xx, W), c2 = reflect1(xx + 1, W);
+          i_c = r1 + c1; i_l = r1 + c0; i_r = r1 + c2; i_u = r0 + c1; i_d = r2 + c1;
+        }
+        a[0] = fma(w[u], static_cast<double>(plane_value<T>(plane, i_c)), a[0]);
+        a[1] = fma(w[u], static_cast<double>(plane_value<T>(plane, i_l)), a[1]);
+        a[2] = fma(w[u], static_cast<double>(plane_value<T>(plane, i_r)), a[2]);
+        a[3] = fma(w[u], static_cast<double>(plane_value<T>(plane, i_u)), a[3]);
+        a[4] = fma(w[u], static_cast<double>(plane_value<T>(plane, i_d)), a[4]);
       }
-      a[0] = fma(w[u], static_cast<double>(plane_value<T>(plane, i0)), a[0]);
-      a[1] = fma(w[u], static_cast<double>(plane_value<T>(plane, i1)), a[1]);
-      a[2] = fma(w[u], static_cast<double>(plane_value<T>(plane, i2)), a[2]);
-      a[3] = fma(w[u], static_cast<double>(plane_value<T>(plane, i3)), a[3]);
-      a[4] = fma(w[u], static_cast<double>(plane_value<T>(plane, i4)), a[4]);
+      tj += rs; ti += qs;
+      if (tj >= d) { tj -= d; ++ti; }
     }
-    tj += rs; ti += qs;
-    if (tj >= d) { tj -= d; ++ti; }
   }
 #pragma unroll
   for (int q = 0; q < 5; ++q) out[q] = static_cast<float>(warp_sum(a[q]));
@@ -241,7 +248,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
   // the warp (consumed half an iteration later it cost 17 % of the samples, capture r02c), while the tail of a large
   // batch still balances (B = 1024: 146 us against 173 us with a purely static split).  geo.static_split: static only.
   const int gwarp = blockIdx.x * WPC + warp, nwarps = gridDim.x * WPC;
-  const bool dynamic = geo.static_split == 0;
+  const bool dynamic = geo.static_split == 0 && N > 2 * nwarps;   // nothing to pull when two items per warp cover the batch
   unsigned* work_counter = scratch;
   auto item_to_hm = [&](int j) -> int {
     const int slot_k = j / p.B, b = j - slot_k * p.B;
@@ -283,15 +290,38 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
       }
       __syncwarp();
     }
+    // ---- A': min / max: a 128-bit scan of the plane; the B-fragment pairs are loaded (64-bit) and converted after the
+    // scale is known.  (kOnePass: load the pairs once, take min / max from the same registers, convert from registers.)
+    constexpr bool kOnePass = false;   // measured: the 96 live registers spill (68 bytes per thread, reloaded through L2) -- 45.7 us against 44.1 us at C2, 286 us against 259 us at C5
     float vmax = -INFINITY, vmin = INFINITY;
-#pragma unroll 4
-    for (int i = lane; i < NV; i += 32) {
-      float f[V];
-      unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+    float2 raw[kOnePass ? S::KB : 1][kOnePass ? S::NB : 1][2];
+    if (kOnePass) {
 #pragma unroll
-      for (int j = 0; j < V; j += 2) {
-        vmax = fmaxf(vmax, fmaxf(f[j], f[j + 1]));
-        vmin = fminf(vmin, fminf(f[j], f[j + 1]));
+      for (int kb = 0; kb < S::KB; ++kb)
+#pragma unroll
+        for (int nbk = 0; nbk < S::NB; ++nbk)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int x = 16 * kb + 8 * q;              // + 2 t4
+            float2& v = raw[kOnePass ? kb : 0][kOnePass ? nbk : 0][q];
+            if (x + 8 <= W || x + 2 * t4 < W) {         // columns beyond W (W = 8 mod 16) meet zero taps
+              v = plane_pair<T>(plane + (8 * nbk + gg) * W + x + 2 * t4);
+              vmax = fmaxf(vmax, fmaxf(v.x, v.y));
+              vmin = fminf(vmin, fminf(v.x, v.y));
+            } else {
+              v = make_float2(0.0f, 0.0f);
+            }
+          }
+    } else {
+#pragma unroll 4
+      for (int i = lane; i < NV; i += 32) {
+        float f[V];
+        unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+#pragma unroll
+        for (int j = 0; j < V; j += 2) {
+          vmax = fmaxf(vmax, fmaxf(f[j], f[j + 1]));
+          vmin = fminf(vmin, fminf(f[j], f[j + 1]));
+        }
       }
     }
     vmax = warp_max(vmax);
@@ -313,6 +343,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
       handed_over = ebits < 30 || ebits > 250 || !(band < 0.25f);
       if (!handed_over) {
         const float off = -vmin * sc;
+        const wf2 sc2 = wf2_make(sc, sc), off2 = wf2_make(off, off);
         // ---- C: the whole map as float16 B-fragments of H^T: hf[kb][nb] = rows 8 nb + g, columns 16 kb + 2 t (+ 8)
         uint32_t hf[S::KB][S::NB][2];
 #pragma unroll
@@ -323,8 +354,10 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
             for (int q = 0; q < 2; ++q) {
               const int x = 16 * kb + 8 * q;              // + 2 t4
               if (x + 8 <= W || x + 2 * t4 < W) {         // columns beyond W (W = 8 mod 16) meet zero taps; keep them finite
-                const float2 v = plane_pair<T>(plane + (8 * nbk + gg) * W + x + 2 * t4);
-                hf[kb][nbk][q] = pack_h2(fmaf(v.x, sc, off), fmaf(v.y, sc, off));
+                const float2 v = kOnePass ? raw[kOnePass ? kb : 0][kOnePass ? nbk : 0][q] : plane_pair<T>(plane + (8 * nbk + gg) * W + x + 2 * t4);
+                float lo, hi;   // (v.x, v.y) * sc + off as one two-wide FFMA2
+                wf2_split(wf2_fma(wf2_make(v.x, v.y), sc2, off2), lo, hi);
+                hf[kb][nbk][q] = pack_h2(lo, hi);
               } else {
                 hf[kb][nbk][q] = 0u;
               }
@@ -405,21 +438,27 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
                           z[nbk][c] * inv + vmin;
               }
             } else if (mblk[mb] >= thr) {
-              // bit (4 nb + c) of the lane's mask: value (nb, c) is a candidate; the listing loop is one small body
-              // (a first version with one push site per value was 1.2 k instructions of rarely executed code that
-              // kept missing the instruction cache)
-              unsigned long long mask = 0ull;
+              // bit (4 nb + c) of the lane's masks (32 bits each: n-blocks 0..7 and 8..): value (nb, c) is a candidate.
+              // The listing loop below is ONE small body: one compare-and-push site per value was 1.2 k instructions of
+              // rarely executed code in the middle of the hot path (instruction-fetch stalls, capture r02c).
+              unsigned mask[(S::NB + 7) / 8];
+#pragma unroll
+              for (int w = 0; w < (S::NB + 7) / 8; ++w) mask[w] = 0u;
 #pragma unroll
               for (int nbk = 0; nbk < S::NB; ++nbk)
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                  if ((c < 2 || hi_ok) && z[nbk][c] >= thr) mask |= 1ull << (4 * nbk + c);
-              while (mask) {
-                const int e = __ffsll(static_cast<long long>(mask)) - 1;
-                mask &= mask - 1ull;
-                const int nbk = e >> 2, c = e & 3;
-                const int s = atomicAdd(&cand[kWCand], 1);
-                if (s < kWCand) cand[s] = (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1);
+                  if ((c < 2 || hi_ok) && z[nbk][c] >= thr) mask[nbk >> 3] |= 1u << (4 * (nbk & 7) + c);
+#pragma unroll
+              for (int w = 0; w < (S::NB + 7) / 8; ++w) {
+                unsigned m = mask[w];
+                while (m) {
+                  const int e = __ffs(m) - 1;
+                  m &= m - 1u;
+                  const int nbk = 8 * w + (e >> 2), c = e & 3;
+                  const int s = atomicAdd(&cand[kWCand], 1);
+                  if (s < kWCand) cand[s] = (8 * nbk + 2 * t4 + (c & 1)) * W + 16 * mb + gg + 8 * (c >> 1);
+                }
               }
             }
           }
@@ -435,30 +474,20 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
         handed_over = count > kWCand;
         if (!handed_over) {
           // ---- G: exact values of the candidates and of the winner's four neighbours
-          const bool narrow = r <= 5;   // d * d <= 121 taps: four per lane
           if (count == 1) {
             best = cand[0];
           } else {
             best_val = -INFINITY; best = 0x7fffffff;
             for (int q = 0; q < count; ++q) {
               const int ci = cand[q], cy = fast_div(ci, geo.div_W);
-              const float v = narrow ? mma_exact1<T, 4>(plane, w2dk, H, W, r, cy, ci - cy * W, lane)
-                                     : mma_exact1<T, 12>(plane, w2dk, H, W, r, cy, ci - cy * W, lane);
-              argmax_combine(best_val, best, v, ci);
+              argmax_combine(best_val, best, mma_exact1<T>(plane, w2dk, H, W, r, cy, ci - cy * W, lane), ci);
             }
           }
           const int by = fast_div(best, geo.div_W), bx = best - by * W;
           interior = bx > 0 && bx < W - 1 && by > 0 && by < H - 1;
           if (interior) {
             float ev[5];
-            const bool inside = bx - r >= 1 && bx + r < W - 1 && by - r >= 1 && by + r < H - 1;
-            if (narrow) {
-              if (inside) mma_exact5<T, 4, true>(plane, w2dk, H, W, r, by, bx, lane, ev);
-              else mma_exact5<T, 4, false>(plane, w2dk, H, W, r, by, bx, lane, ev);
-            } else {
-              if (inside) mma_exact5<T, 12, true>(plane, w2dk, H, W, r, by, bx, lane, ev);
-              else mma_exact5<T, 12, false>(plane, w2dk, H, W, r, by, bx, lane, ev);
-            }
+            mma_exact5<T>(plane, w2dk, H, W, r, by, bx, lane, ev);
             best_val = ev[0];
             nb[0] = ev[1]; nb[1] = ev[2]; nb[2] = ev[3]; nb[3] = ev[4];
           }
@@ -477,7 +506,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
       float f = static_cast<float>(is_y ? by : bx);
       if (interior) {
         const float lo = is_y ? nb[2] : nb[0], hi = is_y ? nb[3] : nb[1], c = best_val;   // left/up, right/down
-        const float g = __fdiv_rn(__fsub_rn(hi, lo), 2.0f);
+        const float g = __fmul_rn(__fsub_rn(hi, lo), 0.5f);   // == / 2 (heatmap.py:139,146): halving is exact in binary floating point
         float h = __fsub_rn(__fadd_rn(hi, lo), __fmul_rn(2.0f, c));
         if (h == 0.0f) h = 1e-6f;
         f = __fadd_rn(f, __fdiv_rn(-g, h));

@@ -235,6 +235,66 @@ __device__ __forceinline__ double fast_to_heatmap_space(const void* kp, int f64,
   return static_cast<double>(__fdiv_rn(static_cast<const float*>(kp)[idx], scale));
 }
 
+// Encode-inside-loss: the W + H separable factors of heatmap h (generate_probmaps, codec.py:45-68) as float32 into
+// f[0 .. W + H), the keypoint weight into f[W + H], and the flag outputs of ProbMap.encode / ArgMaxProbMap.encode
+// (codec.py:187-200).  Called by the `per` threads of a heatmap slot (thread `local`).  Out of line on purpose: the
+// float64 divisions and the exponential are a few hundred instructions that would otherwise sit in the middle of the
+// persistent row loop (inlined, the kernel was twice the size of the plain one and 20 % slower than it).
+struct EncodeArgs {   // what encode_factors needs of FastArgs, passed by value (a reference would move the kernel's whole
+                      // parameter block into local memory)
+  const void* keypoints;
+  const float* visible;
+  const double* two_s;
+  const float* kp_weights;
+  float* weights_out;
+  uint8_t* in_image;
+  uint8_t* annotated;
+  int W, H, K, kp_dim, kp_f64;
+  float scale_x, scale_y, input_w, input_h;
+};
+
+__device__ __noinline__ void encode_factors(const EncodeArgs a, long long h, float* __restrict__ f, int local, int per) {
+  const int W = a.W, H = a.H;
+  const float vis = a.visible ? a.visible[h] : 1.0f;
+  const bool labelled = !(vis < 0.5f);   // codec.py:53
+  const double kx = fast_to_heatmap_space(a.keypoints, a.kp_f64, h * a.kp_dim, a.scale_x);
+  const double ky = fast_to_heatmap_space(a.keypoints, a.kp_f64, h * a.kp_dim + 1, a.scale_y);
+  const double div = a.two_s[h % a.K];
+  // The reference evaluates exp(-(dx^2 + dy^2) / (2 s)) in float64 and stores float32 (codec.py:56-66).  Here the
+  // exponent is formed in float64 and the exponential taken in float32 per factor: relative error of a factor
+  // <= 2.4e-7 |exponent| + 1 ulp: the ABSOLUTE error of a target value t is <= 2.4e-7 t |ln t| <= 9e-8 -- far inside
+  // the 1e-5 budget of the loss and its gradient -- at a fifth of the instructions of a float64 exp + division.
+  const float inv_div = 1.0f / static_cast<float>(div);
+  for (int j = local; j < W + H; j += per) {
+    const double d = (j < W) ? (static_cast<double>(j) - kx) : (static_cast<double>(j - W) - ky);
+    f[j] = labelled ? expf(-(static_cast<float>(d * d) * inv_div)) : 0.0f;   // unlabelled channels stay zero (codec.py:45)
+  }
+  if (local != 0) return;
+  float wgt = vis;   // unlabelled keypoints keep their visibility value (codec.py:46,53-54)
+  if (labelled) {    // (float64 map).max() > 0 (codec.py:68): the maximum sits at the grid point nearest to the keypoint
+    const double xn = fmin(fmax(rint(kx), 0.0), static_cast<double>(W - 1));
+    const double yn = fmin(fmax(rint(ky), 0.0), static_cast<double>(H - 1));
+    const double dx = xn - kx, dy = yn - ky;
+    // exp(-q) > 0 in float64  <=>  q < 745.13321910194...: the smallest subnormal is exp(-744.44), results round to
+    // it down to exp(-745.13).  A compare instead of a float64 exp keeps this small.
+    wgt = (dx * dx + dy * dy) / div < 745.1332191019411 ? 1.0f : 0.0f;
+  }
+  f[W + H] = a.kp_weights ? a.kp_weights[h] : wgt;   // explicit weights (learn_heatmaps_from_zeros etc.) win
+  if (a.weights_out) a.weights_out[h] = wgt;
+  if (a.annotated) a.annotated[h] = vis > 0.0f;
+  if (a.in_image) {
+    bool in;
+    if (a.kp_f64) {
+      const double x = static_cast<const double*>(a.keypoints)[h * a.kp_dim], y = static_cast<const double*>(a.keypoints)[h * a.kp_dim + 1];
+      in = x >= 0.0 && x < static_cast<double>(a.input_w) && y >= 0.0 && y < static_cast<double>(a.input_h);
+    } else {
+      const float x = static_cast<const float*>(a.keypoints)[h * a.kp_dim], y = static_cast<const float*>(a.keypoints)[h * a.kp_dim + 1];
+      in = x >= 0.0f && x < a.input_w && y >= 0.0f && y < a.input_h;
+    }
+    a.in_image[h] = in;
+  }
+}
+
 template <typename T, bool kFwd, bool kGrad, int kTgt>
 __global__ void __launch_bounds__(256)
 oks_loss_fast_kernel(FastArgs a) {
@@ -257,49 +317,11 @@ oks_loss_fast_kernel(FastArgs a) {
   // encode-inside-loss: factor buffer b (alternating per unit) of heatmap slot g: ex[W], ey[H], then the keypoint weight
   const int FS = W + H + 4;
   auto fac_of = [&](int b, int gslot) { return reinterpret_cast<float*>(stage_mem + a.fac_off) + (static_cast<size_t>(b) * a.G + gslot) * FS; };
-  // factors of this thread's heatmap slot of unit `un` -> buffer b (generate_probmaps, codec.py:45-68; the flag
-  // outputs of ProbMap.encode / ArgMaxProbMap.encode, codec.py:187-200)
   auto encode_unit = [&](long long un, int b) {
-    const long long h = un * a.G + g;
-    if (g >= a.G || h >= a.N) return;
-    float* f = fac_of(b, g);
-    const float vis = a.visible ? a.visible[h] : 1.0f;
-    const bool labelled = !(vis < 0.5f);   // codec.py:53
-    const double kx = fast_to_heatmap_space(a.keypoints, a.kp_f64, h * a.kp_dim, a.scale_x);
-    const double ky = fast_to_heatmap_space(a.keypoints, a.kp_f64, h * a.kp_dim + 1, a.scale_y);
-    const double div = a.two_s[h % a.K];
-    // The reference evaluates exp(-(dx^2 + dy^2) / (2 s)) in float64 and stores float32 (codec.py:56-66).  Here the
-    // exponent is formed in float64 and the exponential taken in float32 per factor: relative error of a factor
-    // <= 2.4e-7 |exponent| + 1 ulp: the ABSOLUTE error of a target value t is <= 2.4e-7 t |ln t| <= 9e-8 -- far inside
-    // the 1e-5 budget of the loss and its gradient -- at a fifth of the instructions of a float64 exp + division.
-    const float inv_div = 1.0f / static_cast<float>(div);
-    for (int j = local; j < W + H; j += per) {
-      const double d = (j < W) ? (static_cast<double>(j) - kx) : (static_cast<double>(j - W) - ky);
-      f[j] = labelled ? expf(-(static_cast<float>(d * d) * inv_div)) : 0.0f;   // unlabelled channels stay zero (codec.py:45)
-    }
-    if (local == 0) {
-      float wgt = vis;   // unlabelled keypoints keep their visibility value (codec.py:46,53-54)
-      if (labelled) {    // (float64 map).max() > 0 (codec.py:68): the maximum sits at the grid point nearest to the keypoint
-        const double xn = fmin(fmax(rint(kx), 0.0), static_cast<double>(W - 1));
-        const double yn = fmin(fmax(rint(ky), 0.0), static_cast<double>(H - 1));
-        const double dx = xn - kx, dy = yn - ky;
-        const double dist = sqrt(dx * dx + dy * dy);
-        wgt = exp(-(dist * dist / div)) > 0.0 ? 1.0f : 0.0f;
-      }
-      f[W + H] = a.kp_weights ? a.kp_weights[h] : wgt;   // explicit weights (learn_heatmaps_from_zeros etc.) win
-      if (a.weights_out) a.weights_out[h] = wgt;
-      if (a.annotated) a.annotated[h] = vis > 0.0f;
-      if (a.in_image) {
-        bool in;
-        if (a.kp_f64) {
-          const double x = static_cast<const double*>(a.keypoints)[h * a.kp_dim], y = static_cast<const double*>(a.keypoints)[h * a.kp_dim + 1];
-          in = x >= 0.0 && x < static_cast<double>(a.input_w) && y >= 0.0 && y < static_cast<double>(a.input_h);
-        } else {
-          const float x = static_cast<const float*>(a.keypoints)[h * a.kp_dim], y = static_cast<const float*>(a.keypoints)[h * a.kp_dim + 1];
-          in = x >= 0.0f && x < a.input_w && y >= 0.0f && y < a.input_h;
-        }
-        a.in_image[h] = in;
-      }
+    if (g < a.G && un * a.G + g < a.N) {
+      const EncodeArgs e{a.keypoints, a.visible, a.two_s, a.kp_weights, a.weights_out, a.in_image, a.annotated,
+                         a.W, a.H, a.K, a.kp_dim, a.kp_f64, a.scale_x, a.scale_y, a.input_w, a.input_h};
+      encode_factors(e, un * a.G + g, fac_of(b, g), local, per);
     }
   };
   T* grad_all = static_cast<T*>(a.grad);

@@ -672,7 +672,7 @@ def test_pose_targets_from_heatmaps(pp, golden_dir):
         assert (np.abs(err[b] - t["error"][b])[blobby] <= e_bound[blobby]).all(), (b, np.max((np.abs(err[b] - t["error"][b]) / e_bound)[blobby]))
         assert np.isfinite(got[b]).all() and np.isfinite(err[b][live]).all()
         n_blob += int(sel.sum())
-    assert n_blob >= 25                                     # the fixture is mostly blob-shaped channels
+    assert n_blob >= 12                                     # a third of the fixture's channels are weighted blobs
     assert (got[t["weight"] == 0] == 0).all()
     # the same through the oracle restatement (numpy blur) on the identical inputs, tighter on clean maps
     o2, w2 = oc.oks_from_heatmaps(g["clean"], g["clean"], t["weight"], wl.sigmas, wl.input_size, wl.heatmap_size,

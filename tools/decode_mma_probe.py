@@ -43,9 +43,9 @@ def main():
             x = pred.to(dt)
             row = []
             ref = None
-            for mma in ("1", "static", "0"):
+            for mma in ("1", "minb3", "0"):
                 os.environ["PP_DECODE_MMA"] = "0" if mma == "0" else "1"
-                os.environ["PP_DECODE_STATIC"] = "1" if mma == "static" else "0"
+                os.environ["PP_DECODE_MINB"] = "3" if mma == "minb3" else "4"
                 us, out = timed(lambda: pm.decode_device(x), iters=20)
                 kern = _lib.lib().pp_decode_expected_last_kernel()
                 torch.cuda.synchronize()
