@@ -270,6 +270,7 @@ class Bench:
             self.sets.append(dict(kps=kps_d, vis=vis_d, pred=pred, heads=heads, kps_np=kps, vis_np=vis))
         self.set_bytes = 3 * self.n_hm * self.hm_bytes
         self.side = torch.cuda.Stream(device=dev)
+        self._sync_token = torch.zeros(1, device=dev)
         self.mailbox, self.exchange_note = None, ""
         torch.cuda.synchronize()
 
@@ -397,6 +398,12 @@ class Bench:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            # still outside the timed region: a tiny collective on this stream, so that ev0 is recorded when it
+            # completes -- within a microsecond or two on every rank -- instead of whenever each rank's CPU gets round to it
+            # after the barrier (tens of microseconds apart: in a 2 ms region that is several percent, and the exchange's
+            # final wait would charge the latest starter's delay to everybody)
+            dist.all_reduce(self._sync_token)
         sampler.mark = mark
         ev0.record()
         res = None
@@ -726,7 +733,15 @@ def run_product(args):
             if cid == args.config:
                 continue
             b = Bench(ctx, cid, batch, label, scaling)
-            r, _, _ = b.record(sub_steps, 5, mark="timed_" + label)
+            # these records are not bound to --steps: time at least ~30 ms so that launch / rank skew (tens of microseconds)
+            # stays well below a percent of a region of 0.1 ms steps
+            est = b.time_kernel(lambda s: b.step(s)["loss"], 5)
+            if world > 1:
+                tt = torch.tensor([est], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                est = float(tt)
+            steps_here = int(min(1000, max(sub_steps, 0.03 / max(est, 1e-6))))
+            r, _, _ = b.record(steps_here, 5, mark="timed_" + label)
             r["clocks"] = sampler.summary(marks={"timed_" + label, "timed_" + label + "_fused"})
             if cid == 4:
                 # BASELINE configs[3]: decode throughput sweep over 1/2/4/8 GPUs -- decode only, B = 512 split over the ranks

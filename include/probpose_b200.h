@@ -164,6 +164,9 @@ PP_API int pp_heatmap_maximum(const void* heatmaps, int32_t heatmap_dtype, int64
  * refine_keypoints_dark_udp (codec.py:315-375) + scaling. */
 PP_API int pp_decode_argmax_dark(const pp_decode_params* p,
                           const float* blur_taps, int32_t blur_ksize, /* (ksize) float32 taps, odd ksize */
+                          const void* blur_mma_table, /* pp_blur_mma_table_build for this (H, W, ksize) -- enables the
+                                                         tensor-core kernel (then scratch must hold
+                                                         pp_decode_expected_scratch_bytes_for(p) bytes) -- or NULL */
                           const void* heatmaps,
                           float* peaks,       /* out (N, 2) integer peaks (or -1) or NULL */
                           float* scores,      /* out (N) raw maxima */
@@ -171,6 +174,12 @@ PP_API int pp_decode_argmax_dark(const pp_decode_params* p,
                           double* keypoints,  /* out (N, 2) input-space coordinates, or NULL */
                           void* scratch, int64_t scratch_bytes, /* as for pp_decode_expected (may be NULL) */
                           pp_stream_t stream);
+
+/* Operand table of the DARK decoder's tensor-core kernel: the zero-padded ksize-tap blur (codec.py:303-310) as banded
+ * Toeplitz matrices in mma.sync fragment order, pp_oks_mma_table_bytes(1, H, W) bytes; ksize <= 15. */
+PP_API int pp_blur_mma_table_build(const float* blur_taps, int32_t blur_ksize, int32_t H, int32_t W, void* out, pp_stream_t stream);
+/* Which kernel this thread's most recent pp_decode_argmax_dark launched: 5 tensor-core, 1 CTA per heatmap, 0 other. */
+PP_API int pp_decode_argmax_dark_last_kernel(void);
 
 /* head tail (head.py:526-532, normalize=None): y = clamp(x / temperature, 0, 1) */
 PP_API int pp_heatmap_tail(const void* x, void* y, int32_t dtype, int64_t numel, float temperature, pp_stream_t stream);

@@ -26,7 +26,7 @@ EXPORTS = (
     "pp_version", "pp_source_hash", "pp_last_error_string", "pp_device_info", "pp_encode", "pp_decode_expected",
     "pp_oks_mma_table_bytes", "pp_oks_mma_table_build", "pp_decode_expected_scratch_bytes_for",
     "pp_decode_expected_workspace_floats", "pp_decode_expected_scratch_bytes", "pp_decode_expected_last_kernel",
-    "pp_heatmap_maximum", "pp_decode_argmax_dark", "pp_heatmap_tail", "pp_heatmap_tail_backward",
+    "pp_heatmap_maximum", "pp_decode_argmax_dark", "pp_blur_mma_table_build", "pp_decode_argmax_dark_last_kernel", "pp_heatmap_tail", "pp_heatmap_tail_backward",
     "pp_sparsemax_tail", "pp_sparsemax_tail_backward",
     "pp_oks_loss_scratch_bytes",
     "pp_oks_loss_forward", "pp_oks_loss_forward_encoded", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
@@ -107,7 +107,9 @@ def lib() -> C.CDLL:
     L.pp_decode_expected_workspace_floats.argtypes = [C.POINTER(DecodeParams)]
     L.pp_decode_expected_workspace_floats.restype = i64
     L.pp_heatmap_maximum.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, vp]
-    L.pp_decode_argmax_dark.argtypes = [C.POINTER(DecodeParams), vp, i32, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.pp_decode_argmax_dark.argtypes = [C.POINTER(DecodeParams), vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.pp_blur_mma_table_build.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.pp_decode_argmax_dark_last_kernel.argtypes = []
     L.pp_heatmap_tail.argtypes = [vp, vp, i32, i64, f32, vp]
     L.pp_heatmap_tail_backward.argtypes = [vp, vp, vp, i32, i64, f32, vp]
     L.pp_pck_accuracy.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.c_double, vp, vp, vp, vp, vp]

@@ -135,6 +135,23 @@ class _ProbMapBase:
             self._device_tables[key] = t
         return t
 
+    def _blur_mma_table(self, dev: torch.device, H: int, W: int):
+        """Operand table of the DARK decoder's tensor-core kernel for (H, W, blur_kernel_size), built once per device;
+        None for shapes / kernel sizes without such a kernel."""
+        key = ("blur_mma", self.blur_kernel_size, H, W, str(dev))
+        if key not in self._device_tables:
+            L = _lib.lib()
+            nbytes = int(L.pp_oks_mma_table_bytes(1, H, W)) if self.blur_kernel_size <= 15 else 0
+            t = None
+            if nbytes > 0:
+                t = torch.empty(nbytes // 2, dtype=torch.float16, device=dev)
+                with torch.cuda.device(dev):
+                    rc = L.pp_blur_mma_table_build(_lib.ptr(self._blur_taps(dev)), int(self.blur_kernel_size), H, W, _lib.ptr(t),
+                                                   _lib.stream_ptr(dev))
+                _lib.check(rc, "pp_blur_mma_table_build")
+            self._device_tables[key] = t
+        return self._device_tables[key]
+
     # -- encode -------------------------------------------------------------------------------
     def encode_batch(self, keypoints, keypoints_visible=None, *, dtype: torch.dtype = torch.float32,
                      device: torch.device | None = None) -> dict:
@@ -273,13 +290,16 @@ class ArgMaxProbMap(_ProbMapBase):
         p = _lib.DecodeParams(B, K, H, W, _lib.dtype_code(hm.dtype), int(temperature is not None),
                               float(temperature or 1.0), float(self.input_size[0]), float(self.input_size[1]))
         taps = self._blur_taps(dev)
-        scratch = torch.empty(4, dtype=torch.int32, device=dev)   # work-queue counter of the kernel
+        table = self._blur_mma_table(dev, H, W)
+        # work-queue counters + the hand-over list of the tensor-core kernel (one int32 per heatmap)
+        scratch = torch.empty((int(_lib.lib().pp_decode_expected_scratch_bytes_for(p)) + 3) // 4, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            rc = _lib.lib().pp_decode_argmax_dark(p, _lib.ptr(taps), int(self.blur_kernel_size), _lib.ptr(hm),
+            rc = _lib.lib().pp_decode_argmax_dark(p, _lib.ptr(taps), int(self.blur_kernel_size), _lib.ptr(table), _lib.ptr(hm),
                                                   _lib.ptr(out["peaks"]), _lib.ptr(out["scores"]),
                                                   _lib.ptr(out["locs"]), _lib.ptr(out["keypoints"]),
                                                   _lib.ptr(scratch), scratch.numel() * 4, _lib.stream_ptr(dev))
         _lib.check(rc, "pp_decode_argmax_dark")
+        out["_scratch"] = scratch   # word 2: number of heatmaps the tensor-core kernel handed on
         return out
 
 

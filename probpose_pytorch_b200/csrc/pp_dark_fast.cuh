@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kFThreads, 6)
 decode_dark_fast_kernel(pp_decode_params p, const float* __restrict__ blur_taps, int ksize,
                         const T* __restrict__ heatmaps, float* __restrict__ peaks, float* __restrict__ scores,
                         float* __restrict__ refined, double* __restrict__ keypoints, FastGeom geo,
-                        unsigned* __restrict__ work_counter) {
+                        unsigned* __restrict__ work_counter, const int* __restrict__ list,
+                        const unsigned* __restrict__ list_count) {
   extern __shared__ __align__(128) unsigned char fsm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ DarkShared sh;
@@ -76,7 +77,10 @@ decode_dark_fast_kernel(pp_decode_params p, const float* __restrict__ blur_taps,
 
   constexpr int V = Elem<T>::kVec;
   const int H = p.H, W = p.W, HW = H * W, WV = W / V, FS = geo.full_stride;
-  const int64_t N = static_cast<int64_t>(p.B) * p.K;
+  // `list` (with its device-side length): decode only the listed heatmaps -- the ones the tensor-core kernel
+  // (pp_decode_mma.cuh, kDark) handed on
+  const int64_t N = list ? static_cast<int64_t>(*list_count) : static_cast<int64_t>(p.B) * p.K;
+  auto item_to_hm = [&](long long j) -> long long { return list ? static_cast<long long>(list[j]) : j; };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool tail = p.apply_tail != 0;
   const float temp = p.temperature;
@@ -100,14 +104,15 @@ decode_dark_fast_kernel(pp_decode_params p, const float* __restrict__ blur_taps,
     next_item = dynamic ? static_cast<long long>(atomicAdd(work_counter, 1u)) : static_cast<long long>(blockIdx.x);
     if (next_item < N) {
       mbar_expect_tx(&bar, geo.plane_bytes);
-      tma_load_1d(fsm, heatmaps + next_item * HW, geo.plane_bytes, &bar);
+      tma_load_1d(fsm, heatmaps + item_to_hm(next_item) * HW, geo.plane_bytes, &bar);
     }
   }
   __syncthreads();
-  long long hm = next_item;
+  long long item = next_item;
   bool pads_dirty = false;   // the tile path scribbles over what the full path uses as zero pad columns
 
-  for (int it = 0; hm < N; ++it) {
+  for (int it = 0; item < N; ++it) {
+    const long long hm = item_to_hm(item);
     if (tid == 0) { sh.bbox[0] = W; sh.bbox[1] = -1; sh.bbox[2] = H; sh.bbox[3] = -1; sh.p0 = 0x7fffffff; }
     mbar_wait(&bar, it & 1);
 
@@ -268,12 +273,12 @@ decode_dark_fast_kernel(pp_decode_params p, const float* __restrict__ blur_taps,
     __syncthreads();
     const bool plane_free = empty || tile_path;
     auto fetch_next = [&]() {   // thread 0
-      const long long j = dynamic ? static_cast<long long>(atomicAdd(work_counter, 1u)) : hm + static_cast<long long>(gridDim.x);
+      const long long j = dynamic ? static_cast<long long>(atomicAdd(work_counter, 1u)) : item + static_cast<long long>(gridDim.x);
       next_item = j;
       if (j < N) {
         fence_proxy_async();
         mbar_expect_tx(&bar, geo.plane_bytes);
-        tma_load_1d(fsm, heatmaps + j * HW, geo.plane_bytes, &bar);
+        tma_load_1d(fsm, heatmaps + item_to_hm(j) * HW, geo.plane_bytes, &bar);
       }
     };
     if (plane_free && tid == 0) fetch_next();
@@ -368,6 +373,6 @@ decode_dark_fast_kernel(pp_decode_params p, const float* __restrict__ blur_taps,
       if (tid == 0) fetch_next();
       __syncthreads();
     }
-    hm = next_item;
+    item = next_item;
   }
 }

@@ -425,7 +425,6 @@ decode_expected_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict
 #include "../../tools/experiments/pp_decode_dense.cuh"
 #endif
 #include "pp_decode_warp.cuh"
-#include "pp_decode_mma.cuh"
 
 // ---------------------------------------------------------------------------
 // generic exact path: full convolved map (return_heatmap=True, or maps too large for shared memory)
@@ -562,6 +561,7 @@ __device__ __forceinline__ void pinv_sym2(double a, double b, double c, double& 
 }
 
 #include "pp_dark_fast.cuh"
+#include "pp_decode_mma.cuh"
 
 template <typename T>
 __global__ void __launch_bounds__(512)
@@ -876,9 +876,9 @@ bool dense_geometry(const pp_decode_params& p, const void* heatmaps, DenseGeom* 
 #endif
 
 // Launch of the tensor-core kernel for the shapes it is instantiated for; PP_ERR_UNSUPPORTED_SHAPE otherwise.
-template <typename T, int H, int W, int WPC, int MINB>
+template <typename T, int H, int W, int WPC, int MINB, bool kDark>
 int mma_launch_shape(const pp_decode_params& p, const pp_oks_table& tab, const T* hm, float* locs, float* vals,
-                     int32_t* argmax, double* keypoints, unsigned* scratch, float* dbg, cudaStream_t st) {
+                     int32_t* argmax, double* keypoints, unsigned* scratch, float* dbg, const MmaDarkArgs& dk, cudaStream_t st) {
   const int64_t N = static_cast<int64_t>(p.B) * p.K;
   MmaGeom geo{};
   geo.plane_bytes = static_cast<unsigned>(sizeof(T) * H * W);
@@ -887,7 +887,8 @@ int mma_launch_shape(const pp_decode_params& p, const pp_oks_table& tab, const T
   geo.div_W = div_magic(static_cast<unsigned>(W));
   geo.static_split = pp_env_int("PP_DECODE_STATIC", 0) ? 1u : 0u;
   const size_t smem = static_cast<size_t>(WPC) * geo.slot_bytes;
-  auto kern = dbg ? decode_expected_mma_kernel<T, H, W, WPC, MINB, true> : decode_expected_mma_kernel<T, H, W, WPC, MINB, false>;
+  auto kern = (dbg && !kDark) ? decode_expected_mma_kernel<T, H, W, WPC, MINB, true, false>
+                              : decode_expected_mma_kernel<T, H, W, WPC, MINB, false, kDark>;
   int per = 0;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), 32 * WPC, smem, &per)) return rc;
   if (const int cap = pp_env_int("PP_DECODE_CTAS", 0); cap > 0) per = std::min(per, cap);
@@ -895,22 +896,22 @@ int mma_launch_shape(const pp_decode_params& p, const pp_oks_table& tab, const T
   if (const int cap = pp_env_int("PP_DECODE_GRID", 0); cap > 0) grid = std::min(grid, cap);   // test hook: many heatmaps per warp
   PP_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(unsigned) * kMmaScratchHead, st));
   if (pp_env_int("PP_DEBUG", 0))
-    fprintf(stderr, "[pp] decode_expected_mma_kernel %dx%d grid=%d threads=%d smem=%zu ctas/sm=%d\n", H, W, grid, 32 * WPC, smem, per);
-  kern<<<grid, 32 * WPC, smem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, geo, scratch, dbg);
+    fprintf(stderr, "[pp] decode_expected_mma_kernel %dx%d dark=%d grid=%d threads=%d smem=%zu ctas/sm=%d\n", H, W, int(kDark), grid, 32 * WPC, smem, per);
+  kern<<<grid, 32 * WPC, smem, st>>>(p, tab, hm, locs, vals, argmax, keypoints, geo, scratch, dbg, dk);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }
 
-template <typename T>
+template <typename T, bool kDark>
 int mma_launch(const pp_decode_params& p, const pp_oks_table& tab, const T* hm, float* locs, float* vals, int32_t* argmax,
-               double* keypoints, unsigned* scratch, float* dbg, cudaStream_t st) {
+               double* keypoints, unsigned* scratch, float* dbg, const MmaDarkArgs& dk, cudaStream_t st) {
   if (!pp_aligned16(hm) || (p.apply_tail && !(p.temperature > 0.0f)) || p.K > kMmaMaxK) return PP_ERR_UNSUPPORTED_SHAPE;
   if (p.H == 64 && p.W == 48) {
-    if (pp_env_int("PP_DECODE_MINB", 4) == 3)   // experiment: 12 warps per SM with up to 168 registers
-      return mma_launch_shape<T, 64, 48, 4, 3>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
-    return mma_launch_shape<T, 64, 48, 4, 4>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
+    if (!kDark && pp_env_int("PP_DECODE_MINB", 4) == 3)   // experiment: 12 warps per SM with up to 168 registers (slower)
+      return mma_launch_shape<T, 64, 48, 4, 3, false>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, dk, st);
+    return mma_launch_shape<T, 64, 48, 4, 4, kDark>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, dk, st);
   }
-  if (p.H == 96 && p.W == 72) return mma_launch_shape<T, 96, 72, 4, 2>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, st);
+  if (p.H == 96 && p.W == 72) return mma_launch_shape<T, 96, 72, 4, 2, kDark>(p, tab, hm, locs, vals, argmax, keypoints, scratch, dbg, dk, st);
   return PP_ERR_UNSUPPORTED_SHAPE;
 }
 
@@ -991,7 +992,7 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   if (warp_fits && want_warp < 0 && pp_env_int("PP_DECODE_MMA", 1) && tab.mma_tables && tab.mma_index &&
       tab.mma_H == p.H && tab.mma_W == p.W && pp_aligned16(tab.mma_tables) && scratch &&
       scratch_bytes >= static_cast<int64_t>(sizeof(unsigned)) * (kMmaScratchHead + N) && N < (1ll << 31)) {
-    int rc = mma_launch<T>(p, tab, hm, locs, vals, argmax, keypoints, static_cast<unsigned*>(scratch), nullptr, st);
+    int rc = mma_launch<T, false>(p, tab, hm, locs, vals, argmax, keypoints, static_cast<unsigned*>(scratch), nullptr, MmaDarkArgs{}, st);
     if (rc == PP_OK) {
       // second, usually empty, launch: the heatmaps the tensor-core kernel could not rank (plateaus, no dynamic range)
       unsigned* words = static_cast<unsigned*>(scratch);
@@ -1061,10 +1062,12 @@ int launch_decode_expected(const pp_decode_params& p, const pp_oks_table& tab, c
   return PP_OK;
 }
 
+thread_local int g_last_dark_kernel = -1;   // 1: CTA-per-heatmap kernel, 5: tensor-core kernel, 0: the other fallbacks
+
 template <typename T>
-int launch_decode_dark(const pp_decode_params& p, const float* taps, int ksize, const void* heatmaps, float* peaks,
-                       float* scores, float* refined, double* keypoints, void* scratch, int64_t scratch_bytes,
-                       cudaStream_t st) {
+int launch_decode_dark(const pp_decode_params& p, const float* taps, int ksize, const void* blur_mma_table,
+                       const void* heatmaps, float* peaks, float* scores, float* refined, double* keypoints, void* scratch,
+                       int64_t scratch_bytes, cudaStream_t st) {
   const int64_t N = static_cast<int64_t>(p.B) * p.K;
   const int r = ksize / 2;
   {
@@ -1074,16 +1077,40 @@ int launch_decode_dark(const pp_decode_params& p, const float* taps, int ksize, 
       int fper = 1;
       if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(decode_dark_fast_kernel<T>), kFThreads, fsmem, &fper))
         return rc;
+      // tensor-core kernel (pp_decode_mma.cuh, kDark): needs the blur's operand table for this shape, scratch for the
+      // hand-over list and the kernel below for the heatmaps on that list.  PP_DARK_MMA=0 disables it.
+      if (blur_mma_table && pp_aligned16(blur_mma_table) && ksize <= 16 && pp_env_int("PP_DARK_MMA", 1) && scratch &&
+          scratch_bytes >= static_cast<int64_t>(sizeof(unsigned)) * (kMmaScratchHead + N) && N < (1ll << 31)) {
+        pp_oks_table tab{};
+        tab.mma_tables = blur_mma_table;
+        MmaDarkArgs dk{taps, ksize, peaks};
+        const int rc = mma_launch<T, true>(p, tab, static_cast<const T*>(heatmaps), refined, scores, nullptr, keypoints,
+                                           static_cast<unsigned*>(scratch), nullptr, dk, st);
+        if (rc == PP_OK) {
+          unsigned* words = static_cast<unsigned*>(scratch);
+          const int cap = pp_env_int("PP_DECODE_RETRY_GRID", 0);
+          const int rgrid = static_cast<int>(std::min<int64_t>(N, cap > 0 ? cap : pp_sm_count()));
+          g_last_dark_kernel = 5;
+          decode_dark_fast_kernel<T><<<rgrid, kFThreads, fsmem, st>>>(p, taps, ksize, static_cast<const T*>(heatmaps), peaks, scores,
+                                                                    refined, keypoints, geo, words + 1,
+                                                                    reinterpret_cast<const int*>(words + kMmaScratchHead), words + 2);
+          PP_CUDA_OK(cudaGetLastError());
+          return PP_OK;
+        }
+        if (rc != PP_ERR_UNSUPPORTED_SHAPE) return rc;
+      }
       int fgrid = static_cast<int>(std::min<int64_t>(N, static_cast<int64_t>(pp_sm_count()) * fper));
       if (const int cap = pp_env_int("PP_DARK_GRID", 0); cap > 0) fgrid = std::min(fgrid, cap);   // test hook: many heatmaps per CTA
       unsigned* counter = (scratch && scratch_bytes >= 4 && N < (1ll << 31)) ? static_cast<unsigned*>(scratch) : nullptr;
       if (counter) PP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+      g_last_dark_kernel = 1;
       decode_dark_fast_kernel<T><<<fgrid, kFThreads, fsmem, st>>>(p, taps, ksize, static_cast<const T*>(heatmaps), peaks,
-                                                                scores, refined, keypoints, geo, counter);
+                                                                scores, refined, keypoints, geo, counter, nullptr, nullptr);
       PP_CUDA_OK(cudaGetLastError());
       return PP_OK;
     }
   }
+  g_last_dark_kernel = 0;
   const PlaneGeom g = plane_geom(p.H, p.W, r == 5 ? 2 * r + kTile : 0);
   const size_t smem = sizeof(float) * (static_cast<size_t>(g.raw_floats) + g.tmp_floats + g.out_floats);
   if (smem + 4096 > static_cast<size_t>(pp_smem_optin())) {   // too large for shared memory: global-memory path
@@ -1152,8 +1179,8 @@ int pp_oks_mma_table_build(const float* taps_f32, const int32_t* radius, int32_t
              "pp_oks_mma_table_build: no tensor-core decoder for %dx%d maps", H, W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = std::min(U * 8, 1024);
-  if (H == 64) build_mma_tables_kernel<64, 48><<<grid, 256, 0, st>>>(taps_f32, radius, U, static_cast<__half*>(out));
-  else build_mma_tables_kernel<96, 72><<<grid, 256, 0, st>>>(taps_f32, radius, U, static_cast<__half*>(out));
+  if (H == 64) build_mma_tables_kernel<64, 48><<<grid, 256, 0, st>>>(taps_f32, radius, U, static_cast<__half*>(out), PP_OKS_TAPS, 0, false);
+  else build_mma_tables_kernel<96, 72><<<grid, 256, 0, st>>>(taps_f32, radius, U, static_cast<__half*>(out), PP_OKS_TAPS, 0, false);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }
@@ -1187,10 +1214,10 @@ __attribute__((visibility("default"))) int pp_debug_decode_mma_prefilter(const p
              PP_ERR_INVALID_ARG, "pp_debug_decode_mma_prefilter: null argument / scratch too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->heatmap_dtype == PP_F32)
-    return mma_launch<float>(*p, *table, static_cast<const float*>(heatmaps), locs, vals, argmax, nullptr,
-                             static_cast<unsigned*>(scratch), prefilter, st);
-  return mma_launch<__nv_bfloat16>(*p, *table, static_cast<const __nv_bfloat16*>(heatmaps), locs, vals, argmax, nullptr,
-                                   static_cast<unsigned*>(scratch), prefilter, st);
+    return mma_launch<float, false>(*p, *table, static_cast<const float*>(heatmaps), locs, vals, argmax, nullptr,
+                                    static_cast<unsigned*>(scratch), prefilter, MmaDarkArgs{}, st);
+  return mma_launch<__nv_bfloat16, false>(*p, *table, static_cast<const __nv_bfloat16*>(heatmaps), locs, vals, argmax, nullptr,
+                                          static_cast<unsigned*>(scratch), prefilter, MmaDarkArgs{}, st);
 }
 
 int64_t pp_decode_expected_workspace_floats(const pp_decode_params* p) {
@@ -1223,8 +1250,22 @@ int pp_heatmap_maximum(const void* heatmaps, int32_t heatmap_dtype, int64_t N, i
   return PP_OK;
 }
 
-int pp_decode_argmax_dark(const pp_decode_params* p, const float* blur_taps, int32_t blur_ksize, const void* heatmaps,
-                          float* peaks, float* scores, float* refined, double* keypoints, void* scratch,
+int pp_blur_mma_table_build(const float* blur_taps, int32_t blur_ksize, int32_t H, int32_t W, void* out, pp_stream_t stream) {
+  PP_REQUIRE(blur_taps && out && blur_ksize % 2 == 1 && blur_ksize >= 3 && blur_ksize <= 16, PP_ERR_INVALID_ARG,
+             "pp_blur_mma_table_build: bad argument (odd kernel size in [3, 15])");
+  PP_REQUIRE(pp_oks_mma_table_bytes(1, H, W) > 0, PP_ERR_UNSUPPORTED_SHAPE,
+             "pp_blur_mma_table_build: no tensor-core decoder for %dx%d maps", H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (H == 64) build_mma_tables_kernel<64, 48><<<8, 256, 0, st>>>(blur_taps, nullptr, 1, static_cast<__half*>(out), blur_ksize, blur_ksize / 2, true);
+  else build_mma_tables_kernel<96, 72><<<8, 256, 0, st>>>(blur_taps, nullptr, 1, static_cast<__half*>(out), blur_ksize, blur_ksize / 2, true);
+  PP_CUDA_OK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_decode_argmax_dark_last_kernel(void) { return g_last_dark_kernel; }
+
+int pp_decode_argmax_dark(const pp_decode_params* p, const float* blur_taps, int32_t blur_ksize, const void* blur_mma_table,
+                          const void* heatmaps, float* peaks, float* scores, float* refined, double* keypoints, void* scratch,
                           int64_t scratch_bytes, pp_stream_t stream) {
   if (int rc = check_decode_params("pp_decode_argmax_dark", p)) return rc;
   PP_REQUIRE(blur_ksize % 2 == 1 && blur_ksize >= 3 && blur_ksize <= PP_MAX_BLUR_KSIZE, PP_ERR_INVALID_ARG,
@@ -1233,8 +1274,8 @@ int pp_decode_argmax_dark(const pp_decode_params* p, const float* blur_taps, int
   PP_REQUIRE(blur_taps && heatmaps && scores && refined, PP_ERR_INVALID_ARG, "pp_decode_argmax_dark: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->heatmap_dtype == PP_F32)
-    return launch_decode_dark<float>(*p, blur_taps, blur_ksize, heatmaps, peaks, scores, refined, keypoints, scratch, scratch_bytes, st);
-  return launch_decode_dark<__nv_bfloat16>(*p, blur_taps, blur_ksize, heatmaps, peaks, scores, refined, keypoints, scratch, scratch_bytes, st);
+    return launch_decode_dark<float>(*p, blur_taps, blur_ksize, blur_mma_table, heatmaps, peaks, scores, refined, keypoints, scratch, scratch_bytes, st);
+  return launch_decode_dark<__nv_bfloat16>(*p, blur_taps, blur_ksize, blur_mma_table, heatmaps, peaks, scores, refined, keypoints, scratch, scratch_bytes, st);
 }
 
 int pp_heatmap_tail(const void* x, void* y, int32_t dtype, int64_t numel, float temperature, pp_stream_t stream) {

@@ -52,8 +52,11 @@ struct MmaShape {
 };
 
 // ---- operand tables (built once per codec and shape by pp_oks_mma_table_build) ----
-__device__ __forceinline__ float folded_tap(const float* __restrict__ g, int r, int n, int o, int i) {
-  float s = 0.0f;   // entry [o][i] of the reflect-folded Toeplitz matrix of taps g (radius r) on an axis of length n
+__device__ __forceinline__ float folded_tap(const float* __restrict__ g, int r, int n, int o, int i, bool zero_pad) {
+  // entry [o][i] of the Toeplitz matrix of taps g (radius r) on an axis of length n: taps that reach beyond the axis are
+  // folded back by the 'reflect' boundary (scipy.ndimage, heatmap.py:361-362) or dropped (zero padding, codec.py:303-310)
+  if (zero_pad) return (i - o >= -r && i - o <= r) ? g[i - o + r] : 0.0f;
+  float s = 0.0f;
   for (int j = 0; j <= 2 * r; ++j)
     if (reflect1(o + j - r, n) == i) s += g[j];
   return s;
@@ -61,15 +64,16 @@ __device__ __forceinline__ float folded_tap(const float* __restrict__ g, int r, 
 
 template <int H, int W>
 __global__ void __launch_bounds__(256)
-build_mma_tables_kernel(const float* __restrict__ taps, const int* __restrict__ radius, int U, __half* __restrict__ out) {
+build_mma_tables_kernel(const float* __restrict__ taps, const int* __restrict__ radius, int U, __half* __restrict__ out,
+                        int taps_stride, int fixed_radius, bool zero_pad) {
   using S = MmaShape<H, W>;
   constexpr int per = (S::kT1 + S::kT2) * 8;   // halves per channel
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < static_cast<long long>(U) * per;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int u = static_cast<int>(idx / per);
     int e = static_cast<int>(idx - static_cast<long long>(u) * per);
-    const float* g = taps + u * PP_OKS_TAPS;
-    const int r = radius[u];
+    const float* g = taps + u * taps_stride;
+    const int r = radius ? radius[u] : fixed_radius;
     float v = 0.0f;
     if (e < S::kT1 * 8) {
       // A fragment of Tx, tile (mb, kb): reg q -> rows g / g+8 (q & 1), k-columns 2t.. / 2t+8.. (q >> 1)
@@ -77,7 +81,7 @@ build_mma_tables_kernel(const float* __restrict__ taps, const int* __restrict__ 
       const int mb = tile / S::KB, kb = tile - mb * S::KB;
       const int gg = lane >> 2, t = lane & 3;
       const int xo = 16 * mb + gg + 8 * (q & 1), xi = 16 * kb + 2 * t + hh + 8 * (q >> 1);
-      if (xo < W && xi < W) v = folded_tap(g, r, W, xo, xi);
+      if (xo < W && xi < W) v = folded_tap(g, r, W, xo, xi, zero_pad);
     } else {
       // B fragments of Ty^T for the n-blocks (2 nbp, 2 nbp + 1), tile (kb2, nbp): reg q -> n-block (q >> 1),
       // k-rows 2t.. / 2t+8.. (q & 1); element [k = y][n = y'] = Ty[y'][y]
@@ -86,7 +90,7 @@ build_mma_tables_kernel(const float* __restrict__ taps, const int* __restrict__ 
       const int kb2 = tile / S::NBP, nbp = tile - kb2 * S::NBP;
       const int gg = lane >> 2, t = lane & 3;
       const int yi = 16 * kb2 + 2 * t + hh + 8 * (q & 1), yo = 8 * (2 * nbp + (q >> 1)) + gg;
-      v = folded_tap(g, r, H, yo, yi);
+      v = folded_tap(g, r, H, yo, yi, zero_pad);
     }
     out[idx] = __float2half_rn(v);
   }
@@ -197,20 +201,56 @@ __device__ __noinline__ void mma_exact5(const T* __restrict__ plane, const doubl
   for (int q = 0; q < 5; ++q) out[q] = static_cast<float>(warp_sum(a[q]));
 }
 
+// ---- argmax + DARK-UDP decoder on the same skeleton (kDark): zero-padded ksize x ksize blur of single pixels in the
+// operation order of decode_dark_fast_kernel's tile path, which is cv2's separable filter (rows first): float32 fmaf
+// chains over the taps in ascending order.  Two pixels per call: half-warp h evaluates pix[h], its lane dy owns row dy
+// of the window (ksize <= 16); the column chain runs over shuffled row values.  Returns (blur(pixA), blur(pixB)).
+template <typename T>
+__device__ __noinline__ float2 dark_blur2(const T* __restrict__ plane, const float* __restrict__ taps, int ksize, int H, int W,
+                                          int pixA, int pixB, int lane) {
+  const int r = ksize >> 1, dy = lane & 15, pix = (lane & 16) ? pixB : pixA;
+  const int y = pix / W, x = pix - y * W, yy = y + dy - r;
+  float row = 0.0f;
+  if (dy < ksize && yy >= 0 && yy < H) {
+    const T* line = plane + yy * W;
+#pragma unroll 1
+    for (int j = 0; j < ksize; ++j) {
+      const int xx = x + j - r;
+      const float v = (xx >= 0 && xx < W) ? Elem<T>::to_f32(line[xx]) : 0.0f;
+      row = fmaf(taps[j], v, row);
+    }
+  }
+  float acc = 0.0f;
+#pragma unroll 1
+  for (int d = 0; d < ksize; ++d) acc = fmaf(taps[d], __shfl_sync(0xffffffffu, row, (lane & 16) + d), acc);
+  return make_float2(__shfl_sync(0xffffffffu, acc, 0), __shfl_sync(0xffffffffu, acc, 16));
+}
+
+struct MmaDarkArgs {   // what the kDark instance needs besides the expected-OKS kernel's arguments
+  const float* blur_taps;   // (ksize) float32
+  int ksize;
+  float* peaks;             // out (N, 2) or null
+};
+
 constexpr int kMmaMaxK = 256;    // channels whose work-queue order / radius / table index are staged in shared memory
 
-template <typename T, int H, int W, int WPC, int MINB, bool kDebug>
+// kDark: the argmax + DARK-UDP decoder (ArgMaxProbMap.decode, codec.py:515-543) on the same skeleton: the proposal step
+// runs on the zero-padded 11 x 11 Gaussian blur instead of the OKS kernel (one operand table for every channel), its
+// candidates give the blurred maximum (exact float32 re-evaluation), seven more exact values around the raw peak feed
+// the refinement of pp_dark_fast.cuh.  locs = refined coordinates, vals = raw maxima (scores).
+template <typename T, int H, int W, int WPC, int MINB, bool kDebug, bool kDark>
 __global__ void __launch_bounds__(32 * WPC, MINB)
 decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __restrict__ heatmaps,
                            float* __restrict__ locs, float* __restrict__ vals, int32_t* __restrict__ argmax,
                            double* __restrict__ keypoints, MmaGeom geo, unsigned* __restrict__ scratch,
-                           float* __restrict__ dbg_prefilter) {
+                           float* __restrict__ dbg_prefilter, MmaDarkArgs dk) {
   using S = MmaShape<H, W>;
   extern __shared__ __align__(128) unsigned char msm[];
   __shared__ __align__(8) uint64_t bars[WPC];
   __shared__ int ch_hm[kMmaMaxK];                 // channel of queue position q (the table's `order`)
   __shared__ unsigned short ch_tab[kMmaMaxK];     // operand table of channel k
   __shared__ unsigned char ch_rad[kMmaMaxK];      // radius of channel k
+  __shared__ float blur_taps[kDark ? 16 : 1];     // kDark: the blur's 1-D taps
 
   constexpr int V = Elem<T>::kVec;
   constexpr int HW = H * W, NV = HW / V;
@@ -229,10 +269,14 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
   int* retry_list = reinterpret_cast<int*>(scratch + kMmaScratchHead);
 
   // per-channel constants: staged once per CTA, so that nothing on a heatmap's path waits for a dependent global load
-  for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
-    ch_hm[i] = tab.order ? tab.order[i] : i;
-    ch_tab[i] = static_cast<unsigned short>(tab.mma_index[i]);
-    ch_rad[i] = static_cast<unsigned char>(tab.radius[i]);
+  if (kDark) {
+    if (threadIdx.x < 16) blur_taps[kDark ? threadIdx.x : 0] = static_cast<int>(threadIdx.x) < dk.ksize ? dk.blur_taps[threadIdx.x] : 0.0f;
+  } else {
+    for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
+      ch_hm[i] = tab.order ? tab.order[i] : i;
+      ch_tab[i] = static_cast<unsigned short>(tab.mma_index[i]);
+      ch_rad[i] = static_cast<unsigned char>(tab.radius[i]);
+    }
   }
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -251,6 +295,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
   const bool dynamic = geo.static_split == 0 && N > 2 * nwarps;   // nothing to pull when two items per warp cover the batch
   unsigned* work_counter = scratch;
   auto item_to_hm = [&](int j) -> int {
+    if (kDark) return j;   // one operand table for every channel: natural order
     const int slot_k = j / p.B, b = j - slot_k * p.B;
     return b * p.K + ch_hm[slot_k];
   };
@@ -270,11 +315,11 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
                    "r"(geo.plane_bytes)
                    : "memory");
 
-    const int k = hm % p.K;
-    const int r = ch_rad[k];
-    const uint4* t1 = reinterpret_cast<const uint4*>(tab.mma_tables) + static_cast<size_t>(ch_tab[k]) * (S::kT1 + S::kT2);
+    const int k = kDark ? 0 : hm % p.K;
+    const int r = kDark ? dk.ksize >> 1 : ch_rad[k];
+    const uint4* t1 = reinterpret_cast<const uint4*>(tab.mma_tables) + (kDark ? 0 : static_cast<size_t>(ch_tab[k]) * (S::kT1 + S::kT2));
     const uint4* t2 = t1 + S::kT1;
-    const double* w2dk = tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
+    const double* w2dk = kDark ? nullptr : tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
 
     mbar_wait(bar, it & 1);
 
@@ -290,59 +335,63 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
       }
       __syncwarp();
     }
-    // ---- A': min / max: a 128-bit scan of the plane; the B-fragment pairs are loaded (64-bit) and converted after the
-    // scale is known.  (kOnePass: load the pairs once, take min / max from the same registers, convert from registers.)
-    constexpr bool kOnePass = false;   // measured: the 96 live registers spill (68 bytes per thread, reloaded through L2) -- 45.7 us against 44.1 us at C2, 286 us against 259 us at C5
+    // ---- A': min / max: a 128-bit scan of the plane (kDark: and the first vector that holds the lane's maximum); the
+    // B-fragment pairs are loaded (64-bit) and converted after the scale is known.  Measured and rejected: loading the
+    // pairs once and taking min / max from the same registers -- the 96 live registers spill (68 bytes per thread,
+    // reloaded through L2): 45.7 us against 44.1 us at C2, 286 us against 259 us at C5.
     float vmax = -INFINITY, vmin = INFINITY;
-    float2 raw[kOnePass ? S::KB : 1][kOnePass ? S::NB : 1][2];
-    if (kOnePass) {
-#pragma unroll
-      for (int kb = 0; kb < S::KB; ++kb)
-#pragma unroll
-        for (int nbk = 0; nbk < S::NB; ++nbk)
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int x = 16 * kb + 8 * q;              // + 2 t4
-            float2& v = raw[kOnePass ? kb : 0][kOnePass ? nbk : 0][q];
-            if (x + 8 <= W || x + 2 * t4 < W) {         // columns beyond W (W = 8 mod 16) meet zero taps
-              v = plane_pair<T>(plane + (8 * nbk + gg) * W + x + 2 * t4);
-              vmax = fmaxf(vmax, fmaxf(v.x, v.y));
-              vmin = fminf(vmin, fminf(v.x, v.y));
-            } else {
-              v = make_float2(0.0f, 0.0f);
-            }
-          }
-    } else {
+    int ivec = 0;
 #pragma unroll 4
-      for (int i = lane; i < NV; i += 32) {
-        float f[V];
-        unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+    for (int i = lane; i < NV; i += 32) {
+      float f[V];
+      unpack(*reinterpret_cast<const uint4*>(plane + i * V), f, T());
+      float m = fmaxf(f[0], f[1]);
+      vmin = fminf(vmin, fminf(f[0], f[1]));
 #pragma unroll
-        for (int j = 0; j < V; j += 2) {
-          vmax = fmaxf(vmax, fmaxf(f[j], f[j + 1]));
-          vmin = fminf(vmin, fminf(f[j], f[j + 1]));
-        }
+      for (int j = 2; j < V; j += 2) {
+        m = fmaxf(m, fmaxf(f[j], f[j + 1]));
+        vmin = fminf(vmin, fminf(f[j], f[j + 1]));
+      }
+      if (kDark) {
+        if (m > vmax) { vmax = m; ivec = i; }
+      } else {
+        vmax = fmaxf(vmax, m);
       }
     }
+    const float lane_max = vmax;
     vmax = warp_max(vmax);
     vmin = -warp_max(-vmin);
+    int p0 = 0;   // kDark: the raw maximum, lowest flat index (NumPy argmax, heatmap.py:35-41)
+    if (kDark) {
+      int idx = 0x7fffffff;
+      if (lane_max == vmax) {
+        float f[V];
+        unpack(*reinterpret_cast<const uint4*>(plane + ivec * V), f, T());
+#pragma unroll
+        for (int j = V - 1; j >= 0; --j) idx = (f[j] == vmax) ? ivec * V + j : idx;
+      }
+      p0 = __reduce_min_sync(0xffffffffu, idx);
+    }
 
     int best = 0;
     float best_val = 0.0f, score = vmax;
     float nb[4] = {0.f, 0.f, 0.f, 0.f};
     bool interior = false, handed_over = false;
 
-    if (vmax != vmin) {   // constant maps (e.g. all zero after the clamp): first index wins, border pixel
-      // ---- B: scale.  range 2^k in [0.5, 1); maps without float32 dynamic range go to the general kernel
-      const float range = vmax - vmin;
-      const int ebits = static_cast<int>((__float_as_uint(range) >> 23) & 0xffu);
+    float dark_x = -1.0f, dark_y = -1.0f;   // kDark: refined coordinates; empty channels (max <= 0) keep the -1 sentinel
+    if (kDark ? vmax > 0.0f : vmax != vmin) {   // constant maps (e.g. all zero after the clamp): first index wins, border pixel
+      // ---- B: scale.  range 2^k in [0.5, 1); maps without float32 dynamic range go to the general kernel.  kDark: the
+      // zero-padded blur does not commute with an offset (the tap mass inside the map varies along the border), so the
+      // map is only scaled, by its largest magnitude
       const float amax = fmaxf(fabsf(vmax), fabsf(vmin));
+      const float range = kDark ? amax : vmax - vmin;
+      const int ebits = static_cast<int>((__float_as_uint(range) >> 23) & 0xffu);
       const float sc = __uint_as_float(static_cast<unsigned>(253 - ebits) << 23);
       // candidate band in scaled units: twice the proposal error + the float32 rounding of the two exact values
       const float band = 2.0f * kMmaErr + 4.0f * 5.9604645e-8f * amax * sc;
       handed_over = ebits < 30 || ebits > 250 || !(band < 0.25f);
       if (!handed_over) {
-        const float off = -vmin * sc;
+        const float off = kDark ? 0.0f : -vmin * sc;
         const wf2 sc2 = wf2_make(sc, sc), off2 = wf2_make(off, off);
         // ---- C: the whole map as float16 B-fragments of H^T: hf[kb][nb] = rows 8 nb + g, columns 16 kb + 2 t (+ 8)
         uint32_t hf[S::KB][S::NB][2];
@@ -354,7 +403,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
             for (int q = 0; q < 2; ++q) {
               const int x = 16 * kb + 8 * q;              // + 2 t4
               if (x + 8 <= W || x + 2 * t4 < W) {         // columns beyond W (W = 8 mod 16) meet zero taps; keep them finite
-                const float2 v = kOnePass ? raw[kOnePass ? kb : 0][kOnePass ? nbk : 0][q] : plane_pair<T>(plane + (8 * nbk + gg) * W + x + 2 * t4);
+                const float2 v = plane_pair<T>(plane + (8 * nbk + gg) * W + x + 2 * t4);
                 float lo, hi;   // (v.x, v.y) * sc + off as one two-wide FFMA2
                 wf2_split(wf2_fma(wf2_make(v.x, v.y), sc2, off2), lo, hi);
                 hf[kb][nbk][q] = pack_h2(lo, hi);
@@ -472,7 +521,32 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
         __syncwarp();
         const int count = cand[kWCand];
         handed_over = count > kWCand;
-        if (!handed_over) {
+        if (kDark && !handed_over) {
+          // ---- G (kDark): the blurred maximum = the largest exact blur among the candidates; the blur at the raw peak
+          // and its six DARK neighbours, edge-clamped (codec.py:346-359).  Pixel list: candidates, then the stencil.
+          const int py = fast_div(p0, geo.div_W), px = p0 - py * W;
+          if (lane < 7) {
+            const int dxs = (0x2424 >> (2 * lane)) & 3, dys = (0x2640 >> (2 * lane)) & 3;   // 0, +1, -1 (as 2) per stencil point
+            const int yy = min(max(py + (dys == 2 ? -1 : dys), 0), H - 1), xx = min(max(px + (dxs == 2 ? -1 : dxs), 0), W - 1);
+            cand[kWCand + 4 + lane] = yy * W + xx;   // the stencil pixels live behind the candidate list
+          }
+          __syncwarp();
+          float bmax = -INFINITY, sten = 0.0f;   // lane q < 7 keeps stencil value q
+          const int n_pix = count + 7;
+          auto pixel = [&](int q) { return q < count ? cand[q] : cand[kWCand + 4 + min(q - count, 6)]; };
+          for (int q = 0; q < n_pix; q += 2) {
+            const float2 v = dark_blur2<T>(plane, blur_taps, dk.ksize, H, W, pixel(q), pixel(q + 1), lane);
+            if (q < count) bmax = fmaxf(bmax, v.x); else if (lane == q - count) sten = v.x;
+            if (q + 1 < count) bmax = fmaxf(bmax, v.y); else if (q + 1 < n_pix && lane == q + 1 - count) sten = v.y;
+          }
+          const float ratio = __fdiv_rn(vmax, __fadd_rn(bmax, 1e-12f));   // codec.py:312
+          const float lg = dark_log(sten, ratio);
+          float b[7];
+#pragma unroll
+          for (int q = 0; q < 7; ++q) b[q] = __shfl_sync(0xffffffffu, lg, q);
+          if (lane == 0) dark_shift(b, px, py, dark_x, dark_y);
+        }
+        if (!kDark && !handed_over) {
           // ---- G: exact values of the candidates and of the winner's four neighbours
           if (count == 1) {
             best = cand[0];
@@ -500,6 +574,22 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
     // hand-over to the general kernel
     if (handed_over) {
       if (lane == 0) retry_list[atomicAdd(retry_count, 1u)] = hm;
+    } else if (kDark) {
+      if (lane == 0) {
+        const bool empty = !(vmax > 0.0f);   // locs[vals <= 0] = -1 (heatmap.py:46): the sentinel is kept
+        const int py = fast_div(p0, geo.div_W), px = p0 - py * W;
+        if (dk.peaks) {
+          dk.peaks[static_cast<size_t>(hm) * 2] = empty ? -1.0f : static_cast<float>(px);
+          dk.peaks[static_cast<size_t>(hm) * 2 + 1] = empty ? -1.0f : static_cast<float>(py);
+        }
+        vals[hm] = vmax;
+        locs[static_cast<size_t>(hm) * 2] = dark_x;
+        locs[static_cast<size_t>(hm) * 2 + 1] = dark_y;
+        if (keypoints) {   // codec.py:541
+          keypoints[static_cast<size_t>(hm) * 2] = static_cast<double>(dark_x) / static_cast<double>(W - 1) * p.input_w;
+          keypoints[static_cast<size_t>(hm) * 2 + 1] = static_cast<double>(dark_y) / static_cast<double>(H - 1) * p.input_h;
+        }
+      }
     } else if (lane < 2) {
       const int by = fast_div(best, geo.div_W), bx = best - by * W;
       const bool is_y = lane == 1;

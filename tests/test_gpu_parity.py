@@ -285,6 +285,17 @@ def test_decoder_fused_head_tail(pp, expected_kernel):
 
 
 # --------------------------------------------------------------------------- DARK decoder
+@pytest.fixture(params=["mma", "mma-grid2", "cta"])
+def dark_kernel(request, monkeypatch):
+    """Which kernel runs the argmax + DARK-UDP decode: the tensor-core kernel (pp_decode_mma.cuh, kDark; default for the
+    64x48 / 96x72 shapes; "-grid2": two CTAs, many heatmaps per warp) or the CTA-per-heatmap kernel (pp_dark_fast.cuh)."""
+    if request.param == "cta":
+        monkeypatch.setenv("PP_DARK_MMA", "0")
+    elif request.param.endswith("grid2"):
+        monkeypatch.setenv("PP_DECODE_GRID", "2")
+    return request.param
+
+
 def _dark_tolerance(hm, peaks, wl, base_rtol):
     """Per-keypoint tolerance (input px).  cv2 / numpy float32 blurs agree to ~2e-7 relative and the
     float32 log to ~1 ulp; DARK multiplies that by the inverse Hessian of the log-map at the peak."""
@@ -315,12 +326,14 @@ def _dark_tolerance(hm, peaks, wl, base_rtol):
 
 
 @pytest.mark.parametrize("name", ["clean", "blob"])
-def test_dark_decoder_matches_golden_reference(pp, golden_dir, name):
+def test_dark_decoder_matches_golden_reference(pp, golden_dir, name, dark_kernel):
+    from probpose_pytorch_b200 import _lib
     g = np.load(golden_dir / "decode.npz")
     wl = synth.WORKLOADS[3]
     arr = g[name]
     am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
     dev = am.decode_device(torch.from_numpy(arr).cuda())
+    assert _lib.lib().pp_decode_argmax_dark_last_kernel() == (1 if dark_kernel == "cta" else 5)
     assert np.array_equal(dev["peaks"].cpu().numpy(), g[f"{name}_peaks"])           # argmax bit-exact
     assert np.array_equal(dev["scores"].cpu().numpy(), g[f"{name}_dark_scores"])
     got = dev["keypoints"].cpu().numpy()
@@ -351,7 +364,7 @@ def test_dark_decoder_matches_golden_reference(pp, golden_dir, name):
 
 
 @pytest.mark.parametrize("cid,batch", [(4, 2), (5, 1)])
-def test_dark_decoder_vs_oracle_other_shapes(pp, cid, batch):
+def test_dark_decoder_vs_oracle_other_shapes(pp, cid, batch, dark_kernel):
     wl = synth.WORKLOADS[cid]
     kps, vis, _ = synth.make_keypoints(wl, batch=batch, seed=300 + cid)
     inside = (kps[..., 0] >= 8) & (kps[..., 0] < wl.input_size[0] - 8) & (kps[..., 1] >= 8) & (kps[..., 1] < wl.input_size[1] - 8)
@@ -637,7 +650,7 @@ def test_head_tail_autograd_and_patch(pp):
     assert m.conv_layers.weight.grad is not None
 
 
-def test_pose_targets_from_heatmaps(pp, golden_dir):
+def test_pose_targets_from_heatmaps(pp, golden_dir, dark_kernel):
     """Device-side ProbPoseLoss._oks_from_heatmaps / _error_from_heatmaps against the reference's outputs."""
     from probpose_pytorch_b200.pose_targets import error_from_heatmaps, oks_from_heatmaps
     g = np.load(golden_dir / "decode.npz")
@@ -1574,3 +1587,50 @@ def test_expected_decoder_maximum_in_a_short_last_band(pp, golden_dir, expected_
             assert int(dev["argmax"][b, k]) == int(conv.reshape(-1).argmax()), (int(k), b)
             np.testing.assert_allclose(dev["locs"][b, k].cpu().numpy(), l[0], rtol=RTOL32, atol=1e-5)
             assert float(dev["vals"][b, k]) == float(v[0])
+
+
+@pytest.mark.parametrize("cid,dtype", [(2, "fp32"), (2, "bf16"), (4, "fp32"), (5, "fp32")])
+def test_dark_decoder_full_size_tensor_core_vs_cta_kernel_and_oracle(pp, cid, dtype, monkeypatch):
+    """The argmax + DARK-UDP decoder at BASELINE batch sizes through the tensor-core kernel: peaks / scores bit-equal to
+    the CTA-per-heatmap kernel on every heatmap, refined coordinates equal to it up to the float32 blur's operation
+    order (the two kernels evaluate the 11 x 11 blur rows-first / columns-first on flat maps), and a 512-heatmap sample
+    of blob-shaped channels against the oracle (cv2) with the conditioning-aware bound of the golden tests."""
+    wl = synth.WORKLOADS[cid]
+    B, K = wl.batch, wl.num_keypoints
+    W, H = wl.heatmap_size
+    kps, vis, _ = synth.make_keypoints(wl, batch=B, seed=1000 + cid)
+    am = pp.ArgMaxProbMap(wl.input_size, wl.heatmap_size, wl.sigmas)
+    blob = am.encode_batch(synth.jitter_keypoints(wl, kps, seed=5000), vis)["heatmaps"]
+    amp = torch.from_numpy(synth.blob_params((B, K), seed=6000)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    pred = (blob * amp[:, :, None, None]).add_(torch.rand(blob.shape, device="cuda", generator=g) * 0.02).clamp_(0, 1)
+    del blob
+    if dtype == "bf16":
+        pred = pred.bfloat16()
+    from probpose_pytorch_b200 import _lib
+    a = am.decode_device(pred)
+    assert _lib.lib().pp_decode_argmax_dark_last_kernel() == 5
+    handed = int(a["_scratch"][2])
+    monkeypatch.setenv("PP_DARK_MMA", "0")
+    b = am.decode_device(pred)
+    assert _lib.lib().pp_decode_argmax_dark_last_kernel() == 1
+    assert torch.equal(a["peaks"], b["peaks"]) and torch.equal(a["scores"], b["scores"])
+    diff = (a["keypoints"] - b["keypoints"]).abs().reshape(B * K, 2).max(dim=1).values
+    strong = (pred.reshape(B * K, -1).float().max(dim=1).values >= 0.1)
+    # input px.  Blobs on a clean floor take the same row-then-column arithmetic in both kernels; a noise floor makes
+    # the CTA kernel blur columns first (its full-plane path), and DARK's inverse Hessian amplifies the 1e-7 difference
+    assert float(diff[strong].max()) <= 0.1, float(diff[strong].max())
+    assert float((diff[strong] <= 1e-3).float().mean()) >= 0.98
+    assert handed <= B * K // 100, f"{handed} heatmaps handed on"
+    # oracle on a sample of blob-shaped heatmaps (whole samples: the oracle decodes (K, H, W) stacks)
+    rng = np.random.default_rng(cid)
+    for bi in rng.choice(B, size=max(1, 512 // K), replace=False):
+        hm = pred[bi].float().cpu().numpy()
+        kp, sc = oc.decode_argmax_dark(hm, wl.input_size, wl.heatmap_size, backend="cv2")
+        peaks, _ = oc.heatmap_maximum(hm)
+        assert np.array_equal(a["peaks"][bi].cpu().numpy(), peaks) and np.array_equal(a["scores"][bi].cpu().numpy(), sc[0])
+        ok = (peaks[:, 0] >= 0) & (hm.reshape(K, -1).max(axis=1) >= 0.1)
+        bound = RTOL32 * np.maximum(np.abs(kp[0]), 1.0) + _dark_tolerance(hm, peaks, wl, RTOL32)
+        if dtype == "bf16":
+            bound = bound + RTOL16
+        assert (np.abs(a["keypoints"][bi].cpu().numpy() - kp[0])[ok] <= bound[ok]).all()
