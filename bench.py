@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--exchange-every", type=int, default=0,
                     help="multi-GPU, --exchange nccl: steps per all-gather bucket (0 = number of buffer sets)")
     ap.add_argument("--serial", action="store_true", help="run decode after encode on one stream (no fork/join)")
+    ap.add_argument("--consumer", choices=["branch", "side"], default="branch",
+                    help="multi-GPU mailbox consumer inside the step graph: a branch of its own, or behind the record packing")
     ap.add_argument("--exchange", choices=["mailbox", "nccl"], default="mailbox",
                     help="multi-GPU record + loss exchange: stores into every rank's mailbox over NVLink peer memory from the "
                          "record-packing kernel (default), or bucketed NCCL all-gathers")
@@ -270,6 +272,7 @@ class Bench:
             self.sets.append(dict(kps=kps_d, vis=vis_d, pred=pred, heads=heads, kps_np=kps, vis_np=vis))
         self.set_bytes = 3 * self.n_hm * self.hm_bytes
         self.side = torch.cuda.Stream(device=dev)
+        self.cons = torch.cuda.Stream(device=dev)
         self._sync_token = torch.zeros(1, device=dev)
         self.mailbox, self.exchange_note = None, ""
         torch.cuda.synchronize()
@@ -287,6 +290,15 @@ class Bench:
             with torch.cuda.stream(self.side):
                 dec = self.pm.decode_device(s["pred"])
                 rec = self.codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
+                if mailbox is not None and args.consumer == "side":
+                    mailbox.read_async((slot - 2) % mailbox.slots)
+            if mailbox is not None and args.consumer == "branch":
+                # the consumer side, a third branch of the same graph: wait for what ALL ranks published two steps ago,
+                # copy the gathered records + losses into this rank's private buffer, acknowledge (flow control).  Two
+                # steps of slack: the wait is normally over before it starts, and no rank runs more than two steps ahead.
+                self.cons.wait_stream(cur)
+                with torch.cuda.stream(self.cons):
+                    mailbox.read_async((slot - 2) % mailbox.slots)
         out = s["pred"].detach().requires_grad_(True)
         tgt = None
         pub = mailbox.descriptor(slot) if mailbox is not None else None   # the loss' finalize kernel publishes it
@@ -301,27 +313,31 @@ class Bench:
         loss.backward()
         if not args.serial:
             cur.wait_stream(self.side)
+            if mailbox is not None and args.consumer == "branch":
+                cur.wait_stream(self.cons)
         if rec is None:
             rec = self.codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
+            if mailbox is not None:
+                mailbox.read_async((slot - 2) % mailbox.slots)
         if mailbox is not None:
             mailbox.loss_enqueued(slot)
         return dict(rec=rec, loss=loss.detach(), grad=out.grad, dec=dec, tgt=tgt)
 
-    def _graphs(self, fn, mailbox=None):
+    def _graphs(self, fn, n_graphs):
+        """Warm up and capture one CUDA graph per step phase: phase g works on buffer set g % sets and mailbox slot g.
+        The phases are visited cyclically, always: the in-graph consumer of phase g acknowledges phase g - 2."""
         torch = self.torch
-        for j, s in enumerate(self.sets):
-            for _ in range(2):
-                fn(s, j)
-                if mailbox is not None:
-                    mailbox.skip(j)       # flow control: every publication is consumed before its slot comes round again
+        for _ in range(2):
+            for g in range(n_graphs):
+                fn(self.sets[g % len(self.sets)], g)
         torch.cuda.synchronize()
         graphs, results = [], []
         if not self.ctx["args"].no_graph:
-            for j, s in enumerate(self.sets):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    results.append(fn(s, j))
-                graphs.append(g)
+            for g in range(n_graphs):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    results.append(fn(self.sets[g % len(self.sets)], g))
+                graphs.append(gr)
             torch.cuda.synchronize()
         return graphs, results
 
@@ -333,43 +349,33 @@ class Bench:
         args, world, dev = ctx["args"], ctx["world"], ctx["dev"]
         mailbox = None
         note = ""
+        n_phases = len(self.sets)
         if world > 1 and exchange and args.exchange == "mailbox":
             try:
                 if self.mailbox is None:
-                    self.mailbox = ppd.PeerMailbox(self.B, self.K, len(self.sets), dev)
+                    self.mailbox = ppd.PeerMailbox(self.B, self.K, max(4, len(self.sets)), dev)
                 mailbox = self.mailbox
-                note = f"records + loss stored into every rank's mailbox over NVLink by pp_pack_records ({len(self.sets)} slots)"
+                n_phases = mailbox.slots
+                note = (f"records + loss stored into every rank's mailbox over NVLink by pp_pack_records and the loss' finalize "
+                        f"kernel ({mailbox.slots} slots, flow control); every rank consumes (waits for, copies, acknowledges) every "
+                        "step's slot two steps later, inside the step's CUDA graph")
             except Exception as e:   # symmetric memory unavailable on this box: the NCCL path still measures the step
                 note = f"NCCL (symmetric memory unavailable: {type(e).__name__}: {str(e)[:80]})"
-        graphs, results = self._graphs(lambda s, j: self.step(s, j, fused=fused, mailbox=mailbox), mailbox)
+        graphs, results = self._graphs(lambda s, g: self.step(s, g, fused=fused, mailbox=mailbox), n_phases)
         use_graph = bool(graphs)
-        cons = torch.cuda.Stream(device=dev) if mailbox is not None else None
         pending, bucket = collections.deque(), []
         every = max(1, min(args.exchange_every or len(self.sets), len(self.sets)))
-        consumed = {"reads": 0}
         nccl = world > 1 and exchange and mailbox is None
 
         def run_step(i):
-            j = i % len(self.sets)
+            g = i % n_phases
             if use_graph:
-                graphs[j].replay()
-                res = results[j]
+                graphs[g].replay()
+                res = results[g]
                 if mailbox is not None:
-                    mailbox.published(j)      # the replayed graph published slot j again
+                    mailbox.published(g)      # the replayed graph published slot g again
             else:
-                res = self.step(self.sets[j], j, fused=fused, mailbox=mailbox)
-            if mailbox is not None:
-                # the consumer side, inside the timed region, on its own stream behind this step: every rank waits for
-                # what ALL ranks published into the step's slot and acknowledges it (flow control: a slot is not
-                # rewritten before everybody is done with it); once per cycle of slots the blocks are also copied out
-                # (what a logger / evaluator does).  No host synchronisation.
-                cons.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(cons):
-                    if j == len(self.sets) - 1:
-                        mailbox.read_async(j)
-                        consumed["reads"] += 1
-                    else:
-                        mailbox.skip(j)
+                res = self.step(self.sets[g % len(self.sets)], g, fused=fused, mailbox=mailbox)
             if nccl:
                 bucket.append((res["rec"], res["loss"]))
                 if len(bucket) == every:
@@ -385,12 +391,11 @@ class Bench:
                 bucket.clear()
             while pending:
                 pending.popleft().wait()
-            if cons is not None:
-                torch.cuda.current_stream(dev).wait_stream(cons)
 
         sampler = ctx["sampler"]
         sampler.mark = "warm"
-        for i in range(max(warmup, 3)):
+        n_warm = -(-max(warmup, 3) // n_phases) * n_phases     # whole cycles of phases: the timed loop starts at phase 0
+        for i in range(n_warm):
             run_step(i)
         drain()
         torch.cuda.synchronize()
@@ -418,12 +423,21 @@ class Bench:
         ms = ev0.elapsed_time(ev1)
         checked = None
         if mailbox is not None:
-            mailbox.check_async()    # raises if a consumer wait timed out / a producer waited in vain for an acknowledgement
+            # finish the cycle of phases (the next user of this mailbox starts at phase 0 again), then consume the two
+            # publications nobody has acknowledged yet; check_async raises if a consumer wait timed out or a producer
+            # waited in vain for an acknowledgement
+            for i in range(steps, -(-steps // n_phases) * n_phases):
+                run_step(i)
+            total = -(-steps // n_phases) * n_phases
+            outs = {}
+            for i in (total - 2, total - 1):
+                outs[i % n_phases] = mailbox.read_async(i % n_phases)
+            mailbox.check_async()
             # what arrived in this rank's mailbox for the last step must be what an all-gather of the ranks' results gives
-            j = (steps - 1) % len(self.sets)
-            got_rec, got_loss = mailbox.peek(j)
-            last = results[j] if use_graph else res
-            want = ppd.exchange_step_results(last["rec"], last["loss"].to(torch.float64))
+            g_last = (total - 1) % n_phases
+            got_rec, got_loss = outs[g_last]
+            last_res = results[g_last] if use_graph else res
+            want = ppd.exchange_step_results(last_res["rec"], last_res["loss"].to(torch.float64))
             checked = bool(torch.equal(got_rec.view(want.records.shape), want.records)
                            and torch.allclose(got_loss.mean(), want.loss.double(), rtol=1e-6, atol=0))
             if not checked:
@@ -432,8 +446,9 @@ class Bench:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
-        last = (results[(steps - 1) % len(self.sets)] if use_graph else res)
-        info = {"exchange": (note + f"; consumer reads inside the timed region: {consumed['reads']}; last step checked against an "
+        last = (results[(steps - 1) % n_phases] if use_graph else res)
+        last = dict(last, _set=((steps - 1) % n_phases) % len(self.sets))
+        info = {"exchange": (note + f"; consumed steps inside the timed region: {max(0, steps - 2)}; last step checked against an "
                              f"all-gather: {checked}") if mailbox is not None else
                 (f"records + loss of {every} step(s) per asynchronous NCCL all-gather" + (f" [{note}]" if note else "")) if nccl else "",
                 "launch": ("CUDA graph replay" if use_graph else "eager")
@@ -512,6 +527,7 @@ class Bench:
         peak, peak_src = hbm_peak()
         ms, last, info = self.time_step(steps, warmup, fused=False, mark=mark)
         ms_f, last_f, _ = self.time_step(steps, warmup, fused=True, mark=mark + "_fused")
+        ms_nox = self.time_step(steps, warmup, fused=False, exchange=False, mark="other")[0] if world > 1 else None
         kernels = self.kernel_times(max(20, min(200, steps)), extra=extra_kernels)
         n_job = world * self.n_hm
         per_step = ms / steps
@@ -532,6 +548,7 @@ class Bench:
             "l2": f"rotating {self.nsets} buffer sets x {self.set_bytes / 1e6:.0f} MB (> 126 MB L2)",
             "steps": steps, "ms_per_step": per_step, "value": n_job * steps / (ms * 1e-3), "unit": UNIT,
             "launch": info["launch"], "exchange": info["exchange"],
+            "ms_per_step_without_exchange": (ms_nox / steps) if ms_nox is not None else None,
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_planes"] * self.n_hm * self.hm_bytes,
@@ -712,7 +729,6 @@ def run_product(args):
     rec, last, last_f = head.record(args.steps, args.warmup, extra_kernels=True, mark="timed")
     parity = None
     if rank == 0:
-        last["_set"] = (args.steps - 1) % len(head.sets)
         parity = parity_check(head, last, last_f)
     sampler.mark = "e2e"
     e2e = run_e2e(head, max(5, min(20, args.steps)))
@@ -728,7 +744,9 @@ def run_product(args):
         sub_steps = max(10, min(args.steps, 100))
         plan = [("C2", 2, synth.WORKLOADS[2].batch, "weak (B = 256 per GPU)"),
                 ("C3", 3, max(1, synth.WORKLOADS[3].batch // world), f"strong (B = 1024 split over {world} GPU(s), loss + records exchanged)"),
-                ("C4", 4, max(1, synth.WORKLOADS[4].batch // world), f"strong (B = 512 split over {world} GPU(s))")]
+                ("C4", 4, max(1, synth.WORKLOADS[4].batch // world), f"strong (B = 512 split over {world} GPU(s))"),
+                ("C3_per_gpu_128", 3, synth.WORKLOADS[3].batch // 8, "weak (B = 128 per GPU, the per-GPU share of C3 as BASELINE "
+                 "quotes it: 128/GPU x 8; loss + records exchanged)")]
         for label, cid, batch, scaling in plan:
             if cid == args.config:
                 continue
@@ -773,8 +791,8 @@ def run_product(args):
 
     if rank == 0:
         # kernels of ours inside the timed region, per step: encode, decode (+ its hand-over launch), loss, loss finalize,
-        # grad-scale check, record packing (+ mailbox commit)
-        launches_per_step = 7 + (1 if world > 1 and args.exchange == "mailbox" else 0)
+        # grad-scale check, record packing (+ the mailbox consumer: wait, acknowledge)
+        launches_per_step = 7 + (2 if world > 1 and args.exchange == "mailbox" else 0)   # + consumer wait, acknowledge
         line = {
             "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -785,6 +803,7 @@ def run_product(args):
                        "batch_per_gpu": rec["batch_per_gpu"], "keypoints": rec["keypoints"], "heatmap": rec["heatmap"],
                        "heatmaps_per_step_per_gpu": rec["heatmaps_per_step_per_gpu"], "l2": rec["l2"], "launch": rec["launch"],
                        "parallelism": f"dp{world} (batch sharded by image)" + (f"; {rec['exchange']}" if rec["exchange"] else "")},
+            "ms_per_step_without_exchange": rec["ms_per_step_without_exchange"],
             "roofline": rec["roofline"], "kernels": rec["kernels"], "fused_step": rec["fused_step"], "e2e": e2e,
             "parity_check": parity, "configs": configs, "cpu_baseline": cpu_baseline,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,

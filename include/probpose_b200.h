@@ -314,8 +314,9 @@ PP_API int pp_pck_accuracy(const float* pred, const float* gt, const uint8_t* ma
 typedef struct pp_mailbox {
   void* const* peer_bufs;   /* device array of `world` pointers: base of every rank's mailbox (own rank included) */
   uint32_t* state;          /* local device memory, pp_mailbox_state_words(slots) words, zero before the first call:
-                               sequence number, arrival counter and finished-block counter of each slot, then a status
-                               word (1 + rank of a consumer whose acknowledgement did not arrive in time) */
+                               sequence number, arrival counter, finished-block counter and consumed sequence number of
+                               each slot, then a status word (1 + rank of a consumer whose acknowledgement did not
+                               arrive in time) */
   int32_t world, rank;
   int32_t slots, slot;      /* the block (slot, rank) of every mailbox is written */
   int64_t block_bytes;      /* pp_mailbox_block_bytes(N) */
@@ -345,6 +346,14 @@ PP_API int pp_mailbox_commit(const pp_mailbox* mailbox, int64_t n_records, const
 /* Consumer side, after the blocks of `mailbox->slot` have been used: tell every producer that this rank is done with
  * sequence number `seq` of the slot (required with flow_control). */
 PP_API int pp_mailbox_ack(const pp_mailbox* mailbox, uint32_t seq, pp_stream_t stream);
+/* The whole consumer side in ONE kernel, with the sequence numbers kept on the device (state words 3 * slots ..): wait
+ * (bounded, *status as for pp_mailbox_wait) for the oldest publication of `mailbox->slot` this rank has not consumed yet,
+ * copy it into compact private buffers -- records_out (world * n_records * 7 doubles, rank order) and losses_out (world
+ * doubles); both may be NULL to skip the copy -- and acknowledge it to every producer.  Returns at once, touching nothing,
+ * when this rank has not published such a step itself.  No host-side values: capturable into the CUDA graph of the step,
+ * e.g. step j publishes slot j % slots and consumes slot (j - 2) % slots. */
+PP_API int pp_mailbox_consume(const pp_mailbox* mailbox, int64_t n_records, double* records_out, double* losses_out,
+                              int64_t timeout_us, int32_t* status, pp_stream_t stream);
 /* Wait until all `world` sources have published sequence number expected_seq into `slot` of this rank's mailbox.
  * *status (device int, zero before the call) becomes 1 + source rank if a source did not arrive within timeout_us and
  * -(1 + source rank) if a source has already published a LATER sequence number (the block was overwritten: only

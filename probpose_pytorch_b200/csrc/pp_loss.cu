@@ -232,7 +232,7 @@ oks_loss_kernel(LossArgs a, bool want_fwd, bool want_grad, int band_h) {
   if (a.range_flag && bad_target) atomicOr(a.range_flag, 1);
 }
 
-// sum of N doubles * scale -> one float; single CTA, fixed order.  With a mailbox (has_mb) the same thread also stores
+// sum of N doubles * scale -> one float; single CTA, fixed order.  With a mailbox (has_mb) the first warp also stores
 // the loss into the step's slot on every rank and arrives at the slot's publication (pp_records.cu): the multi-GPU
 // exchange needs no launch after the loss.
 __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int64_t n, double scale,
@@ -243,12 +243,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {                        // every lane forms the same sum, in the same fixed order
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += red[w];
     const float loss = static_cast<float>(t * scale);
-    out[0] = loss;
-    if (has_mb) pp_mailbox_dev::mailbox_store_loss_and_arrive(mb, mb_records, static_cast<double>(loss));
+    if (threadIdx.x == 0) out[0] = loss;
+    if (has_mb) pp_mailbox_dev::mailbox_store_loss_and_arrive(mb, mb_records, static_cast<double>(loss));   // warp-wide
   }
 }
 

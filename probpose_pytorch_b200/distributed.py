@@ -221,8 +221,9 @@ class PeerMailbox:
         self._state = torch.zeros(int(L.pp_mailbox_state_words(self.slots)), dtype=torch.int32, device=self.device)
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._published = [0] * self.slots       # host copy of the sequence numbers (launch order)
-        self._consumed = [0] * self.slots        # sequence number this rank has acknowledged, per slot
-        self._staging = None                     # private copy of one slot (consumer side)
+        # the consumer's private, compact copies of every slot (allocated up front: read_async may be captured in a graph)
+        self._st_rec = torch.zeros((self.slots, self.world, self.n_records * 7), dtype=torch.float64, device=self.device)
+        self._st_loss = torch.zeros((self.slots, self.world, 1), dtype=torch.float64, device=self.device)
         self._pending_reads: list = []
         self._lib = _lib
 
@@ -261,33 +262,43 @@ class PeerMailbox:
         return rec, loss
 
     def _consume(self, slot: int, timeout_us: int, copy: bool):
-        expected = self._consumed[slot] + 1 if self.flow_control else self._published[slot]
-        assert 0 < expected <= self._published[slot], "nothing (new) published into this slot yet"
         L = self._lib.lib()
-        with torch.cuda.device(self.device):
-            rc = L.pp_mailbox_wait(self._lib.ptr(self.buf), self.world, int(slot), self.n_records, expected & 0xFFFFFFFF,
-                                   int(timeout_us), self._lib.ptr(self._status), self._lib.stream_ptr(self.device))
-        self._lib.check(rc, "pp_mailbox_wait")
+        st = self._lib.stream_ptr(self.device)
         out = None
         if copy:
-            if self._staging is None:
-                self._staging = torch.empty(self.world * self.block_bytes, dtype=torch.uint8, device=self.device)
-            self._staging.copy_(self.buf[slot * self.world * self.block_bytes:(slot + 1) * self.world * self.block_bytes])
-            out = self._views(self._staging)
+            out = (self._st_rec[slot].view((self.world * self.shape[0],) + self.shape[1:]), self._st_loss[slot].view(self.world))
         if self.flow_control:
+            # one kernel (pp_mailbox_consume), sequence numbers on the device: nothing host-side is baked into the launch,
+            # so the consumer side can sit in the same CUDA graph as the step that publishes
             with torch.cuda.device(self.device):
-                rc = L.pp_mailbox_ack(self.descriptor(slot), expected & 0xFFFFFFFF, self._lib.stream_ptr(self.device))
-            self._lib.check(rc, "pp_mailbox_ack")
-        self._consumed[slot] = expected
-        self._pending_reads.append((slot, expected))
+                rc = L.pp_mailbox_consume(self.descriptor(slot), self.n_records,
+                                          self._lib.ptr(self._st_rec[slot]) if copy and self.n_records else None,
+                                          self._lib.ptr(self._st_loss[slot]) if copy else None,
+                                          int(timeout_us), self._lib.ptr(self._status), st)
+            self._lib.check(rc, "pp_mailbox_consume")
+        else:
+            expected = self._published[slot]
+            assert expected > 0, "nothing published into this slot yet"
+            with torch.cuda.device(self.device):
+                rc = L.pp_mailbox_wait(self._lib.ptr(self.buf), self.world, int(slot), self.n_records, expected & 0xFFFFFFFF,
+                                       int(timeout_us), self._lib.ptr(self._status), st)
+            self._lib.check(rc, "pp_mailbox_wait")
+            if copy:
+                bb = self.block_bytes
+                blocks = self.buf[slot * self.world * bb:(slot + 1) * self.world * bb].view(self.world, bb)
+                if self.n_records:
+                    self._st_rec[slot].copy_(blocks[:, :self.n_records * 56].view(torch.float64))
+                self._st_loss[slot].copy_(blocks[:, bb - 16:bb - 8].view(torch.float64))
+        self._pending_reads.append(slot)
         return out
 
     def read_async(self, slot: int, timeout_us: int = 2_000_000):
         """Enqueue on the current stream, without a host synchronisation, the consumer side for ``slot``: wait on the
         device until every source rank has published it (with flow control: the oldest publication this rank has not
-        consumed yet; otherwise the latest), copy the slot's blocks into a private buffer, acknowledge.  Returns that
-        buffer's ``(records, losses)`` views (valid once the stream has run, until the next read); ``check_async()``
-        reports time-outs / overwritten blocks of everything enqueued so far."""
+        consumed yet, nothing if there is none; otherwise the latest), copy the slot's blocks into a private per-slot
+        buffer, acknowledge.  CUDA-graph capturable (flow control): the step's graph can consume an earlier step's slot.
+        Returns that buffer's ``(records, losses)`` views (valid once the stream has run, until the slot is read again);
+        ``check_async()`` reports time-outs / overwritten blocks of everything enqueued so far."""
         return self._consume(slot, timeout_us, True)
 
     def skip(self, slot: int, timeout_us: int = 2_000_000) -> None:
@@ -298,10 +309,10 @@ class PeerMailbox:
         """Synchronise and raise if a consumer wait timed out / found a newer sequence number, or a producer of this
         rank ran out of patience waiting for an acknowledgement."""
         code = int(self._status.item())
-        prod = int(self._state[3 * self.slots].item())
+        prod = int(self._state[5 * self.slots].item())
         pending, self._pending_reads = self._pending_reads, []
         self._status.zero_()
-        self._state[3 * self.slots].zero_()
+        self._state[5 * self.slots].zero_()
         if code > 0:
             raise RuntimeError(f"PeerMailbox: rank {code - 1} did not publish in time (consumed: {pending})")
         if code < 0:

@@ -27,7 +27,7 @@ int main(void) {
     if (pp_mailbox_block_bytes(85) != 85 * 56 + 8 + 16) return 5;      /* records, pad to 16, loss + flag + pad */
     if (pp_mailbox_block_bytes(4352) % 16 != 0) return 6;
     if (pp_mailbox_bytes(85, 8, 4) != 4 * 8 * pp_mailbox_block_bytes(85) + 4 * 8 * 4) return 6;   /* blocks + acknowledgements */
-    if (pp_mailbox_state_words(4) != 13 || pp_mailbox_ack(&mb, 1u, NULL) == PP_OK) return 6;
+    if (pp_mailbox_state_words(4) != 21 || pp_mailbox_ack(&mb, 1u, NULL) == PP_OK) return 6;
     rc = pp_pack_records(4, NULL, NULL, NULL, NULL, NULL, NULL, 1.0f, NULL, NULL, NULL);
     if (rc == PP_OK) return 7;
     rc = pp_mailbox_commit(&mb, 4, NULL, NULL);                          /* inconsistent (all-zero) mailbox */

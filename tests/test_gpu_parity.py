@@ -1250,10 +1250,60 @@ def test_mailbox_guards_readers_against_overwrites(pp, monkeypatch):
     codec.decode_device((pred, *heads), mailbox=mb, slot=0, loss=one)
     with pytest.raises(RuntimeError, match="did not acknowledge"):
         mb.check_async()
-    mb = PeerMailbox(B, K, 1, pred.device)
+    mb = PeerMailbox(B, K, 1, pred.device, flow_control=False)
     mb._published[0] = 1      # the host believes a step was published; no kernel ever raised the flag
     with pytest.raises(RuntimeError, match="did not publish in time"):
         mb.read(0, timeout_us=2000)
+
+
+def test_mailbox_consumer_inside_the_step_graph(pp):
+    """The consumer side keeps its sequence numbers on the device (pp_mailbox_consume), so one CUDA graph
+    per phase can publish slot g AND consume slot g - 2: every replay finds the records + loss of two steps ago in the
+    consumer's private copy, nothing before anything was published, and the producers never run into the
+    acknowledgement time-out (bench.py runs its multi-GPU steps exactly like this)."""
+    from probpose_pytorch_b200.distributed import PeerMailbox
+    wl = synth.WORKLOADS[2]
+    B, K, S = 3, wl.num_keypoints, 4
+    rng = np.random.default_rng(17)
+    pred = torch.from_numpy(rng.random((B, K, 64, 48), dtype=np.float32)).cuda()
+    heads = [torch.from_numpy(rng.random((B, K, 1, 1), dtype=np.float32)).cuda() for _ in range(4)]
+    codec = pp.Codec(pp.ProbMap(wl.input_size, wl.heatmap_size, wl.sigmas))
+    mb = PeerMailbox(B, K, S, pred.device)
+    loss = torch.zeros((), device="cuda")
+    marker = heads[0]
+
+    def phase(g):
+        r = codec.decode_device((pred, *heads), mailbox=mb, slot=g, loss=loss)
+        return r, mb.read_async((g - 2) % S)
+
+    step = 0
+    for g in range(S):                                   # eager cycle first (also the warm-up before capture)
+        marker.fill_(step); loss.fill_(step)
+        _, (rec, ls) = phase(g)
+        if step >= 2:
+            assert float(rec[0, 0, 3]) == step - 2 and float(ls[0]) == step - 2
+        else:
+            assert float(rec.abs().sum()) == 0.0          # nothing published into that slot yet: nothing consumed
+        step += 1
+    graphs = []
+    for g in range(S):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            out = phase(g)
+        graphs.append((gr, out))
+    for _ in range(3 * S + 1):
+        g = step % S
+        marker.fill_(step); loss.fill_(step)
+        graphs[g][0].replay()
+        mb.published(g)
+        r, (rec, ls) = graphs[g][1]
+        assert float(r[0, 0, 3]) == step
+        assert float(rec[0, 0, 3]) == step - 2 and float(ls[0]) == step - 2
+        step += 1
+    mb.check_async()                                      # no consumer or producer time-out along the way
+    for back in (2, 1):                                   # the two publications nobody has consumed yet
+        rec, ls = mb.read((step - back) % S)
+        assert float(rec[0, 0, 3]) == step - back and float(ls[0]) == step - back
 
 
 def test_expected_decoder_kernel_selection(pp, monkeypatch):
