@@ -66,6 +66,9 @@ def parse_args():
     ap.add_argument("--serial", action="store_true", help="run decode after encode on one stream (no fork/join)")
     ap.add_argument("--consumer", choices=["branch", "side"], default="branch",
                     help="multi-GPU mailbox consumer inside the step graph: a branch of its own, or behind the record packing")
+    ap.add_argument("--publish", choices=["deferred", "finalize"], default="deferred",
+                    help="multi-GPU mailbox: the loss of a step is published at the start of the next step (deferred) or by "
+                         "the loss' own finalize kernel at the end of its step")
     ap.add_argument("--exchange", choices=["mailbox", "nccl"], default="mailbox",
                     help="multi-GPU record + loss exchange: stores into every rank's mailbox over NVLink peer memory from the "
                          "record-packing kernel (default), or bucketed NCCL all-gathers")
@@ -280,34 +283,47 @@ class Bench:
     # ---- the step on device-resident inputs -------------------------------------------------------------
     def step(self, s, slot=0, fused=False, mailbox=None):
         """encode -> loss on the current stream, decode + record packing beside them on a second stream (fork / join;
-        inside a captured graph these are two branches).  `fused`: the encode happens inside the loss kernel."""
+        inside a captured graph these are two branches).  `fused`: the encode happens inside the loss kernel.
+        With a mailbox (multi-GPU) the step also carries the exchange: its records are stored into every rank's mailbox
+        by the packing kernel; its loss lands in the mailbox's loss slot and is published at the START of the next step
+        (commit_deferred: the NVLink round trips of a publication are not at the tail of the step that produced it);
+        and a third branch consumes -- waits for, copies, acknowledges -- what ALL ranks published two steps ago.  Two
+        steps of slack: that wait is normally over before it starts, and no rank runs more than two steps ahead."""
         torch, args = self.torch, self.ctx["args"]
         cur = torch.cuda.current_stream(self.ctx["dev"])
         pred5 = (s["pred"], *s["heads"])
         rec = None
+
+        def exchange_side():
+            if args.publish == "deferred":
+                mailbox.commit_deferred((slot - 1) % mailbox.slots)
+            mailbox.read_async((slot - 2) % mailbox.slots)
+
         if not args.serial:
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):
                 dec = self.pm.decode_device(s["pred"])
                 rec = self.codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
                 if mailbox is not None and args.consumer == "side":
-                    mailbox.read_async((slot - 2) % mailbox.slots)
+                    exchange_side()
             if mailbox is not None and args.consumer == "branch":
-                # the consumer side, a third branch of the same graph: wait for what ALL ranks published two steps ago,
-                # copy the gathered records + losses into this rank's private buffer, acknowledge (flow control).  Two
-                # steps of slack: the wait is normally over before it starts, and no rank runs more than two steps ahead.
                 self.cons.wait_stream(cur)
                 with torch.cuda.stream(self.cons):
-                    mailbox.read_async((slot - 2) % mailbox.slots)
+                    exchange_side()
         out = s["pred"].detach().requires_grad_(True)
         tgt = None
-        pub = mailbox.descriptor(slot) if mailbox is not None else None   # the loss' finalize kernel publishes it
+        pub = loss_out = None
+        if mailbox is not None:
+            if args.publish == "deferred":
+                loss_out = mailbox.loss_slot(slot)
+            else:
+                pub = mailbox.descriptor(slot)          # the loss' finalize kernel publishes it
         if fused:
-            loss = self.loss_fn.forward_mean_encoded(out, self.am, s["kps"], s["vis"], publish=pub)
+            loss = self.loss_fn.forward_mean_encoded(out, self.am, s["kps"], s["vis"], publish=pub, loss_out=loss_out)
         else:
             enc = self.am.encode_batch(s["kps"], s["vis"], dtype=self.tdtype)
             tgt = enc["heatmaps"]
-            loss = self.loss_fn.forward_mean(out, tgt, enc["keypoint_weights"], publish=pub)
+            loss = self.loss_fn.forward_mean(out, tgt, enc["keypoint_weights"], publish=pub, loss_out=loss_out)
         if args.serial:
             dec = self.pm.decode_device(s["pred"])
         loss.backward()
@@ -318,8 +334,8 @@ class Bench:
         if rec is None:
             rec = self.codec.pack_records(dec, pred5, mailbox=mailbox, slot=slot)
             if mailbox is not None:
-                mailbox.read_async((slot - 2) % mailbox.slots)
-        if mailbox is not None:
+                exchange_side()
+        if mailbox is not None and pub is not None:
             mailbox.loss_enqueued(slot)
         return dict(rec=rec, loss=loss.detach(), grad=out.grad, dec=dec, tgt=tgt)
 
@@ -356,9 +372,11 @@ class Bench:
                     self.mailbox = ppd.PeerMailbox(self.B, self.K, max(4, len(self.sets)), dev)
                 mailbox = self.mailbox
                 n_phases = mailbox.slots
-                note = (f"records + loss stored into every rank's mailbox over NVLink by pp_pack_records and the loss' finalize "
-                        f"kernel ({mailbox.slots} slots, flow control); every rank consumes (waits for, copies, acknowledges) every "
-                        "step's slot two steps later, inside the step's CUDA graph")
+                how = ("the loss at the start of the next step (pp_mailbox_commit_deferred)" if args.publish == "deferred"
+                       else "the loss by the loss' finalize kernel")
+                note = (f"records stored into every rank's mailbox over NVLink by pp_pack_records, {how} ({mailbox.slots} slots, "
+                        "flow control); every rank consumes (waits for, copies, acknowledges) every step's slot two steps later, "
+                        "inside the step's CUDA graph")
             except Exception as e:   # symmetric memory unavailable on this box: the NCCL path still measures the step
                 note = f"NCCL (symmetric memory unavailable: {type(e).__name__}: {str(e)[:80]})"
         graphs, results = self._graphs(lambda s, g: self.step(s, g, fused=fused, mailbox=mailbox), n_phases)
@@ -414,6 +432,8 @@ class Bench:
         res = None
         for i in range(steps):
             res = run_step(i)
+        if mailbox is not None and args.publish == "deferred":
+            mailbox.commit_deferred((steps - 1) % n_phases)    # the last step's loss: published inside the timed region too
         drain()          # the main stream waits for the last exchanges: they are inside the timed region
         ev1.record()
         torch.cuda.synchronize()
@@ -429,6 +449,8 @@ class Bench:
             for i in range(steps, -(-steps // n_phases) * n_phases):
                 run_step(i)
             total = -(-steps // n_phases) * n_phases
+            if args.publish == "deferred":
+                mailbox.commit_deferred((total - 1) % n_phases)
             outs = {}
             for i in (total - 2, total - 1):
                 outs[i % n_phases] = mailbox.read_async(i % n_phases)
@@ -792,7 +814,7 @@ def run_product(args):
     if rank == 0:
         # kernels of ours inside the timed region, per step: encode, decode (+ its hand-over launch), loss, loss finalize,
         # grad-scale check, record packing (+ the mailbox consumer: wait, acknowledge)
-        launches_per_step = 7 + (2 if world > 1 and args.exchange == "mailbox" else 0)   # + consumer wait, acknowledge
+        launches_per_step = 7 + (2 if world > 1 and args.exchange == "mailbox" else 0)   # + deferred commit, consumer
         line = {
             "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

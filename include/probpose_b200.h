@@ -343,6 +343,10 @@ PP_API int pp_pack_records(int64_t N,
  * pp_pack_records and this call, or pp_oks_loss_forward[_encoded] with `publish` -- finishes last; they may run on
  * different streams without an ordering between them.  Exactly one of each per publication. */
 PP_API int pp_mailbox_commit(const pp_mailbox* mailbox, int64_t n_records, const float* loss, pp_stream_t stream);
+/* The same one step late, for a pipelined loop that keeps the NVLink round trips of the publication off the end of its
+ * step: launched at the START of step j + 1 for the slot of step j (whose loss is final by then), it publishes only if
+ * the slot's records party has arrived and is waiting, and does nothing otherwise (first step; slot already flushed). */
+PP_API int pp_mailbox_commit_deferred(const pp_mailbox* mailbox, int64_t n_records, const float* loss, pp_stream_t stream);
 /* Consumer side, after the blocks of `mailbox->slot` have been used: tell every producer that this rank is done with
  * sequence number `seq` of the slot (required with flow_control). */
 PP_API int pp_mailbox_ack(const pp_mailbox* mailbox, uint32_t seq, pp_stream_t stream);

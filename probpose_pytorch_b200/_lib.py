@@ -32,7 +32,7 @@ EXPORTS = (
     "pp_oks_loss_forward", "pp_oks_loss_forward_encoded", "pp_oks_loss_backward", "pp_scale_inplace", "pp_pose_targets",
     "pp_pck_accuracy", "pp_binary_accuracy", "pp_masked_mae",
     "pp_mailbox_block_bytes", "pp_mailbox_bytes", "pp_mailbox_state_words", "pp_pack_records", "pp_mailbox_commit",
-    "pp_mailbox_wait", "pp_mailbox_ack", "pp_mailbox_consume",
+    "pp_mailbox_wait", "pp_mailbox_ack", "pp_mailbox_consume", "pp_mailbox_commit_deferred",
 )
 
 
@@ -133,6 +133,7 @@ def lib() -> C.CDLL:
     L.pp_mailbox_state_words.argtypes = [i32]
     L.pp_mailbox_state_words.restype = i64
     L.pp_mailbox_ack.argtypes = [C.POINTER(Mailbox), C.c_uint32, vp]
+    L.pp_mailbox_commit_deferred.argtypes = [C.POINTER(Mailbox), i64, vp, vp]
     L.pp_mailbox_consume.argtypes = [C.POINTER(Mailbox), i64, vp, vp, i64, vp, vp]
     L.pp_pack_records.argtypes = [i64, vp, vp, vp, vp, vp, vp, f32, vp, C.POINTER(Mailbox), vp]
     L.pp_mailbox_commit.argtypes = [C.POINTER(Mailbox), i64, vp, vp]

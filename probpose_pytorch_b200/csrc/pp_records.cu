@@ -114,6 +114,14 @@ __global__ void mailbox_commit_kernel(pp_mailbox mb, int64_t N, const float* __r
   mailbox_store_loss_and_arrive(mb, N, loss ? static_cast<double>(*loss) : 0.0);
 }
 
+// the loss party, one step late: only if the records party of the slot has arrived and is waiting (nothing otherwise)
+__global__ void mailbox_commit_deferred_kernel(pp_mailbox mb, int64_t N, const float* __restrict__ loss) {   // <<<1, 32>>>
+  unsigned arrived = 0;
+  if (threadIdx.x == 0) arrived = *reinterpret_cast<volatile unsigned*>(mb.state + mb.slots + mb.slot);
+  if (__shfl_sync(0xffffffffu, arrived, 0) != 1u) return;
+  mailbox_store_loss_and_arrive(mb, N, loss ? static_cast<double>(*loss) : 0.0);
+}
+
 __global__ void mailbox_ack_kernel(pp_mailbox mb, unsigned seq) {
   const int p = threadIdx.x;
   if (p < mb.world) st_release_sys(ack_word(mb.peer_bufs[p], mb, mb.slot, mb.rank), seq);
@@ -227,6 +235,8 @@ mailbox_consume_kernel(pp_mailbox mb, int64_t N, double* __restrict__ rec_out, d
 
 extern "C" {
 
+static int check_consumer_mailbox(const char* fn, const pp_mailbox* mailbox, int64_t n_records);
+
 int64_t pp_mailbox_block_bytes(int64_t n_records) { return loss_offset(n_records) + 16; }
 
 int64_t pp_mailbox_bytes(int64_t n_records, int32_t world, int32_t slots) {
@@ -267,6 +277,13 @@ int pp_mailbox_commit(const pp_mailbox* mailbox, int64_t n_records, const float*
                  mb.slot < mb.slots && mb.block_bytes == pp_mailbox_block_bytes(n_records),
              PP_ERR_INVALID_ARG, "pp_mailbox_commit: inconsistent mailbox");
   mailbox_commit_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(mb, n_records, loss);
+  PP_CUDA_OK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_mailbox_commit_deferred(const pp_mailbox* mailbox, int64_t n_records, const float* loss, pp_stream_t stream) {
+  if (int rc = check_consumer_mailbox("pp_mailbox_commit_deferred", mailbox, n_records)) return rc;
+  mailbox_commit_deferred_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(*mailbox, n_records, loss);
   PP_CUDA_OK(cudaGetLastError());
   return PP_OK;
 }

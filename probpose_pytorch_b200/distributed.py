@@ -224,6 +224,7 @@ class PeerMailbox:
         # the consumer's private, compact copies of every slot (allocated up front: read_async may be captured in a graph)
         self._st_rec = torch.zeros((self.slots, self.world, self.n_records * 7), dtype=torch.float64, device=self.device)
         self._st_loss = torch.zeros((self.slots, self.world, 1), dtype=torch.float64, device=self.device)
+        self._loss_slots = torch.zeros((self.slots, 1), dtype=torch.float32, device=self.device)   # see loss_slot()
         self._pending_reads: list = []
         self._lib = _lib
 
@@ -242,6 +243,25 @@ class PeerMailbox:
                                                    self._lib.stream_ptr(self.device))
         self._lib.check(rc, "pp_mailbox_commit")
         self.loss_enqueued(slot)
+
+    def loss_slot(self, slot: int) -> Tensor:
+        """A persistent (1,) float32 tensor for the loss of ``slot``: pass it as ``loss_out=`` to
+        ``OKSHeatmapLoss.forward_mean[_encoded]`` and publish it one step late with ``commit_deferred(slot)``."""
+        return self._loss_slots[slot]
+
+    def commit_deferred(self, slot: int, loss: Tensor | None = None) -> None:
+        """The loss party of ``slot`` one step late (``pp_mailbox_commit_deferred``): call it at the START of the next
+        step -- typically on a side branch of that step's CUDA graph -- so that the NVLink round trips of the
+        publication do not sit at the end of the step that produced the loss.  ``loss`` defaults to ``loss_slot(slot)``.
+        Publishes only if the slot's records have been packed and are waiting for their loss; otherwise (very first
+        step, or the slot was flushed already) nothing happens, so it is safe to call unconditionally.  Flow control
+        only (the host keeps no count of these publications)."""
+        assert self.flow_control, "deferred commits need flow_control=True"
+        src = self._loss_slots[slot] if loss is None else loss.detach().reshape(1).to(torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self._lib.lib().pp_mailbox_commit_deferred(self.descriptor(slot), self.n_records, self._lib.ptr(src),
+                                                            self._lib.stream_ptr(self.device))
+        self._lib.check(rc, "pp_mailbox_commit_deferred")
 
     def loss_enqueued(self, slot: int) -> None:
         """Book-keeping after the loss party of ``slot`` has been enqueued (``commit`` calls it; call it yourself after

@@ -25,6 +25,14 @@ def _scratch(p: _lib.LossParams, dev: torch.device) -> Tensor:
     return torch.empty((n + 7) // 8, dtype=torch.float64, device=dev)
 
 
+def _check_loss_out(loss_out, output):
+    if loss_out is None:
+        return None
+    if not (loss_out.dtype == torch.float32 and loss_out.numel() == 1 and loss_out.device == output.device and loss_out.is_contiguous()):
+        raise ValueError("loss_out must be a (1,) float32 tensor on the device of `output`")
+    return loss_out.view(1)
+
+
 class _Prepared:
     """Validated, contiguous inputs + the parameter block shared by forward and backward."""
 
@@ -69,12 +77,13 @@ class _Prepared:
         self.scratch = _scratch(self.params, dev)
 
     publish = None   # pp_mailbox descriptor: the loss' finalize kernel also publishes it (multi-GPU exchange)
+    scalar_out = None   # optional caller-owned (1,) float32 tensor that receives the scalar loss
 
     def forward(self, *, want_grad: bool, grad_scale: float = 1.0):
         B, K, H, W = self.shape
         dev, mode = self.device, self.params.mode
         loss_map = loss_kpt = peak = grad = None
-        scalar = torch.empty(1, dtype=torch.float32, device=dev)
+        scalar = self.scalar_out if self.scalar_out is not None else torch.empty(1, dtype=torch.float32, device=dev)
         flag = torch.empty(1, dtype=torch.int32, device=dev)
         if mode == _lib.PP_LOSS_PER_PIXEL:
             loss_map = torch.empty(self.shape, dtype=self.dtype, device=dev)
@@ -144,10 +153,11 @@ class _PreparedEncoded:
         self.last_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # an encoded target is in [0, 1] by construction
 
     publish = None
+    scalar_out = None
 
     def forward(self, *, want_grad: bool, grad_scale: float = 1.0):
         dev = self.device
-        scalar = torch.empty(1, dtype=torch.float32, device=dev)
+        scalar = self.scalar_out if self.scalar_out is not None else torch.empty(1, dtype=torch.float32, device=dev)
         grad = torch.empty(self.shape, dtype=self.dtype, device=dev) if want_grad else None
         e = self.encoded
         with torch.cuda.device(dev):
@@ -261,9 +271,10 @@ class OKSHeatmapLoss(nn.Module):
         self.check_target = check_target
         assert self.oks_type in ["minus", "plus", "both"]
 
-    def _run(self, output, target, target_weights, mask, mode, default_mean, fused, publish=None):
+    def _run(self, output, target, target_weights, mask, mode, default_mean, fused, publish=None, loss_out=None):
         prep = _Prepared(self, output, target, target_weights, mask, mode)
         prep.publish = publish
+        prep.scalar_out = _check_loss_out(loss_out, output)
         loss = _OKSLossFunction.apply(output, prep, default_mean, fused)
         if self.check_target:
             assert int(prep.last_flag.item()) == 0, "target should be normalized"
@@ -285,14 +296,17 @@ class OKSHeatmapLoss(nn.Module):
         return self._run(output, target, target_weights, mask, _lib.PP_LOSS_PER_KEYPOINT, not per_keypoint, False)
 
     def forward_mean(self, output: Tensor, target: Tensor, target_weights: Tensor | None = None,
-                     mask: Tensor | None = None, publish=None) -> Tensor:
+                     mask: Tensor | None = None, publish=None, loss_out: Tensor | None = None) -> Tensor:
         """``forward(..., per_pixel=True).mean()`` in a single fused kernel (forward + backward).  ``publish``: a
         ``PeerMailbox.descriptor(slot)`` -- the kernel that finishes the loss also stores it into that mailbox slot on
-        every GPU (the loss party of the multi-GPU exchange; call ``mailbox.loss_enqueued(slot)`` afterwards)."""
-        return self._run(output, target, target_weights, mask, _lib.PP_LOSS_PIXEL_MEAN, False, True, publish)
+        every GPU (the loss party of the multi-GPU exchange; call ``mailbox.loss_enqueued(slot)`` afterwards).
+        ``loss_out``: a caller-owned (1,) float32 CUDA tensor that receives the scalar (e.g. ``PeerMailbox.loss_slot(s)``,
+        for a publication one step late); the returned loss is a view of it."""
+        return self._run(output, target, target_weights, mask, _lib.PP_LOSS_PIXEL_MEAN, False, True, publish, loss_out)
 
     def forward_mean_encoded(self, output: Tensor, probmap, keypoints, keypoints_visible=None,
-                             target_weights: Tensor | None = None, return_encoded: bool = False, publish=None):
+                             target_weights: Tensor | None = None, return_encoded: bool = False, publish=None,
+                             loss_out: Tensor | None = None):
         """``forward_mean(output, probmap.encode_batch(keypoints, keypoints_visible)["heatmaps"], weights)`` without
         the target: ONE pass reads ``output``, forms the target of every pixel from the keypoint's separable factors
         (generate_probmaps, codec.py:56-66), reduces the loss and writes ``d loss / d output`` -- 2 H W e bytes per
@@ -305,5 +319,6 @@ class OKSHeatmapLoss(nn.Module):
         probmap = getattr(probmap, "probmap", probmap)
         prep = _PreparedEncoded(self, output, probmap, keypoints, keypoints_visible, target_weights)
         prep.publish = publish
+        prep.scalar_out = _check_loss_out(loss_out, output)
         loss = _OKSLossFunction.apply(output, prep, False, True)
         return (loss, prep.encoded) if return_encoded else loss

@@ -1256,11 +1256,13 @@ def test_mailbox_guards_readers_against_overwrites(pp, monkeypatch):
         mb.read(0, timeout_us=2000)
 
 
-def test_mailbox_consumer_inside_the_step_graph(pp):
-    """The consumer side keeps its sequence numbers on the device (pp_mailbox_consume), so one CUDA graph
-    per phase can publish slot g AND consume slot g - 2: every replay finds the records + loss of two steps ago in the
-    consumer's private copy, nothing before anything was published, and the producers never run into the
-    acknowledgement time-out (bench.py runs its multi-GPU steps exactly like this)."""
+@pytest.mark.parametrize("publish", ["in-step", "deferred"])
+def test_mailbox_consumer_inside_the_step_graph(pp, publish):
+    """The consumer side keeps its sequence numbers on the device (pp_mailbox_consume), so one CUDA graph per phase can
+    publish slot g AND consume slot g - 2: every replay finds the records + loss of two steps ago in the consumer's
+    private copy, nothing before anything was published, and the producers never run into the acknowledgement time-out
+    (bench.py runs its multi-GPU steps exactly like this).  "deferred": the loss of a step is written to the mailbox's
+    loss slot and published at the start of the NEXT step (pp_mailbox_commit_deferred), a no-op when nothing waits."""
     from probpose_pytorch_b200.distributed import PeerMailbox
     wl = synth.WORKLOADS[2]
     B, K, S = 3, wl.num_keypoints, 4
@@ -1273,9 +1275,16 @@ def test_mailbox_consumer_inside_the_step_graph(pp):
     marker = heads[0]
 
     def phase(g):
+        if publish == "deferred":
+            mb.commit_deferred((g - 1) % S)                       # last step's loss; nothing on the very first step
+            got = mb.read_async((g - 2) % S)
+            r = codec.decode_device((pred, *heads), mailbox=mb, slot=g)      # records party only
+            mb.loss_slot(g).copy_(loss.reshape(1))                            # "the loss kernel" of this step
+            return r, got
         r = codec.decode_device((pred, *heads), mailbox=mb, slot=g, loss=loss)
         return r, mb.read_async((g - 2) % S)
 
+    # with the deferred publication a slot becomes visible one step later, still before its consumer two steps on
     step = 0
     for g in range(S):                                   # eager cycle first (also the warm-up before capture)
         marker.fill_(step); loss.fill_(step)
@@ -1300,6 +1309,9 @@ def test_mailbox_consumer_inside_the_step_graph(pp):
         assert float(r[0, 0, 3]) == step
         assert float(rec[0, 0, 3]) == step - 2 and float(ls[0]) == step - 2
         step += 1
+    if publish == "deferred":
+        mb.commit_deferred((step - 1) % S)                # flush the last step's loss
+        mb.commit_deferred((step - 1) % S)                # ... and a second call finds nothing waiting
     mb.check_async()                                      # no consumer or producer time-out along the way
     for back in (2, 1):                                   # the two publications nobody has consumed yet
         rec, ls = mb.read((step - back) % S)
