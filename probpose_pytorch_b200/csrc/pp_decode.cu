@@ -887,7 +887,7 @@ int mma_launch_shape(const pp_decode_params& p, const pp_oks_table& tab, const T
   geo.div_W = div_magic(static_cast<unsigned>(W));
   geo.static_split = pp_env_int("PP_DECODE_STATIC", 0) ? 1u : 0u;
   const size_t smem = static_cast<size_t>(WPC) * geo.slot_bytes;
-  auto kern = (dbg && !kDark) ? decode_expected_mma_kernel<T, H, W, WPC, MINB, true, false>
+  auto kern = ((dbg || dk.dbg_times) && !kDark) ? decode_expected_mma_kernel<T, H, W, WPC, MINB, true, false>
                               : decode_expected_mma_kernel<T, H, W, WPC, MINB, false, kDark>;
   int per = 0;
   if (int rc = pp_configure_kernel(reinterpret_cast<const void*>(kern), 32 * WPC, smem, &per)) return rc;
@@ -1218,6 +1218,22 @@ __attribute__((visibility("default"))) int pp_debug_decode_mma_prefilter(const p
                                     static_cast<unsigned*>(scratch), prefilter, MmaDarkArgs{}, st);
   return mma_launch<__nv_bfloat16, false>(*p, *table, static_cast<const __nv_bfloat16*>(heatmaps), locs, vals, argmax, nullptr,
                                           static_cast<unsigned*>(scratch), prefilter, MmaDarkArgs{}, st);
+}
+
+// Debug entry point (not in the header): the tensor-core kernel with a per-heatmap timeline -- `times` (N, 8) uint64, see
+// the kernel; tools/decode_timeline.py turns it into phase latencies and a picture of when the warps finish.
+__attribute__((visibility("default"))) int pp_debug_decode_mma_timeline(const pp_decode_params* p, const pp_oks_table* table,
+                                                                        const void* heatmaps, float* locs, float* vals,
+                                                                        int32_t* argmax, unsigned long long* times, void* scratch,
+                                                                        int64_t scratch_bytes, pp_stream_t stream) {
+  if (int rc = check_decode_params("pp_debug_decode_mma_timeline", p)) return rc;
+  PP_REQUIRE(table && table->mma_tables && table->mma_index && heatmaps && locs && vals && times && scratch &&
+                 scratch_bytes >= pp_decode_expected_scratch_bytes_for(p) && p->heatmap_dtype == PP_F32,
+             PP_ERR_INVALID_ARG, "pp_debug_decode_mma_timeline: null argument / scratch too small / not float32");
+  MmaDarkArgs dk{};
+  dk.dbg_times = times;
+  return mma_launch<float, false>(*p, *table, static_cast<const float*>(heatmaps), locs, vals, argmax, nullptr,
+                                  static_cast<unsigned*>(scratch), nullptr, dk, static_cast<cudaStream_t>(stream));
 }
 
 int64_t pp_decode_expected_workspace_floats(const pp_decode_params* p) {

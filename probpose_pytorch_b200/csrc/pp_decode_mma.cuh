@@ -137,29 +137,50 @@ constexpr int kMmaScratchHead = 4;
 // loop iteration was the largest stall of the kernel after the work-queue atomic).  One body for every radius and for
 // windows inside / across the map border: the fully unrolled per-radius variants of a first version ran into the
 // instruction cache instead (capture r02h: 29 % of the stall samples were instruction fetches).
-template <typename T>
-__device__ __noinline__ float mma_exact1(const T* __restrict__ plane, const double* __restrict__ w2d, int H, int W, int r,
-                                         int y, int x, int lane) {
+// Exact float64 values R(p) of up to NC candidate pixels at once (cand[0 .. n_c), flat indices; NC = 2 or 4): every tap
+// weight is loaded once and used NC times, and the NC accumulation chains overlap.  One candidate per call cost ~1.4 us
+// each whatever the radius -- the call's fixed latency (cold table load, fp64 shuffle reduction), not its arithmetic --
+// which was the long tail of a small batch (tools/decode_timeline.py).  Slots beyond n_c repeat candidate 0 (NC = 2 for
+// the common two-candidate map keeps that waste to one slot).  The taps are summed in the same lane / order whatever
+// the grouping (per-lane partial sums, then warp_sum), so the values do not depend on it.
+template <typename T, int NC>
+__device__ __noinline__ void mma_exact_n(const T* __restrict__ plane, const double* __restrict__ w2d, int H, int W, int r,
+                                         const int* __restrict__ cand, int n_c, unsigned div_W, int lane, float (&out)[NC]) {
   const int d = 2 * r + 1, n = d * d;
   const int qs = 32 / d, rs = 32 - qs * d;
+  int cy[NC], cx[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ci = cand[c < n_c ? c : 0];
+    cy[c] = fast_div(ci, div_W);
+    cx[c] = ci - cy[c] * W - r;
+    cy[c] -= r;
+  }
   int ti = lane / d, tj = lane - ti * d;
-  double a = 0.0;
+  double a[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) a[c] = 0.0;
+  constexpr int U = NC == 2 ? 4 : 2;   // tap weights in flight per lane
 #pragma unroll 1
-  for (int i0 = lane; i0 < n; i0 += 128) {
-    double w[4];
+  for (int i0 = lane; i0 < n; i0 += 32 * U) {
+    double w[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = (i0 + 32 * u < n) ? __ldg(w2d + i0 + 32 * u) : 0.0;
+    for (int u = 0; u < U; ++u) w[u] = (i0 + 32 * u < n) ? __ldg(w2d + i0 + 32 * u) : 0.0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (i0 + 32 * u < n) {
-        const float v = plane_value<T>(plane, reflect1(y + ti - r, H) * W + reflect1(x + tj - r, W));
-        a = fma(w[u], static_cast<double>(v), a);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const float v = plane_value<T>(plane, reflect1(cy[c] + ti, H) * W + reflect1(cx[c] + tj, W));
+          a[c] = fma(w[u], static_cast<double>(v), a[c]);
+        }
       }
       tj += rs; ti += qs;
       if (tj >= d) { tj -= d; ++ti; }
     }
   }
-  return static_cast<float>(warp_sum(a));
+#pragma unroll
+  for (int c = 0; c < NC; ++c) out[c] = static_cast<float>(warp_sum(a[c]));
 }
 
 // an interior pixel and its left / right / upper / lower neighbours (out[0..4]); the five windows share every tap.
@@ -230,6 +251,7 @@ struct MmaDarkArgs {   // what the kDark instance needs besides the expected-OKS
   const float* blur_taps;   // (ksize) float32
   int ksize;
   float* peaks;             // out (N, 2) or null
+  unsigned long long* dbg_times;   // kDebug only: 8 words per heatmap (tools/decode_timeline.py), or null
 };
 
 constexpr int kMmaMaxK = 256;    // channels whose work-queue order / radius / table index are staged in shared memory
@@ -292,7 +314,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
   // the warp (consumed half an iteration later it cost 17 % of the samples, capture r02c), while the tail of a large
   // batch still balances (B = 1024: 146 us against 173 us with a purely static split).  geo.static_split: static only.
   const int gwarp = blockIdx.x * WPC + warp, nwarps = gridDim.x * WPC;
-  const bool dynamic = geo.static_split == 0 && N > 2 * nwarps;   // nothing to pull when two items per warp cover the batch
+  const bool dynamic = geo.static_split == 0 && N > 2 * nwarps;
   unsigned* work_counter = scratch;
   auto item_to_hm = [&](int j) -> int {
     if (kDark) return j;   // one operand table for every channel: natural order
@@ -310,10 +332,6 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
     unsigned pulled_raw = 0u;
     if (dynamic && lane == 0) pulled_raw = atomicAdd(work_counter, 1u);   // the item after the next one
     const int next_hm = next_item < N ? item_to_hm(next_item) : 0;
-    if (lane == 0 && next_item < N)   // the next plane is on its way into L2 while this one is decoded
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(heatmaps + static_cast<size_t>(next_hm) * HW),
-                   "r"(geo.plane_bytes)
-                   : "memory");
 
     const int k = kDark ? 0 : hm % p.K;
     const int r = kDark ? dk.ksize >> 1 : ch_rad[k];
@@ -321,7 +339,26 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
     const uint4* t2 = t1 + S::kT1;
     const double* w2dk = kDark ? nullptr : tab.kernel2d + static_cast<size_t>(k) * PP_OKS_TAPS * PP_OKS_TAPS;
 
+    // kDebug: per-heatmap timeline -- [0] global ns at the start, [1..6] SM clock at start / plane arrived / scan done /
+    // sweep done / re-evaluation done / outputs written, [7] smid << 32 | candidates << 8 | iteration
+    unsigned long long* tl = (kDebug && dk.dbg_times) ? dk.dbg_times + static_cast<size_t>(hm) * 8 : nullptr;
+    int tl_count = 0;
+    if (kDebug && tl && lane == 0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      tl[0] = ns;
+      tl[1] = clock64();
+    }
+
     mbar_wait(bar, it & 1);
+    if (kDebug && tl && lane == 0) tl[2] = clock64();
+    // the next plane is on its way into L2 while this one is decoded -- asked for AFTER this one has arrived: at kernel
+    // start every warp's first request would otherwise compete with its second (timeline: first plane after 1.5 us
+    // instead of 4 us)
+    if (lane == 0 && next_item < N)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(heatmaps + static_cast<size_t>(next_hm) * HW),
+                   "r"(geo.plane_bytes)
+                   : "memory");
 
     // ---- A: head tail in place (optional), then min / max
     if (tail) {
@@ -373,6 +410,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
       p0 = __reduce_min_sync(0xffffffffu, idx);
     }
 
+    if (kDebug && tl && lane == 0) tl[3] = clock64();
     int best = 0;
     float best_val = 0.0f, score = vmax;
     float nb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -521,6 +559,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
         __syncwarp();
         const int count = cand[kWCand];
         handed_over = count > kWCand;
+        if (kDebug && tl && lane == 0) { tl[4] = clock64(); tl_count = count; }
         if (kDark && !handed_over) {
           // ---- G (kDark): the blurred maximum = the largest exact blur among the candidates; the blur at the raw peak
           // and its six DARK neighbours, edge-clamped (codec.py:346-359).  Pixel list: candidates, then the stencil.
@@ -552,9 +591,19 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
             best = cand[0];
           } else {
             best_val = -INFINITY; best = 0x7fffffff;
-            for (int q = 0; q < count; ++q) {
-              const int ci = cand[q], cy = fast_div(ci, geo.div_W);
-              argmax_combine(best_val, best, mma_exact1<T>(plane, w2dk, H, W, r, cy, ci - cy * W, lane), ci);
+            if (count == 2) {
+              float ev[2];
+              mma_exact_n<T, 2>(plane, w2dk, H, W, r, cand, 2, geo.div_W, lane, ev);
+              argmax_combine(best_val, best, ev[0], cand[0]);
+              argmax_combine(best_val, best, ev[1], cand[1]);
+            } else {
+              for (int q = 0; q < count; q += 4) {
+                float ev[4];
+                mma_exact_n<T, 4>(plane, w2dk, H, W, r, cand + q, min(4, count - q), geo.div_W, lane, ev);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if (q + c < count) argmax_combine(best_val, best, ev[c], cand[q + c]);
+              }
             }
           }
           const int by = fast_div(best, geo.div_W), bx = best - by * W;
@@ -570,6 +619,7 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
       }
     }
 
+    if (kDebug && tl && lane == 0) tl[5] = clock64();
     // ---- H: outputs (thread 0: x, thread 1: y; heatmap.py:136-165 in float32, the reference's operation order) or
     // hand-over to the general kernel
     if (handed_over) {
@@ -611,6 +661,12 @@ decode_expected_mma_kernel(pp_decode_params p, pp_oks_table tab, const T* __rest
       }
     }
 
+    if (kDebug && tl && lane == 0) {
+      unsigned smid;
+      asm("mov.u32 %0, %%smid;" : "=r"(smid));
+      tl[6] = clock64();
+      tl[7] = (static_cast<unsigned long long>(smid) << 32) | (static_cast<unsigned long long>(tl_count) << 8) | static_cast<unsigned>(it & 255);
+    }
     // ---- next heatmap: the warp is done with the plane, lane 0 starts the copy (an L2 hit by now)
     __syncwarp();
     if (lane == 0 && next_item < N) {
