@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--serial", action="store_true", help="run decode after encode on one stream (no fork/join)")
     ap.add_argument("--consumer", choices=["branch", "side"], default="branch",
                     help="multi-GPU mailbox consumer inside the step graph: a branch of its own, or behind the record packing")
+    ap.add_argument("--plain-backward", action="store_true",
+                    help="loss.backward() with autograd's implicit ones_like gradient instead of backward(unit_upstream)")
     ap.add_argument("--publish", choices=["deferred", "finalize"], default="deferred",
                     help="multi-GPU mailbox: the loss of a step is published at the start of the next step (deferred) or by "
                          "the loss' own finalize kernel at the end of its step")
@@ -326,7 +328,10 @@ class Bench:
             loss = self.loss_fn.forward_mean(out, tgt, enc["keypoint_weights"], publish=pub, loss_out=loss_out)
         if args.serial:
             dec = self.pm.decode_device(s["pred"])
-        loss.backward()
+        if args.plain_backward:
+            loss.backward()
+        else:      # the same without the ones_like fill and the no-op rescale launch (loss.unit_upstream)
+            loss.backward(gradient=self.pp.unit_upstream(loss.device, loss.dtype))
         if not args.serial:
             cur.wait_stream(self.side)
             if mailbox is not None and args.consumer == "branch":
@@ -812,9 +817,9 @@ def run_product(args):
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
     if rank == 0:
-        # kernels of ours inside the timed region, per step: encode, decode (+ its hand-over launch), loss, loss finalize,
-        # grad-scale check, record packing (+ the mailbox consumer: wait, acknowledge)
-        launches_per_step = 7 + (2 if world > 1 and args.exchange == "mailbox" else 0)   # + deferred commit, consumer
+        # kernels of ours inside the timed region, per step: encode, decode + its hand-over launch, record packing, loss,
+        # loss finalize (+ the gradient rescale launch with --plain-backward) (+ the mailbox's deferred commit and consumer)
+        launches_per_step = 6 + (1 if args.plain_backward else 0) + (2 if world > 1 and args.exchange == "mailbox" else 0)
         line = {
             "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -16,10 +16,10 @@ fallback -- calls raise when the library or a GPU is missing.
 from .codec import ArgMaxProbMap, Codec, ProbMap, generate_probmaps  # noqa: F401
 from .head import HeatmapTail, Sparsemax, heatmap_tail, patch_probmap_head  # noqa: F401
 from .heatmap import get_heatmap_expected_value, get_heatmap_maximum  # noqa: F401
-from .loss import OKSHeatmapLoss  # noqa: F401
+from .loss import OKSHeatmapLoss, unit_upstream  # noqa: F401
 from .probpose_loss import FusedOKSHeatmapLoss, ground_truth_from_keypoints, patch_probpose_loss  # noqa: F401
 
 __all__ = ["ArgMaxProbMap", "Codec", "ProbMap", "generate_probmaps", "heatmap_tail", "HeatmapTail",
            "patch_probmap_head", "Sparsemax",
            "get_heatmap_expected_value", "get_heatmap_maximum", "OKSHeatmapLoss",
-           "FusedOKSHeatmapLoss", "patch_probpose_loss", "ground_truth_from_keypoints"]
+           "FusedOKSHeatmapLoss", "patch_probpose_loss", "ground_truth_from_keypoints", "unit_upstream"]

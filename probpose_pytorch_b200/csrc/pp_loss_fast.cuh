@@ -303,6 +303,10 @@ oks_loss_fast_kernel(FastArgs a) {
   __shared__ double red[8];
   __shared__ int red_flag;
 
+  // the one-block kernel that sums this grid's partial sums is launched programmatically dependent on it (pp_loss.cu,
+  // launch_finalize): let it become resident now -- it waits (griddepcontrol.wait) until this grid has completed and
+  // flushed -- instead of paying its launch latency after this grid's last CTA
+  asm volatile("griddepcontrol.launch_dependents;");
   const int tid = threadIdx.x;
   const int H = a.H, W = a.W;
   const long long HW = static_cast<long long>(H) * W;
