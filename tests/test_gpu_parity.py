@@ -1530,6 +1530,32 @@ def test_dark_and_loss_persistent_loops_vs_oracle(pp, monkeypatch):
         _close(o.grad.float().cpu().numpy(), o_ref.grad.numpy(), rtol)
 
 
+def test_backward_with_unit_upstream(pp):
+    """loss.backward(gradient=unit_upstream(...)) = loss.backward() without the ones_like fill and the rescale launch: the
+    gradient written by the fused forward pass is returned as is; any other upstream value still rescales it."""
+    wl = synth.WORKLOADS[2]
+    B, K = 3, wl.num_keypoints
+    rng = np.random.default_rng(23)
+    out = torch.from_numpy(rng.random((B, K, 64, 48), dtype=np.float32)).cuda()
+    tgt = torch.from_numpy(rng.random((B, K, 64, 48), dtype=np.float32)).cuda()
+    w = torch.from_numpy((rng.random((B, K)) < 0.8).astype(np.float32)).cuda()
+    loss_fn = pp.OKSHeatmapLoss(use_target_weight=True, smoothing_weight=0.05, oks_type="minus", check_target=False)
+    grads = []
+    for how in ("plain", "unit", "scaled"):
+        o = out.clone().requires_grad_(True)
+        loss = loss_fn.forward_mean(o, tgt, w)
+        if how == "plain":
+            loss.backward()
+        elif how == "unit":
+            loss.backward(gradient=pp.unit_upstream(loss.device, loss.dtype))
+        else:
+            (loss * 3.0).backward()
+        grads.append(o.grad)
+    assert torch.equal(grads[0], grads[1])
+    assert torch.allclose(grads[2], 3.0 * grads[0], rtol=1e-6, atol=0)
+    assert float(pp.unit_upstream(out.device)) == 1.0
+
+
 # --------------------------------------------------------------------------- encode-inside-loss (one pass, 2 H W e bytes)
 @pytest.mark.parametrize("cid,batch,dtype,grid", [(2, 6, "fp32", 0), (2, 6, "fp32", 3), (3, 5, "bf16", 0), (4, 3, "fp32", 2),
                                                  (5, 1, "fp32", 4), (1, 4, "fp32", 0)])
