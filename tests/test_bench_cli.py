@@ -1,0 +1,33 @@
+"""bench.py on a box without a GPU: the reference arm runs (CPU oracle port, bounded sample) and prints the contract's
+JSON line; the product arm refuses to run -- there is no CPU fallback."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _run(*args):
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    return subprocess.run([sys.executable, str(ROOT / "bench.py"), *args], capture_output=True, text=True, timeout=600, env=env)
+
+
+def test_reference_arm_prints_the_contract_line():
+    res = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--sample", "2")
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "heatmaps/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    e2e = line["e2e"]
+    assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_product_arm_refuses_to_run_without_a_gpu():
+    res = _run("--steps", "1", "--warmup", "1")
+    assert res.returncode != 0
+    assert "no CPU fallback" in res.stderr
