@@ -31,3 +31,16 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     res = _run("--steps", "1", "--warmup", "1")
     assert res.returncode != 0
     assert "no CPU fallback" in res.stderr
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """Launched like the driver launches N > 1 (torch.distributed.run, one process per GPU): rank 0 alone runs the CPU
+    arm and prints the line, the other ranks exit 0 without work."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+           "--sample", "2"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["value"] > 0

@@ -121,3 +121,23 @@ def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
     from probpose_pytorch_b200 import _lib
     import ctypes
     assert f"sizeof mailbox: {ctypes.sizeof(_lib.Mailbox)}" in res.stdout      # the ctypes mirror has the C layout
+
+
+def test_loss_out_and_unit_upstream_argument_checks():
+    """Host-side argument handling of the small-step helpers (no GPU needed): `loss_out` must be a one-element float32
+    tensor on the prediction's device; `unit_upstream` hands out one cached scalar 1 per (device, dtype)."""
+    import pytest
+    import torch
+    from probpose_pytorch_b200 import unit_upstream
+    from probpose_pytorch_b200.loss import _check_loss_out, _is_unit_upstream
+    out = torch.zeros(2, 3, 4, 4)
+    assert _check_loss_out(None, out) is None
+    assert _check_loss_out(torch.zeros(1), out).shape == (1,)
+    assert _check_loss_out(torch.zeros(()), out).shape == (1,)
+    for bad in (torch.zeros(2), torch.zeros(1, dtype=torch.float64)):
+        with pytest.raises(ValueError):
+            _check_loss_out(bad, out)
+    one = unit_upstream("cpu")
+    assert one is unit_upstream(torch.device("cpu")) and float(one) == 1.0 and one.dim() == 0
+    assert _is_unit_upstream(one) and _is_unit_upstream(one.reshape(1))
+    assert not _is_unit_upstream(torch.ones(())) and not _is_unit_upstream(one.clone())
